@@ -1,0 +1,120 @@
+/* laplace_b200 -- C ABI of the B200-native curvature hot path for the Laplace library.
+ *
+ * Drop-in boundary: the reference's curvature backends are Python classes deriving from
+ * laplace.curvature.CurvatureInterface (reference laplace/curvature/curvature.py:12-291).  The
+ * per-batch arithmetic those classes perform is what this library replaces; the Python subclass
+ * `laplace_b200.B200GGN / B200EF` binds these entry points through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current device unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all calls are asynchronous on `stream`; nothing is allocated or freed by the library
+ *     except where a `workspace` argument is documented; buffers are owned by the caller;
+ *   - return value 0 = success, non-zero = failure with a message in lpb_last_error()
+ *     (thread-local).  The Python wrapper raises RuntimeError (reference error convention:
+ *     Python exceptions only);
+ *   - "K-major operand": matrix X[rows, ld] with the contraction index k contiguous
+ *     (element (j, k) at X[j*ld + k]).  The pack entry points produce this layout.
+ *   - bf16 buffers are passed as void* (uint16 storage).  out_kind: 0 = fp32, 1 = bf16,
+ *     2 = bf16 hi + bf16 lo (error-compensated split: x ~= hi + lo, |x - hi - lo| <= 2^-17 |x|).
+ */
+#ifndef LAPLACE_B200_H_
+#define LAPLACE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPB_OUT_F32 0
+#define LPB_OUT_BF16 1
+#define LPB_OUT_BF16_HILO 2
+#define LPB_PACK_SQUARE 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int lpb_version(void);
+const char* lpb_last_error(void);
+/* sm count / compute capability of the current device */
+int lpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- pack: layer inputs / output gradients -> K-major staging ----------------------------
+ * Front end of the KFAC factor contractions that curvlinops performs as einsum("b i,b j->i j")
+ * behind reference laplace/curvature/curvlinops.py:100 (linop._compute_kfac()).              */
+
+/* src [rows, cols] fp32 row-major (ld_src)  ->  dst[(z*cols + j), k0 + k] = f(scale*src[k, j]) * row_scale[z*rows + k]
+ * (f = square if flags & LPB_PACK_SQUARE; row_scale may be NULL when nrep == 1).            */
+int lpb_pack_rows_t(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* row_scale, int nrep,
+                    float scale, int flags, void* dst_hi, void* dst_lo, int out_kind, int64_t ldk, int64_t k0,
+                    void* stream);
+
+/* x [N, C, H, W] fp32 -> unfolded patches dst[(ci,kh,kw), k0 + (n,oh,ow)] (the rows KFAC-expand
+ * uses for nn.Conv2d); reduce_mean != 0: KFAC-reduce rows dst[(ci,kh,kw), k0 + n] = mean over (oh,ow). */
+int lpb_pack_conv2d_t(const float* x, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int DH,
+                      int DW, float scale, int flags, int reduce_mean, void* dst_hi, void* dst_lo, int out_kind,
+                      int64_t ldk, int64_t k0, void* stream);
+
+/* g [Nn, Cc, HW] fp32 (NCHW gradient of a conv output) -> dst[ch, k0 + n*HW + hw];
+ * reduce_sum != 0: dst[ch, k0 + n] = sum_hw (KFAC-reduce).                                    */
+int lpb_pack_nchw_t(const float* g, int64_t Nn, int Cc, int HW, float scale, int flags, int reduce_sum, void* dst_hi,
+                    void* dst_lo, int out_kind, int64_t ldk, int64_t k0, void* stream);
+
+/* ---- contractions ------------------------------------------------------------------------
+ * D[M, N] (fp32, ldd)  (+)=  alpha * A[M, K] * B[N, K]^T   on K-major operands.
+ * symmetric != 0 (requires A == B, M == N): SYRK -- only tiles on/above the diagonal are
+ * computed and mirrored.  accumulate == 0 overwrites D.
+ * Replaces: KFAC factor einsums (curvlinops.py:100), full GGN einsum "bcp,bck,bkq->pq"
+ * (curvature.py:406/408), EF einsum "bp,bq->pq" (curvature.py:492), the eigenbasis rotations of
+ * KronDecomposed._bmm (utils/matrix.py:447-450) and J Sigma J^T (baselaplace.py:1683-1684).  */
+
+/* exact fp32 SIMT path */
+int lpb_gemm_nt_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                    float alpha, int accumulate, float* D, int64_t ldd, int symmetric, void* stream);
+
+/* tcgen05 tensor-core path: bf16 operands (TMA -> smem -> tcgen05.mma, fp32 accumulation in TMEM).
+ * A_lo/B_lo non-NULL: error-compensated 3-product mode hi*hi + hi*lo + lo*hi.
+ * Requirements: lda, ldb multiples of 8 elements, operand base pointers 16-byte aligned.      */
+int lpb_gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                     int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd,
+                     int symmetric, void* stream);
+
+/* ---- weight-sharing layers: per-sample layer Jacobians ------------------------------------
+ * P_q[i,j] = sum_t G[i, q*T+t] * A[j, (q % Nn)*T + t], q = c*Nn + n over ncols back-propagated columns.
+ * mode 0: out[i*out_ld + j] += scale * sum_q P_q[i,j]^2      (diag GGN / EF, curvature.py:429-431, :504)
+ * mode 1: Js[n*js_stride_n + c*js_stride_c + i*d_in + j] = P_q[i,j]   (Jacobian rows, curvature.py:115-124) */
+int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const float* A, int64_t lda, int d_out, int d_in,
+                               int T, int Nn, int ncols, float scale, float* out, int64_t out_ld, int64_t js_stride_n,
+                               int64_t js_stride_c, void* stream);
+
+/* ---- Jacobian writers (reference CurvatureInterface.jacobians / last_layer_jacobians) ----- */
+/* no weight sharing: Js[n,c, off_w + i*d_in + j] = g[c,n,i]*a[n,j]; Js[n,c, off_b + i] = g[c,n,i]
+ * (off_w / off_b < 0: skip that block).  g [C, Nn, d_out], a [Nn, d_in].                      */
+int lpb_jac_linear_write(const float* g, const float* a, int Nn, int C, int d_out, int d_in, float* Js,
+                         int64_t js_stride_n, int64_t js_stride_c, int64_t off_w, int64_t off_b, void* stream);
+/* J_n = [I_C (x) phi_n^T, I_C] (curvature.py:157-165); Js [Nn, C, C*D (+C)] contiguous.        */
+int lpb_ll_jacobian_write(const float* phi, int Nn, int C, int D, int has_bias, float* Js, void* stream);
+
+/* ---- batched pair reductions (epilogues of the predictive quadratic forms) -----------------
+ * out[n, c, k] (+)= sum_i X[n*x_stride_n + c*x_stride_c + i] * Z[n*z_stride_n + k*z_stride_c + i] * (m ? m[n*m_stride + i] : 1)
+ * Replaces torch.bmm(W, SW^T) in KronDecomposed.inv_square_form (utils/matrix.py:458-461).     */
+int lpb_batched_pair_dot(const float* X, const float* Z, const float* m, int64_t m_stride, int Nn, int CX, int CZ, int d,
+                         int64_t x_stride_n, int64_t x_stride_c, int64_t z_stride_n, int64_t z_stride_c, int accumulate,
+                         float* out, void* stream);
+
+/* ---- last-layer full GGN (structured form of curvature.py:398-408 with last_layer=True) ---- */
+/* G [Dt, C(C+1)/2, Dt] (Dt = D + has_bias) -> H [P, P], P = C*D (+C), ordering [vec(W) row-major; b] */
+int lpb_ll_ggn_expand(const float* G, int C, int D, int has_bias, int accumulate, float* H, void* stream);
+/* Sigma [P, P] -> Sg [C*C, Dt, Dt] with Sg[(c,k), et, dt] = Sigma[idx(c,dt), idx(k,et)]         */
+int lpb_ll_sigma_gather(const float* Sigma, int C, int D, int has_bias, float* Sg, void* stream);
+
+/* ---- symmetric eigendecomposition (reference Kron.decompose -> symeig, utils/utils.py:193-228)
+ * Batched cyclic one-sided Jacobi for n <= LPB_EIGH_MAX_N; A [batch, n, n] fp32 symmetric (upper
+ * triangle read) -> eigenvalues ascending, clamped at 0, NaN -> 0; eigenvectors in columns of Q.
+ * Returns non-zero (with message) when n exceeds the limit.                                     */
+#define LPB_EIGH_MAX_N 128
+int lpb_eigh_jacobi(const float* A, int batch, int n, float* evals, float* Q, int max_sweeps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAPLACE_B200_H_ */

@@ -1,0 +1,74 @@
+"""ctypes binding of ``liblaplace_b200.so`` (C ABI declared in ``include/laplace_b200.h``).
+
+The product path has no fallback: if the shared library is missing or a call fails the
+wrapper raises (``RuntimeError``), mirroring the reference's "Python exceptions only" error
+convention.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblaplace_b200.so")
+
+c_i64, c_int, c_f32, c_vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+# name -> argtypes ; every entry point of include/laplace_b200.h returning int
+SIGNATURES = {
+    "lpb_device_info": [C.POINTER(c_int)] * 3,
+    "lpb_pack_rows_t": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
+    "lpb_pack_conv2d_t": [c_vp] + [c_int] * 12 + [c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
+    "lpb_pack_nchw_t": [c_vp, c_i64, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
+    "lpb_gemm_nt_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_vp],
+    "lpb_gemm_nt_bf16": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int,
+                         c_vp],
+    "lpb_shared_weight_contract": [c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp,
+                                   c_i64, c_i64, c_i64, c_vp],
+    "lpb_jac_linear_write": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
+    "lpb_ll_jacobian_write": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "lpb_batched_pair_dot": [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_int, c_vp,
+                             c_vp],
+    "lpb_ll_ggn_expand": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
+    "lpb_ll_sigma_gather": [c_vp, c_int, c_int, c_int, c_vp, c_vp],
+    "lpb_eigh_jacobi": [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp],
+}
+EXPORTS = ["lpb_version", "lpb_last_error"] + list(SIGNATURES)
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the native library (once).  Raises ``NativeLibraryError`` when it is absent --
+    there is deliberately no Python/torch fallback for the kernels."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `bash laplace_b200/csrc/build.sh` (needs nvcc, sm_100a)."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.lpb_version.restype = c_int
+    lib.lpb_version.argtypes = []
+    lib.lpb_last_error.restype = C.c_char_p
+    lib.lpb_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.lpb_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{name} failed: {msg}")

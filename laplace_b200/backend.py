@@ -1,0 +1,597 @@
+"""``B200GGN`` / ``B200EF`` -- curvature backends for the Laplace library whose per-batch hot path
+runs on hand-written sm_100a kernels (``liblaplace_b200.so``).
+
+Plug-in surface = reference ``laplace.curvature.CurvatureInterface`` (curvature/curvature.py:12-291):
+``jacobians``, ``last_layer_jacobians``, ``gradients``, ``full``, ``kron``, ``diag``.  Semantics of every
+method follow the reference's default backend, the curvlinops adapter (curvature/curvlinops.py:46-188)
+for ``kron`` and the in-tree GGN/EF (curvature/curvature.py:375-505) for ``full`` / ``diag``.
+
+How a batch is processed:
+
+1. one forward pass of the model with hooks on every ``nn.Linear`` / ``nn.Conv2d`` that owns a trainable
+   parameter captures the layer input ``a`` and the layer output tensor;
+2. one *batched* reverse pass (``autograd.grad(..., is_grads_batched=True)``) propagates the ``ncols``
+   columns that define the curvature (C columns of the loss-Hessian square root for the GGN, the
+   loss gradient for the EF, sampled gradients for the MC Fisher) down to every captured layer
+   output -- this is the network's own forward/backward (cuDNN/cuBLAS through autograd) and is *below*
+   the plug-in boundary, exactly as in the reference;
+3. everything above it -- packing ``a`` / ``g`` into K-major bf16 (hi/lo) or fp32 staging, the
+   ``X^T X`` factor contractions, diagonal reductions, Jacobian materialisation, the last-layer
+   structured GGN -- runs in the native kernels.
+"""
+from __future__ import annotations
+
+import math
+from collections.abc import MutableMapping
+from typing import Any
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from .interface import CurvatureInterface, EFInterface, GGNInterface
+from .matrix import B200Kron, JacobianFactors
+
+SUPPORTED = (nn.Linear, nn.Conv2d)
+PRECISIONS = ("auto", "fp32", "bf16", "bf16x3")
+
+
+class _Layer:
+    __slots__ = ("name", "mod", "has_w", "has_b", "d_in", "d_out", "is_conv")
+
+    def __init__(self, name, mod, has_w, has_b):
+        self.name, self.mod, self.has_w, self.has_b = name, mod, has_w, has_b
+        self.is_conv = isinstance(mod, nn.Conv2d)
+        if self.is_conv:
+            if mod.groups != 1:
+                raise ValueError(f"{name}: grouped convolutions are not supported by the B200 backend")
+            if isinstance(mod.padding, str) or mod.padding_mode != "zeros":
+                raise ValueError(f"{name}: only zero padding given as ints is supported")
+            self.d_in = mod.in_channels * mod.kernel_size[0] * mod.kernel_size[1]
+            self.d_out = mod.out_channels
+        else:
+            self.d_in, self.d_out = mod.in_features, mod.out_features
+
+
+class _B200Mixin:
+    """Shared machinery of the GGN and EF flavours."""
+
+    def _b200_init(self, precision: str = "auto", batched_backward: bool = True):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.precision = precision
+        self.batched_backward = batched_backward
+        self._layers: list[_Layer] | None = None
+        self._unsupported: list[str] = []
+        self._hooks = []
+        self._capturing = False
+        self._acts: dict[str, torch.Tensor] = {}
+        self._outs: dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ layer plan
+    def _plan(self) -> list[_Layer]:
+        """Layers in ``named_modules()`` order that own parameters of ``self.params`` (the walk order of
+        ``CurvlinopsInterface._get_kron_factors``, curvature/curvlinops.py:55-75)."""
+        if self._layers is not None:
+            return self._layers
+        ids = {id(p) for p in self.params}
+        layers, unsupported, covered = [], [], set()
+        for name, mod in self.model.named_modules():
+            own = [p for p in mod.parameters(recurse=False) if id(p) in ids]
+            if not own:
+                continue
+            if isinstance(mod, SUPPORTED):
+                has_w = id(mod.weight) in ids
+                has_b = mod.bias is not None and id(mod.bias) in ids
+                layers.append(_Layer(name, mod, has_w, has_b))
+                covered.update(id(p) for p in own)
+            else:
+                unsupported.append(f"{name} ({type(mod).__name__})")
+        order = {id(p): i for i, p in enumerate(self.params)}
+        pos = []
+        for L in layers:
+            if L.has_w:
+                pos.append(order[id(L.mod.weight)])
+            if L.has_b:
+                pos.append(order[id(L.mod.bias)])
+        if pos != sorted(pos) or len(set(pos)) != len(pos):
+            raise ValueError("module order and parameters() order disagree (shared or re-used parameters?)")
+        self._layers, self._unsupported = layers, unsupported
+        for L in layers:
+            self._hooks.append(L.mod.register_forward_hook(self._make_hook(L.name)))
+        return layers
+
+    def _require_supported(self, what: str):
+        self._plan()
+        if self._unsupported:
+            raise ValueError(
+                f"B200 backend: {what} supports trainable parameters in nn.Linear / nn.Conv2d only; found "
+                + ", ".join(self._unsupported) + ". Freeze them (requires_grad=False) as for the reference KFAC path."
+            )
+
+    def _make_hook(self, name):
+        def hook(mod, inp, out):
+            if self._capturing:
+                self._acts[name] = inp[0].detach()
+                self._outs[name] = out
+        return hook
+
+    # ------------------------------------------------------------------ forward / backward
+    def _device_check(self, t: torch.Tensor):
+        if not t.is_cuda:
+            raise RuntimeError("the B200 curvature backend runs on CUDA only (model/input on %s); there is no "
+                               "CPU fallback" % t.device)
+
+    def _forward(self, x):
+        self._plan()
+        self._acts, self._outs = {}, {}
+        self._capturing = True
+        try:
+            with torch.enable_grad():
+                f = self.model(x)
+        finally:
+            self._capturing = False
+        if f.ndim != 2:
+            raise ValueError(f"the B200 backend supports (batch, outputs) model outputs, got shape {tuple(f.shape)}")
+        self._device_check(f)
+        return f
+
+    def _backward(self, f: torch.Tensor, cols: torch.Tensor) -> list[torch.Tensor]:
+        """Gradients of ``sum_n <cols[j, n], f[n]>`` w.r.t. every captured layer output, for all ``j`` at once.
+        Returns one fp32 tensor ``[ncols, M, ...]`` per planned layer."""
+        outs = [self._outs[L.name] for L in self._layers]
+        cols = cols.to(f.dtype)
+        grads = None
+        if self.batched_backward and cols.shape[0] > 1:
+            try:
+                grads = torch.autograd.grad(f, outs, grad_outputs=cols, is_grads_batched=True, retain_graph=True,
+                                            allow_unused=True)
+            except (RuntimeError, NotImplementedError):
+                grads = None  # an op without a batching rule: fall back to one reverse pass per column
+        if grads is None:
+            per = []
+            for j in range(cols.shape[0]):
+                per.append(torch.autograd.grad(f, outs, grad_outputs=cols[j], retain_graph=j + 1 < cols.shape[0],
+                                               allow_unused=True))
+            grads = [None if per[0][i] is None else torch.stack([p[i] for p in per]) for i in range(len(outs))]
+        res = []
+        for L, g, o in zip(self._layers, grads, outs):
+            if g is None:
+                g = torch.zeros((cols.shape[0],) + tuple(o.shape), device=o.device, dtype=torch.float32)
+            res.append(g.detach().float().contiguous())
+        self._outs = {}
+        return res
+
+    # ------------------------------------------------------------------ columns that define the curvature
+    def _hessian_sqrt_cols(self, f: torch.Tensor) -> torch.Tensor:
+        """GGN: columns of ``S_n`` with ``S_n S_n^T`` = functional Hessian of the reference
+        (``diag(p) - p p^T`` / identity, curvature/curvature.py:366-373).  Shape ``[C, M, C]``."""
+        M, C = f.shape
+        if self.likelihood == "regression":
+            return torch.eye(C, device=f.device, dtype=f.dtype).unsqueeze(1).expand(C, M, C).contiguous()
+        p = torch.softmax(f, dim=-1)
+        sp = p.sqrt()
+        S = torch.diag_embed(sp) - p.unsqueeze(2) * sp.unsqueeze(1)   # [M, C(row), C(col)]
+        return S.permute(2, 0, 1).contiguous()
+
+    def _mc_cols(self, f: torch.Tensor, n_samples: int) -> torch.Tensor:
+        """MC Fisher (``_get_mc_functional_fisher``, curvature/curvature.py:341-364): ``n_samples`` sampled
+        functional gradients scaled by ``1/sqrt(n_samples)``.  Shape ``[n_samples, M, C]``."""
+        cols = []
+        for _ in range(n_samples):
+            if self.likelihood == "regression":
+                cols.append(-torch.randn_like(f))
+            else:
+                p = torch.softmax(f, dim=-1)
+                ys = torch.multinomial(p, 1).squeeze(1)
+                cols.append(p - torch.nn.functional.one_hot(ys, f.shape[-1]).to(f.dtype))
+        return torch.stack(cols) / math.sqrt(n_samples)
+
+    def _loss_grad_cols(self, f: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """d(sum-reduced torch loss)/df: ``p - onehot(y)`` (CE) / ``2 (f - y)`` (MSE).  Shape ``[1, M, C]``."""
+        if self.likelihood == "regression":
+            return (2.0 * (f - y)).unsqueeze(0)
+        p = torch.softmax(f, dim=-1)
+        return (p - torch.nn.functional.one_hot(y, f.shape[-1]).to(f.dtype)).unsqueeze(0)
+
+    # ------------------------------------------------------------------ precision policy
+    def _kind(self, d: int, k: int) -> int:
+        """Operand format of one contraction with output dim ``d`` and reduction length ``k``."""
+        if self.precision == "fp32":
+            return K.F32
+        if self.precision == "bf16":
+            return K.BF16
+        if self.precision == "bf16x3":
+            return K.BF16X3
+        return K.BF16X3 if (d >= 64 and k >= 256) else K.F32
+
+    # ------------------------------------------------------------------ per-layer operand packing
+    def _pack_act(self, L: _Layer, a: torch.Tensor, kind: int, reduce: bool = False):
+        """K-major layer-input rows ``[d_in, M*T]`` (expand) / ``[d_in, M]`` (reduce).  Returns (packed, T)."""
+        a = a.float() if a.dtype != torch.float32 else a
+        if L.is_conv:
+            return K.pack_conv(a, L.mod, kind, reduce_mean=reduce)
+        M = a.shape[0]
+        rows = a.reshape(M, -1, a.shape[-1])
+        T = rows.shape[1]
+        if reduce and T > 1:
+            rows = rows.mean(1, keepdim=True)
+        rows = rows.reshape(-1, a.shape[-1]).contiguous()
+        return K.pack_rows(rows, kind), T
+
+    def _pack_grad(self, L: _Layer, g: torch.Tensor, kind: int, reduce: bool = False):
+        """K-major output-gradient rows ``[d_out, ncols*M*T]`` (column-major over ``(col, n, t)``)."""
+        if L.is_conv:
+            nc, M, Co, OH, OW = g.shape
+            return K.pack_nchw(g.reshape(nc * M, Co, OH * OW), kind, reduce_sum=reduce)
+        nc, M = g.shape[:2]
+        rows = g.reshape(nc * M, -1, g.shape[-1])
+        if reduce and rows.shape[1] > 1:
+            rows = rows.sum(1, keepdim=True)
+        return K.pack_rows(rows.reshape(-1, g.shape[-1]).contiguous(), kind)
+
+    # ------------------------------------------------------------------ KFAC
+    def _kron_impl(self, x, y, N, cols_fn, weight: float, kfac_approx: str = "expand"):
+        if kfac_approx not in ("expand", "reduce"):
+            raise ValueError(f"kfac_approx must be 'expand' or 'reduce', got {kfac_approx!r}")
+        self._require_supported("kron()")
+        reduce = kfac_approx == "reduce"
+        f = self._forward(x)
+        fd = f.detach()
+        M = fd.shape[0]
+        y = y.to(fd.device)
+        loss = self.factor * self.lossfunc(fd, y)
+        cols = cols_fn(fd, y)
+        acts = self._acts
+        grads = self._backward(f, cols)
+        self._acts = {}
+        dims = []
+        for L in self._layers:
+            if L.has_w:
+                dims.append([L.d_out, L.d_in])
+            if L.has_b:
+                dims.append([L.d_out])
+        kron = B200Kron.zeros(dims, fd.device, torch.float32)
+        sq = math.sqrt(self.factor)
+        idx = 0
+        for L, g in zip(self._layers, grads):
+            a = acts[L.name]
+            ncols = g.shape[0]
+            gk = self._kind(L.d_out, g.numel() // L.d_out)
+            G = self._pack_grad(L, g, gk, reduce)
+            if L.has_w:
+                Bf, Af = kron.kfacs[idx]
+                k_rows = (g.numel() // (ncols * L.d_out)) if L.is_conv else (a.numel() // a.shape[-1])
+                ak = self._kind(L.d_in, M if reduce else k_rows)
+                A, T = self._pack_act(L, a, ak, reduce)
+                Teff = 1 if reduce else T
+                # A = factor^(1/2) * (M/N) * 1/(M*T) * sum a a^T   (curvlinops.py:46-53, matrix.py:116-118)
+                K.gemm_nt(A, A, Af, alpha=sq / (N * Teff), accumulate=True, symmetric=True)
+                K.gemm_nt(G, G, Bf, alpha=sq * weight, accumulate=True, symmetric=True)
+                idx += 1
+                if L.has_b:
+                    kron.kfacs[idx][0].copy_(Bf).mul_(sq)  # bias block: factor * B   (len(F) == 1)
+                    idx += 1
+            elif L.has_b:
+                K.gemm_nt(G, G, kron.kfacs[idx][0], alpha=self.factor * weight, accumulate=True, symmetric=True)
+                idx += 1
+        dtype = next(self.model.parameters()).dtype
+        if dtype != torch.float32:
+            kron = B200Kron([[H.to(dtype) for H in F] for F in kron.kfacs])
+        return loss.detach(), kron
+
+    # ------------------------------------------------------------------ Jacobian rows (dense) + factors
+    def _rows(self, x, cols_fn, y=None, n_major: bool = False, want_factors: bool = False):
+        """Dense rows ``Z[(col, n), :] = sum_c cols[col, n, c] * d f_c(x_n)/d theta`` for all trainable params
+        (``parameters()`` order, row-major flattening; curvature/curvature.py:115-124).
+        Returns ``(Z [ncols, M, P] or [M, ncols, P] if n_major, f, factors)``."""
+        self._require_supported("jacobians()/full()/diag()")
+        f = self._forward(x)
+        fd = f.detach()
+        M, C = fd.shape
+        cols = cols_fn(fd, y)
+        ncols = cols.shape[0]
+        acts = self._acts
+        grads = self._backward(f, cols)
+        self._acts = {}
+        sizes = []
+        for L in self._layers:
+            if L.has_w:
+                sizes.append(L.d_out * L.d_in)
+            if L.has_b:
+                sizes.append(L.d_out)
+        P = sum(sizes)
+        Z = torch.empty((M, ncols, P) if n_major else (ncols, M, P), device=fd.device, dtype=torch.float32)
+        sn, sc = (ncols * P, P) if n_major else (P, M * P)
+        blocks, off = [], 0
+        for L, g in zip(self._layers, grads):
+            a = acts[L.name]
+            a = a.float() if a.dtype != torch.float32 else a
+            shared = L.is_conv or a.dim() > 2
+            off_w = off if L.has_w else -1
+            off_b = (off + (L.d_out * L.d_in if L.has_w else 0)) if L.has_b else -1
+            if not shared:
+                K.jac_linear_write(g, a.contiguous(), Z, sn, sc, off_w, off_b)
+                if L.has_w:
+                    blocks.append(("outer", g, a.contiguous()))
+                if L.has_b:
+                    blocks.append(("vec", g))
+            else:
+                if L.has_w:
+                    A, T = self._pack_act(L, a, K.F32)
+                    G = self._pack_grad(L, g, K.F32)
+                    K.shared_weight_contract(1, G, A, L.d_out, L.d_in, T, M, ncols, Z[..., off_w:], js_stride_n=sn,
+                                             js_stride_c=sc)
+                    if want_factors:
+                        blocks.append(("dense", None))
+                if L.has_b:
+                    gb = g.reshape(ncols, M, L.d_out, -1).sum(-1) if L.is_conv else g.reshape(ncols, M, -1, L.d_out).sum(2)
+                    gb = gb.contiguous()
+                    dummy = torch.zeros(M, 1, device=fd.device, dtype=torch.float32)
+                    K.jac_linear_write(gb, dummy, Z, sn, sc, -1, off_b)
+                    if want_factors:
+                        blocks.append(("vec", gb))
+            off += (L.d_out * L.d_in if L.has_w else 0) + (L.d_out if L.has_b else 0)
+        factors = None
+        if want_factors and n_major:
+            # fill dense blocks with views of the materialised rows
+            fixed, o = [], 0
+            for blk, p in zip(blocks, sizes):
+                fixed.append(("dense", Z[:, :, o:o + p].contiguous()) if blk[0] == "dense" else blk)
+                o += p
+            factors = JacobianFactors(fixed, M, ncols, sizes)
+        return Z, fd, factors
+
+    def _identity_cols(self, f, y=None):
+        M, C = f.shape
+        return torch.eye(C, device=f.device, dtype=f.dtype).unsqueeze(1).expand(C, M, C).contiguous()
+
+    # ------------------------------------------------------------------ public: jacobians
+    def jacobians(self, x, enable_backprop: bool = False):
+        """``CurvatureInterface.jacobians`` (curvature/curvature.py:88-129): ``Js (B, C, P)``, ``f (B, C)``."""
+        if enable_backprop:
+            return self._reference_fallback("jacobians", x, enable_backprop=True)
+        Z, f, factors = self._rows(x, self._identity_cols, n_major=True, want_factors=self.subnetwork_indices is None)
+        dtype = next(self.model.parameters()).dtype
+        Js = Z.to(dtype)
+        if self.subnetwork_indices is not None:
+            Js = Js[:, :, self.subnetwork_indices]
+        elif factors is not None and dtype == torch.float32:
+            Js._lpb_factors = factors
+        return Js, f.to(dtype)
+
+    functorch_jacobians = jacobians
+
+    def last_layer_jacobians(self, x, enable_backprop: bool = False):
+        """``CurvatureInterface.last_layer_jacobians`` (curvature/curvature.py:131-167)."""
+        if enable_backprop:
+            return self._reference_fallback("last_layer_jacobians", x, enable_backprop=True)
+        with torch.no_grad():
+            f, phi = self.model.forward_with_features(x)
+        self._device_check(f)
+        C = int(f.numel() / phi.shape[0])
+        has_bias = self.model.last_layer.bias is not None
+        Js = K.ll_jacobian_write(phi.detach().float(), C, has_bias)
+        dtype = next(self.model.parameters()).dtype
+        Js = Js.to(dtype)
+        Js._lpb_ll = (phi.detach().float().contiguous(), C, has_bias)
+        return Js, f.detach()
+
+    def gradients(self, x, y):
+        """``CurvatureInterface.gradients`` (curvature/curvature.py:169-210): per-sample loss gradients ``(B, P)``."""
+        y = y.to(next(self.model.parameters()).device)
+        Z, f, _ = self._rows(x, self._loss_grad_cols, y=y)
+        Gs = Z[0]
+        if self.subnetwork_indices is not None:
+            Gs = Gs[:, self.subnetwork_indices]
+        dtype = next(self.model.parameters()).dtype
+        return Gs.to(dtype), self.lossfunc(f, y).detach()
+
+    def _reference_fallback(self, name, *args, **kwargs):
+        from .interface import HAVE_REFERENCE
+
+        if not HAVE_REFERENCE:
+            raise NotImplementedError(f"{name} with enable_backprop=True needs the reference's torch.func path "
+                                      "(the B200 kernels are not differentiable)")
+        return getattr(CurvatureInterface, name)(self, *args, **kwargs)
+
+    # ------------------------------------------------------------------ dense SYRK of rows
+    def _rows_syrk(self, Z2d: torch.Tensor, alpha: float) -> torch.Tensor:
+        Kr, P = Z2d.shape
+        H = torch.zeros(P, P, device=Z2d.device, dtype=torch.float32)
+        Zt = K.pack_rows(Z2d, self._kind(P, Kr))
+        K.gemm_nt(Zt, Zt, H, alpha=alpha, accumulate=True, symmetric=True)
+        return H
+
+    # ------------------------------------------------------------------ last-layer structured curvature
+    def _ll_forward(self, x):
+        with torch.no_grad():
+            f, phi = self.model.forward_with_features(x)
+        self._device_check(f)
+        if f.ndim != 2 or phi.ndim != 2:
+            raise ValueError("last-layer curvature needs (batch, outputs) logits and (batch, features) features")
+        return f.detach(), phi.detach().float().contiguous()
+
+    def _ll_full(self, phi: torch.Tensor, Lam: torch.Tensor, scale: float) -> torch.Tensor:
+        """``sum_n Lam_n (x) [phi;1][phi;1]^T`` in the reference's last-layer ordering ``[vec(W); b]``
+        (structured form of curvature/curvature.py:398-408 with last_layer=True)."""
+        M, D = phi.shape
+        C = Lam.shape[1]
+        has_bias = self.model.last_layer.bias is not None
+        phit = torch.cat([phi, torch.ones(M, 1, device=phi.device)], 1).contiguous() if has_bias else phi
+        Dt = phit.shape[1]
+        iu = torch.triu_indices(C, C, device=phi.device)
+        w = Lam[:, iu[0], iu[1]].t().contiguous().float()            # [npairs, M]
+        npairs = w.shape[0]
+        kind = self._kind(Dt, M)
+        A = K.pack_rows(phit, kind)
+        Bw = K.pack_rows(phit, kind, row_scale=w.reshape(-1), nrep=npairs)
+        G = torch.zeros(Dt, npairs * Dt, device=phi.device, dtype=torch.float32)
+        K.gemm_nt(A, Bw, G, alpha=scale, accumulate=True)
+        P = C * D + (C if has_bias else 0)
+        H = torch.empty(P, P, device=phi.device, dtype=torch.float32)
+        K.ll_ggn_expand(G, C, D, has_bias, H, accumulate=False)
+        return H
+
+    def _ll_diag(self, phi: torch.Tensor, lam_diag: torch.Tensor, scale: float) -> torch.Tensor:
+        """diag of the above: ``sum_n Lam_n[c,c] * [phi;1]^2`` -> ``[C*D (+C)]``."""
+        has_bias = self.model.last_layer.bias is not None
+        M = phi.shape[0]
+        phit = torch.cat([phi, torch.ones(M, 1, device=phi.device)], 1).contiguous() if has_bias else phi
+        lam_diag = lam_diag.float().contiguous()                       # [C, M] is already K-major
+        A = K.Packed(lam_diag, None, K.F32, lam_diag.shape[0], lam_diag.shape[1])
+        Bq = K.pack_rows(phit, K.F32, square=True)                     # [Dt, M]
+        out = torch.zeros(lam_diag.shape[0], phit.shape[1], device=phi.device, dtype=torch.float32)
+        K.gemm_nt(A, Bq, out, alpha=scale, accumulate=True)
+        D = phi.shape[1]
+        return torch.cat([out[:, :D].reshape(-1), out[:, D]]) if has_bias else out.reshape(-1)
+
+    def _out_dtype(self, t: torch.Tensor) -> torch.Tensor:
+        dtype = next(self.model.parameters()).dtype
+        return t if t.dtype == dtype else t.to(dtype)
+
+
+# =========================================================================================
+class B200GGN(_B200Mixin, GGNInterface):
+    """GGN / Fisher curvature on B200 (drop-in for ``CurvlinopsGGN``, curvature/curvlinops.py:144-168).
+
+    Parameters beyond the reference's: ``precision`` in {"auto", "fp32", "bf16", "bf16x3"} selects the
+    operand format of the tensor-core contractions (fp32 accumulation always); ``batched_backward=False``
+    falls back to one reverse pass per column for models with ops that lack a vmap rule.
+    """
+
+    def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
+                 dict_key_y="labels", stochastic=False, num_samples=1, precision="auto", batched_backward=True):
+        GGNInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y,
+                              stochastic, num_samples)
+        self._b200_init(precision, batched_backward)
+
+    def _ggn_cols(self, f, y=None):
+        return self._mc_cols(f, self.num_samples) if self.stochastic else self._hessian_sqrt_cols(f)
+
+    def _functional_hessian(self, f):
+        if self.stochastic:
+            cols = self._mc_cols(f, self.num_samples)               # [S, M, C]
+            return torch.einsum("smc,smk->mck", cols, cols)
+        if self.likelihood == "regression":
+            return torch.eye(f.shape[1], device=f.device, dtype=f.dtype).expand(f.shape[0], -1, -1)
+        p = torch.softmax(f, dim=-1)
+        return torch.diag_embed(p) - p.unsqueeze(2) * p.unsqueeze(1)
+
+    def kron(self, x, y, N, **kwargs: Any):
+        """``CurvlinopsInterface.kron`` (curvature/curvlinops.py:77-108) with ``FisherType.TYPE2`` /
+        ``FisherType.MC`` (:162-164): returns ``(factor * loss, Kron)``."""
+        approx = kwargs.get("kfac_approx", "expand")
+        if self.stochastic:
+            S = int(kwargs.get("mc_samples", 1))
+            sq2 = 2.0 if self.likelihood == "regression" else 1.0   # MSE-sum Hessian is 2 I
+            return self._kron_impl(x, y, N, lambda f, yy: self._mc_cols(f, S) * math.sqrt(S * sq2), 1.0 / S, approx)
+        sq2 = math.sqrt(2.0) if self.likelihood == "regression" else 1.0
+        return self._kron_impl(x, y, N, lambda f, yy: self._hessian_sqrt_cols(f) * sq2, 1.0, approx)
+
+    def full(self, x, y, **kwargs: Any):
+        """``GGNInterface.full`` (curvature/curvature.py:375-411): ``H = sum_n J_n^T L_n J_n``; loss = factor * loss;
+        no ``factor`` on ``H`` (identical in value to ``CurvlinopsGGN.full``, curvlinops.py:110-141)."""
+        if self.last_layer:
+            f, phi = self._ll_forward(x)
+            y = y.to(f.device)
+            H = self._ll_full(phi, self._functional_hessian(f), 1.0)
+            return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(H)
+        y = y.to(next(self.model.parameters()).device)
+        Z, f, _ = self._rows(x, self._ggn_cols)
+        P = Z.shape[-1]
+        Z2 = Z.reshape(-1, P)
+        if self.subnetwork_indices is not None:
+            Z2 = Z2[:, self.subnetwork_indices].contiguous()
+        H = self._rows_syrk(Z2, 1.0)
+        return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(H)
+
+    def diag(self, x, y, **kwargs: Any):
+        """``GGNInterface.diag`` (curvature/curvature.py:413-433)."""
+        if self.last_layer:
+            f, phi = self._ll_forward(x)
+            y = y.to(f.device)
+            lam = torch.diagonal(self._functional_hessian(f), dim1=1, dim2=2).t()   # [C, M]
+            return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(self._ll_diag(phi, lam, 1.0))
+        y = y.to(next(self.model.parameters()).device)
+        loss_f, d = self._diag_impl(x, self._ggn_cols, None, 1.0)
+        if self.subnetwork_indices is not None:
+            d = d[self.subnetwork_indices]
+        return (self.factor * self.lossfunc(loss_f, y)).detach(), self._out_dtype(d)
+
+    # structured diagonal: never materialises (B, C, P)
+    def _diag_impl(self, x, cols_fn, y, scale):
+        self._require_supported("diag()")
+        f = self._forward(x)
+        fd = f.detach()
+        M = fd.shape[0]
+        cols = cols_fn(fd, y)
+        ncols = cols.shape[0]
+        acts = self._acts
+        grads = self._backward(f, cols)
+        self._acts = {}
+        parts = []
+        for L, g in zip(self._layers, grads):
+            a = acts[L.name]
+            a = a.float() if a.dtype != torch.float32 else a
+            shared = L.is_conv or a.dim() > 2
+            if L.has_w:
+                out = torch.zeros(L.d_out, L.d_in, device=fd.device, dtype=torch.float32)
+                if not shared:
+                    # sum_n (sum_col g^2)[n, i] * a[n, j]^2   -- one GEMM on element-wise squares
+                    g2 = K.pack_rows((g * g).sum(0).contiguous(), K.F32)
+                    a2 = K.pack_rows(a.contiguous(), K.F32, square=True)
+                    K.gemm_nt(g2, a2, out, alpha=scale, accumulate=True)
+                else:
+                    A, T = self._pack_act(L, a, K.F32)
+                    G = self._pack_grad(L, g, K.F32)
+                    K.shared_weight_contract(0, G, A, L.d_out, L.d_in, T, M, ncols, out, scale=scale, out_ld=L.d_in)
+                parts.append(out.reshape(-1))
+            if L.has_b:
+                gb = g if not shared else (g.reshape(ncols, M, L.d_out, -1).sum(-1) if L.is_conv
+                                           else g.reshape(ncols, M, -1, L.d_out).sum(2))
+                parts.append(scale * (gb * gb).sum((0, 1)))
+        return fd, torch.cat(parts)
+
+
+class B200EF(_B200Mixin, EFInterface):
+    """Empirical Fisher on B200 (drop-in for ``CurvlinopsEF``, curvature/curvlinops.py:171-180)."""
+
+    def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
+                 dict_key_y="labels", precision="auto", batched_backward=True):
+        EFInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y)
+        self._b200_init(precision, batched_backward)
+
+    def kron(self, x, y, N, **kwargs: Any):
+        """``CurvlinopsInterface.kron`` with ``FisherType.EMPIRICAL`` (curvature/curvlinops.py:174-176)."""
+        return self._kron_impl(x, y, N, self._loss_grad_cols, 1.0, kwargs.get("kfac_approx", "expand"))
+
+    def full(self, x, y, **kwargs: Any):
+        """``EFInterface.full`` (curvature/curvature.py:467-493): ``factor * sum_n g_n g_n^T``."""
+        if self.last_layer:
+            f, phi = self._ll_forward(x)
+            y = y.to(f.device)
+            r = self._loss_grad_cols(f, y)[0]
+            H = self._ll_full(phi, r.unsqueeze(2) * r.unsqueeze(1), self.factor)
+            return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(H)
+        y = y.to(next(self.model.parameters()).device)
+        Z, f, _ = self._rows(x, self._loss_grad_cols, y=y)
+        Z2 = Z[0]
+        if self.subnetwork_indices is not None:
+            Z2 = Z2[:, self.subnetwork_indices].contiguous()
+        H = self._rows_syrk(Z2, self.factor)
+        return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(H)
+
+    def diag(self, x, y, **kwargs: Any):
+        """``EFInterface.diag`` (curvature/curvature.py:495-505): ``factor * sum_n g_n^2``."""
+        if self.last_layer:
+            f, phi = self._ll_forward(x)
+            y = y.to(f.device)
+            r = self._loss_grad_cols(f, y)[0]
+            d = self._ll_diag(phi, (r * r).t().contiguous(), self.factor)
+            return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(d)
+        y = y.to(next(self.model.parameters()).device)
+        f, d = B200GGN._diag_impl(self, x, self._loss_grad_cols, y, self.factor)
+        if self.subnetwork_indices is not None:
+            d = d[self.subnetwork_indices]
+        return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(d)

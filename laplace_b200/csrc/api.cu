@@ -1,0 +1,158 @@
+// C ABI of laplace_b200 (see include/laplace_b200.h for the contract of every entry point).
+#include <stdarg.h>
+
+#include "../../include/laplace_b200.h"
+#include "common.cuh"
+
+namespace lpb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+
+int pack_rows_t(const float*, int64_t, int64_t, int64_t, const float*, int, float, int, void*, void*, int, int64_t,
+                int64_t, cudaStream_t);
+int pack_conv2d_t(const float*, const ConvGeom&, float, int, int, void*, void*, int, int64_t, int64_t, cudaStream_t);
+int pack_nchw_t(const float*, int64_t, int, int, float, int, int, void*, void*, int, int64_t, int64_t, cudaStream_t);
+int gemm_nt_f32(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float, int, float*, int64_t, int,
+                cudaStream_t);
+int gemm_nt_bf16(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
+                 int, float*, int64_t, int, cudaStream_t);
+int shared_weight_contract(int, const float*, int64_t, const float*, int64_t, int, int, int, int, int, float, float*,
+                           int64_t, int64_t, int64_t, cudaStream_t);
+int jac_linear_write(const float*, const float*, int, int, int, int, float*, int64_t, int64_t, int64_t, int64_t,
+                     cudaStream_t);
+int ll_jacobian_write(const float*, int, int, int, int, float*, cudaStream_t);
+int batched_pair_dot(const float*, const float*, const float*, int64_t, int, int, int, int, int64_t, int64_t, int64_t,
+                     int64_t, int, float*, cudaStream_t);
+int ll_ggn_expand(const float*, int, int, int, int, float*, cudaStream_t);
+int ll_sigma_gather(const float*, int, int, int, float*, cudaStream_t);
+int eigh_jacobi(const float*, int, int, float*, float*, int, cudaStream_t);
+
+}  // namespace lpb
+
+using lpb::set_error;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int lpb_version(void) { return 100; }
+
+const char* lpb_last_error(void) { return lpb::get_error(); }
+
+int lpb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  if (lpb::check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+  int sms = 0, maj = 0, min = 0;
+  if (lpb::check_cuda(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "attr sm count")) return 1;
+  if (lpb::check_cuda(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev), "attr cc major")) return 1;
+  if (lpb::check_cuda(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev), "attr cc minor")) return 1;
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  return 0;
+}
+
+int lpb_pack_rows_t(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* row_scale, int nrep,
+                    float scale, int flags, void* dst_hi, void* dst_lo, int out_kind, int64_t ldk, int64_t k0,
+                    void* stream) {
+  LPB_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols, "lpb_pack_rows_t: bad extents");
+  LPB_REQUIRE(k0 >= 0 && k0 + rows <= ldk, "lpb_pack_rows_t: rows [%lld, %lld) exceed ldk=%lld", (long long)k0,
+              (long long)(k0 + rows), (long long)ldk);
+  return lpb::pack_rows_t(src, rows, cols, ld_src, row_scale, nrep, scale, flags, dst_hi, dst_lo, out_kind, ldk, k0,
+                          ST(stream));
+}
+
+int lpb_pack_conv2d_t(const float* x, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int DH,
+                      int DW, float scale, int flags, int reduce_mean, void* dst_hi, void* dst_lo, int out_kind,
+                      int64_t ldk, int64_t k0, void* stream) {
+  LPB_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && SH > 0 && SW > 0 && DH > 0 && DW > 0,
+              "lpb_pack_conv2d_t: bad geometry");
+  lpb::ConvGeom g{N, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW, 0, 0};
+  g.OH = (H + 2 * PH - DH * (KH - 1) - 1) / SH + 1;
+  g.OW = (W + 2 * PW - DW * (KW - 1) - 1) / SW + 1;
+  LPB_REQUIRE(g.OH > 0 && g.OW > 0, "lpb_pack_conv2d_t: empty output");
+  const int64_t K = reduce_mean ? N : (int64_t)N * g.OH * g.OW;
+  LPB_REQUIRE(k0 >= 0 && k0 + K <= ldk, "lpb_pack_conv2d_t: rows exceed ldk");
+  return lpb::pack_conv2d_t(x, g, scale, flags, reduce_mean, dst_hi, dst_lo, out_kind, ldk, k0, ST(stream));
+}
+
+int lpb_pack_nchw_t(const float* g, int64_t Nn, int Cc, int HW, float scale, int flags, int reduce_sum, void* dst_hi,
+                    void* dst_lo, int out_kind, int64_t ldk, int64_t k0, void* stream) {
+  LPB_REQUIRE(Nn >= 0 && Cc > 0 && HW > 0, "lpb_pack_nchw_t: bad extents");
+  const int64_t K = reduce_sum ? Nn : Nn * HW;
+  LPB_REQUIRE(k0 >= 0 && k0 + K <= ldk, "lpb_pack_nchw_t: rows exceed ldk");
+  return lpb::pack_nchw_t(g, Nn, Cc, HW, scale, flags, reduce_sum, dst_hi, dst_lo, out_kind, ldk, k0, ST(stream));
+}
+
+int lpb_gemm_nt_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                    float alpha, int accumulate, float* D, int64_t ldd, int symmetric, void* stream) {
+  LPB_REQUIRE(lda >= K && ldb >= K && ldd >= N, "lpb_gemm_nt_f32: leading dimension too small");
+  return lpb::gemm_nt_f32(A, lda, B, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, ST(stream));
+}
+
+int lpb_gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                     int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd,
+                     int symmetric, void* stream) {
+  LPB_REQUIRE(lda >= K && ldb >= K && ldd >= N, "lpb_gemm_nt_bf16: leading dimension too small");
+  LPB_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "lpb_gemm_nt_bf16: A_lo and B_lo must both be given or both NULL");
+  return lpb::gemm_nt_bf16(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, ST(stream));
+}
+
+int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const float* A, int64_t lda, int d_out, int d_in,
+                               int T, int Nn, int ncols, float scale, float* out, int64_t out_ld, int64_t js_stride_n,
+                               int64_t js_stride_c, void* stream) {
+  LPB_REQUIRE(mode == 0 || mode == 1, "lpb_shared_weight_contract: mode must be 0 or 1");
+  LPB_REQUIRE(T > 0 && ldg >= (int64_t)Nn * ncols * T && lda >= (int64_t)Nn * T, "lpb_shared_weight_contract: bad extents");
+  return lpb::shared_weight_contract(mode, G, ldg, A, lda, d_out, d_in, T, Nn, ncols, scale, out, out_ld, js_stride_n,
+                                     js_stride_c, ST(stream));
+}
+
+int lpb_jac_linear_write(const float* g, const float* a, int Nn, int C, int d_out, int d_in, float* Js,
+                         int64_t js_stride_n, int64_t js_stride_c, int64_t off_w, int64_t off_b, void* stream) {
+  return lpb::jac_linear_write(g, a, Nn, C, d_out, d_in, Js, js_stride_n, js_stride_c, off_w, off_b, ST(stream));
+}
+
+int lpb_ll_jacobian_write(const float* phi, int Nn, int C, int D, int has_bias, float* Js, void* stream) {
+  return lpb::ll_jacobian_write(phi, Nn, C, D, has_bias, Js, ST(stream));
+}
+
+int lpb_batched_pair_dot(const float* X, const float* Z, const float* m, int64_t m_stride, int Nn, int CX, int CZ, int d,
+                         int64_t x_stride_n, int64_t x_stride_c, int64_t z_stride_n, int64_t z_stride_c, int accumulate,
+                         float* out, void* stream) {
+  return lpb::batched_pair_dot(X, Z, m, m_stride, Nn, CX, CZ, d, x_stride_n, x_stride_c, z_stride_n, z_stride_c,
+                               accumulate, out, ST(stream));
+}
+
+int lpb_ll_ggn_expand(const float* G, int C, int D, int has_bias, int accumulate, float* H, void* stream) {
+  return lpb::ll_ggn_expand(G, C, D, has_bias, accumulate, H, ST(stream));
+}
+
+int lpb_ll_sigma_gather(const float* Sigma, int C, int D, int has_bias, float* Sg, void* stream) {
+  return lpb::ll_sigma_gather(Sigma, C, D, has_bias, Sg, ST(stream));
+}
+
+int lpb_eigh_jacobi(const float* A, int batch, int n, float* evals, float* Q, int max_sweeps, void* stream) {
+  return lpb::eigh_jacobi(A, batch, n, evals, Q, max_sweeps, ST(stream));
+}
+
+}  // extern "C"

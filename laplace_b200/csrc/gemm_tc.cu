@@ -1,0 +1,336 @@
+// tcgen05 tensor-core contraction for the factor GEMMs (K1/K2/K3 of SURVEY 2.3):
+//
+//     D[M,N] (fp32) += alpha * A[M,K] * B[N,K]^T        A, B: bf16, K-major
+//
+// B200-native structure (no library GEMM):
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a multi-stage shared
+//     memory ring guarded by full/empty mbarriers;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M=128 x N=128 x K=16) with the
+//     fp32 accumulator resident in TMEM; tcgen05.commit releases ring slots / signals the epilogue;
+//   * 4 epilogue warps read TMEM with tcgen05.ld and add the tile into the accumulated factor
+//     buffer with vector fp32 reductions (split-K CTAs all reduce into the same buffer);
+//   * SYRK mode visits only tiles on/above the diagonal and mirrors them;
+//   * optional error-compensated mode (NPROD = 3): hi*hi + hi*lo + lo*hi with bf16 hi/lo splits,
+//     all three products accumulated in the same TMEM tile (relative product error ~2^-16).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace lpb {
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64;        // BK * 2 B = 128 B = one swizzle row
+constexpr int TILE_BYTES = BM * BK * 2;           // 16 KiB per operand tile
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;                  // warp0 TMA, warp1 MMA/TMEM, warps2-5 epilogue
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// shared-memory matrix descriptor: K-major tile, 128B swizzle, rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address        bits [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset  (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // layout: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int NPROD>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int M, int N,
+                  float alpha, float* __restrict__ D, int64_t ldd, int symmetric, int tiles_m, int tiles_n,
+                  int total_kchunks, int kchunks_per_split, int num_stages) {
+  constexpr int TILES_PER_STAGE = NPROD == 3 ? 4 : 2;
+  constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + num_stages;
+  uint64_t* tmem_full_bar = empty_bar + num_stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  // ---- tile / split decode (uniform per CTA) ----
+  int tm, tn;
+  if (symmetric) {
+    int t = blockIdx.x, r = 0, cnt = tiles_m;
+    while (t >= cnt) { t -= cnt; ++r; --cnt; }
+    tm = r; tn = r + t;
+  } else {
+    tm = blockIdx.x / tiles_n; tn = blockIdx.x % tiles_n;
+  }
+  const int kc_begin = blockIdx.y * kchunks_per_split;
+  const int kc_end = min(total_kchunks, kc_begin + kchunks_per_split);
+  if (kc_begin >= kc_end) return;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        tma_load_2d(&tmA_hi, &full_bar[stage], st, kc * BK, tm * BM);
+        tma_load_2d(&tmB_hi, &full_bar[stage], st + TILE_BYTES, kc * BK, tn * BN);
+        if (NPROD == 3) {
+          tma_load_2d(&tmA_lo, &full_bar[stage], st + 2 * TILE_BYTES, kc * BK, tm * BM);
+          tma_load_2d(&tmB_lo, &full_bar[stage], st + 3 * TILE_BYTES, kc * BK, tn * BN);
+        }
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0; uint32_t phase = 0; uint32_t acc = 0;
+      for (int kc = kc_begin; kc < kc_end; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+          umma_f16(tmem_base, a_hi + koff, b_hi + koff, idesc, acc);
+          acc = 1;
+          if (NPROD == 3) {
+            const uint64_t a_lo = make_smem_desc(sbase + 2 * TILE_BYTES), b_lo = make_smem_desc(sbase + 3 * TILE_BYTES);
+            umma_f16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+            umma_f16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> fp32 reductions into D =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int row = tm * BM + q * 32 + lane;
+    const bool mirror = symmetric && (tm != tn);
+    const bool vec_ok = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), v);
+      const int col0 = tn * BN + chunk * 32;
+      if (row < M) {
+        float* drow = D + (int64_t)row * ldd + col0;
+        if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) red_add_v4(drow + j, alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) atomicAdd(drow + j, alpha * v[j]);
+        }
+        if (mirror) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) atomicAdd(D + (int64_t)(col0 + j) * ldd + row, alpha * v[j]);
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int make_tmap(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld) {
+  PFN_encodeTiled enc = get_encode();
+  LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)K, (long long)ld);
+  return 0;
+}
+
+int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                 int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                 cudaStream_t st) {
+  LPB_REQUIRE(!symmetric || M == N, "gemm_nt_bf16: symmetric needs M == N");
+  LPB_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "gemm_nt_bf16: leading dimensions must be multiples of 8 elements");
+  LPB_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 &&
+                  ((uintptr_t)B_lo % 16) == 0,
+              "gemm_nt_bf16: operands must be 16-byte aligned");
+  if (M == 0 || N == 0) return 0;
+  if (!accumulate) {
+    if (check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, N * sizeof(float), M, st), "gemm_nt_bf16 memset"))
+      return 1;
+  }
+  if (K == 0) return 0;
+  const bool x3 = A_lo != nullptr;
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  if (make_tmap(&tA_hi, A_hi, M, K, lda) || make_tmap(&tB_hi, B_hi, N, K, ldb)) return 1;
+  if (x3) {
+    if (make_tmap(&tA_lo, A_lo, M, K, lda) || make_tmap(&tB_lo, B_lo, N, K, ldb)) return 1;
+  } else {
+    tA_lo = tA_hi; tB_lo = tB_hi;
+  }
+  const int tiles_m = (int)ceil_div(M, tc::BM), tiles_n = (int)ceil_div(N, tc::BN);
+  const int64_t tiles = symmetric ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
+  const int total_kchunks = (int)ceil_div(K, tc::BK);
+  // split K so that about two CTAs per SM exist while each CTA keeps >= 4 k-chunks
+  const int sms = sm_count();
+  int64_t splits = imax(1, (2 * (int64_t)sms) / tiles);
+  splits = imin(splits, imax(1, total_kchunks / 4));
+  splits = imin(splits, 65535);
+  const int kchunks_per_split = (int)ceil_div(total_kchunks, splits);
+  splits = ceil_div(total_kchunks, kchunks_per_split);
+  const int stage_bytes = (x3 ? 4 : 2) * tc::TILE_BYTES;
+  const int num_stages = x3 ? 3 : 6;
+  const size_t smem = (size_t)num_stages * stage_bytes + (2 * num_stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr1 = false, attr3 = false;
+  if (x3 && !attr3) {
+    if (check_cuda(cudaFuncSetAttribute(tc::gemm_nt_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                   "gemm_nt_bf16 attr"))
+      return 1;
+    attr3 = true;
+  }
+  if (!x3 && !attr1) {
+    if (check_cuda(cudaFuncSetAttribute(tc::gemm_nt_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                   "gemm_nt_bf16 attr"))
+      return 1;
+    attr1 = true;
+  }
+  LPB_REQUIRE(tiles <= 2147483647LL, "gemm_nt_bf16: too many tiles");
+  dim3 grid((unsigned)tiles, (unsigned)splits);
+  if (x3)
+    tc::gemm_nt_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
+                                                                  symmetric, tiles_m, tiles_n, total_kchunks,
+                                                                  kchunks_per_split, num_stages);
+  else
+    tc::gemm_nt_tc_kernel<1><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
+                                                                  symmetric, tiles_m, tiles_n, total_kchunks,
+                                                                  kchunks_per_split, num_stages);
+  LPB_CHECK_LAUNCH("gemm_nt_bf16");
+  return 0;
+}
+
+}  // namespace lpb

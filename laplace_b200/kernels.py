@@ -1,0 +1,240 @@
+"""Tensor-level wrappers over the C ABI (``include/laplace_b200.h``).
+
+PyTorch is used here only for device memory and streams: every function below turns
+``torch.Tensor`` arguments into raw device pointers and launches one native kernel on the
+current CUDA stream.  There is no torch/CPU fallback; a missing library or a non-CUDA tensor
+raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+F32, BF16, BF16X3 = 0, 1, 2  # out_kind of the pack kernels (LPB_OUT_*)
+KIND_OF = {"fp32": F32, "bf16": BF16, "bf16x3": BF16X3}
+
+LAUNCHES = 0  # number of native kernel launches issued through this module (bench.py reads it)
+
+
+def _bump(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t: torch.Tensor, dtype=torch.float32, name="tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"laplace_b200 kernels need CUDA tensors ({name} is on {t.device}); there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+@dataclass
+class Packed:
+    """K-major operand ``[rows, ldk]`` (contraction index contiguous)."""
+
+    hi: torch.Tensor
+    lo: torch.Tensor | None
+    kind: int
+    rows: int
+    K: int
+
+    @property
+    def ldk(self) -> int:
+        return self.hi.shape[1]
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def alloc_packed(rows: int, K: int, kind: int, device) -> Packed:
+    ldk = max(round_up(K, 8), 8)
+    if kind == F32:
+        return Packed(torch.empty(rows, ldk, device=device, dtype=torch.float32), None, kind, rows, K)
+    hi = torch.empty(rows, ldk, device=device, dtype=torch.bfloat16)
+    lo = torch.empty(rows, ldk, device=device, dtype=torch.bfloat16) if kind == BF16X3 else None
+    return Packed(hi, lo, kind, rows, K)
+
+
+def device_info():
+    import ctypes as C
+
+    sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    _lib.call("lpb_device_info", C.byref(sm), C.byref(maj), C.byref(mnr))
+    return sm.value, maj.value, mnr.value
+
+
+# ------------------------------------------------------------------------------ pack
+def pack_rows(src: torch.Tensor, kind: int, out: Packed | None = None, k0: int = 0, scale: float = 1.0,
+              square: bool = False, row_scale: torch.Tensor | None = None, nrep: int = 1, total_K: int | None = None) -> Packed:
+    """``src [K, d]`` fp32 (last dim contiguous) -> K-major ``[nrep*d, ldk]`` at columns ``k0..k0+K``."""
+    _check(src, name="src")
+    assert src.dim() == 2 and src.stride(1) == 1
+    K, d = src.shape
+    if out is None:
+        out = alloc_packed(nrep * d, total_K if total_K is not None else K, kind, src.device)
+    if row_scale is not None:
+        _check(row_scale, name="row_scale")
+        assert row_scale.is_contiguous() and row_scale.numel() == nrep * K
+    _lib.call("lpb_pack_rows_t", _ptr(src), K, d, src.stride(0), _ptr(row_scale), nrep, scale, 1 if square else 0,
+              _ptr(out.hi), _ptr(out.lo), out.kind, out.ldk, k0, _stream())
+    _bump()
+    return out
+
+
+def conv_out_hw(x_shape, mod) -> tuple[int, int]:
+    H, W = x_shape[-2:]
+    kh, kw = mod.kernel_size
+    sh, sw = mod.stride
+    ph, pw = mod.padding
+    dh, dw = mod.dilation
+    return (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1, (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+
+
+def pack_conv(x: torch.Tensor, mod, kind: int, reduce_mean: bool = False, square: bool = False) -> tuple[Packed, int]:
+    """Unfolded conv patches, K-major ``[C_in*kh*kw, N*OH*OW]`` (or ``[.., N]`` means for KFAC-reduce).
+    Returns the packed operand and ``T = OH*OW``."""
+    _check(x, name="x")
+    x = x.contiguous()
+    if isinstance(mod.padding, str):
+        raise ValueError("string padding modes are not supported")
+    N, Cin, H, W = x.shape
+    OH, OW = conv_out_hw(x.shape, mod)
+    kh, kw = mod.kernel_size
+    K = N if reduce_mean else N * OH * OW
+    out = alloc_packed(Cin * kh * kw, K, kind, x.device)
+    _lib.call("lpb_pack_conv2d_t", _ptr(x), N, Cin, H, W, kh, kw, mod.stride[0], mod.stride[1], mod.padding[0],
+              mod.padding[1], mod.dilation[0], mod.dilation[1], 1.0, 1 if square else 0, 1 if reduce_mean else 0,
+              _ptr(out.hi), _ptr(out.lo), out.kind, out.ldk, 0, _stream())
+    _bump()
+    return out, OH * OW
+
+
+def pack_nchw(g: torch.Tensor, kind: int, reduce_sum: bool = False, square: bool = False) -> Packed:
+    """``g [Nn, Cc, HW]`` fp32 contiguous -> K-major ``[Cc, Nn*HW]`` (or ``[Cc, Nn]`` sums)."""
+    _check(g, name="g")
+    assert g.dim() == 3 and g.is_contiguous()
+    Nn, Cc, HW = g.shape
+    K = Nn if reduce_sum else Nn * HW
+    out = alloc_packed(Cc, K, kind, g.device)
+    _lib.call("lpb_pack_nchw_t", _ptr(g), Nn, Cc, HW, 1.0, 1 if square else 0, 1 if reduce_sum else 0, _ptr(out.hi),
+              _ptr(out.lo), out.kind, out.ldk, 0, _stream())
+    _bump()
+    return out
+
+
+# ------------------------------------------------------------------------------ contractions
+def gemm_nt(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumulate: bool = True,
+            symmetric: bool = False) -> torch.Tensor:
+    """``out[M,N] (+)= alpha * A[M,K] @ B[N,K]^T`` ; fp32 SIMT or tcgen05 bf16 / bf16x3 by operand kind."""
+    _check(out, name="out")
+    assert out.dim() == 2 and out.stride(1) == 1
+    M, N = out.shape
+    assert A.rows == M and B.rows == N and A.K == B.K and A.kind == B.kind, (A.rows, M, B.rows, N, A.K, B.K)
+    if symmetric:
+        assert A.hi.data_ptr() == B.hi.data_ptr() and M == N
+    if A.kind == F32:
+        _lib.call("lpb_gemm_nt_f32", _ptr(A.hi), A.ldk, _ptr(B.hi), B.ldk, M, N, A.K, alpha, 1 if accumulate else 0,
+                  _ptr(out), out.stride(0), 1 if symmetric else 0, _stream())
+    else:
+        _lib.call("lpb_gemm_nt_bf16", _ptr(A.hi), _ptr(A.lo), A.ldk, _ptr(B.hi), _ptr(B.lo), B.ldk, M, N, A.K, alpha,
+                  1 if accumulate else 0, _ptr(out), out.stride(0), 1 if symmetric else 0, _stream())
+    _bump()
+    return out
+
+
+def shared_weight_contract(mode: int, G: Packed, A: Packed, d_out: int, d_in: int, T: int, Nn: int, ncols: int,
+                           out: torch.Tensor, scale: float = 1.0, out_ld: int = 0, js_stride_n: int = 0,
+                           js_stride_c: int = 0) -> None:
+    assert G.kind == F32 and A.kind == F32
+    _check(out, name="out")
+    _lib.call("lpb_shared_weight_contract", mode, _ptr(G.hi), G.ldk, _ptr(A.hi), A.ldk, d_out, d_in, T, Nn, ncols,
+              scale, _ptr(out), out_ld, js_stride_n, js_stride_c, _stream())
+    _bump()
+
+
+def jac_linear_write(g: torch.Tensor, a: torch.Tensor, Js_view: torch.Tensor, stride_n: int, stride_c: int, off_w: int,
+                     off_b: int) -> None:
+    """``g [C, Nn, d_out]``, ``a [Nn, d_in]`` contiguous; ``Js_view`` = base pointer tensor of the Jacobian rows."""
+    _check(g, name="g"), _check(a, name="a"), _check(Js_view, name="Js")
+    assert g.is_contiguous() and a.is_contiguous()
+    Cc, Nn, d_out = g.shape
+    d_in = a.shape[1]
+    _lib.call("lpb_jac_linear_write", _ptr(g), _ptr(a), Nn, Cc, d_out, d_in, _ptr(Js_view), stride_n, stride_c, off_w,
+              off_b, _stream())
+    _bump()
+
+
+def ll_jacobian_write(phi: torch.Tensor, C_out: int, has_bias: bool) -> torch.Tensor:
+    _check(phi, name="phi")
+    phi = phi.contiguous()
+    Nn, D = phi.shape
+    P = C_out * D + (C_out if has_bias else 0)
+    Js = torch.empty(Nn, C_out, P, device=phi.device, dtype=torch.float32)
+    _lib.call("lpb_ll_jacobian_write", _ptr(phi), Nn, C_out, D, 1 if has_bias else 0, _ptr(Js), _stream())
+    _bump()
+    return Js
+
+
+def batched_pair_dot(X: torch.Tensor, Z: torch.Tensor, m: torch.Tensor | None, out: torch.Tensor,
+                     accumulate: bool = False) -> torch.Tensor:
+    """``out[n,c,k] (+)= sum_i X[n,c,i] Z[n,k,i] m[n,i]`` for 3-D (possibly permuted) views ``X [Nn,CX,d]``,
+    ``Z [Nn,CZ,d]`` whose last dim is contiguous; ``m [Nn,d]`` or ``[d]`` contiguous."""
+    _check(X, name="X"), _check(Z, name="Z"), _check(out, name="out")
+    assert X.stride(2) == 1 and Z.stride(2) == 1 and out.is_contiguous()
+    Nn, CX, d = X.shape
+    CZ = Z.shape[1]
+    assert Z.shape[0] == Nn and Z.shape[2] == d and out.shape == (Nn, CX, CZ)
+    m_stride = 0
+    if m is not None:
+        _check(m, name="m")
+        assert m.is_contiguous() and m.shape[-1] == d
+        m_stride = d if m.dim() == 2 else 0
+    _lib.call("lpb_batched_pair_dot", _ptr(X), _ptr(Z), _ptr(m), m_stride, Nn, CX, CZ, d, X.stride(0), X.stride(1),
+              Z.stride(0), Z.stride(1), 1 if accumulate else 0, _ptr(out), _stream())
+    _bump()
+    return out
+
+
+def ll_ggn_expand(G: torch.Tensor, C_out: int, D: int, has_bias: bool, H: torch.Tensor, accumulate: bool) -> None:
+    _check(G, name="G"), _check(H, name="H")
+    assert G.is_contiguous() and H.is_contiguous()
+    _lib.call("lpb_ll_ggn_expand", _ptr(G), C_out, D, 1 if has_bias else 0, 1 if accumulate else 0, _ptr(H), _stream())
+    _bump()
+
+
+def ll_sigma_gather(Sigma: torch.Tensor, C_out: int, D: int, has_bias: bool) -> torch.Tensor:
+    _check(Sigma, name="Sigma")
+    Sigma = Sigma.contiguous()
+    Dt = D + (1 if has_bias else 0)
+    Sg = torch.empty(C_out * C_out * Dt, Dt, device=Sigma.device, dtype=torch.float32)
+    _lib.call("lpb_ll_sigma_gather", _ptr(Sigma), C_out, D, 1 if has_bias else 0, _ptr(Sg), _stream())
+    _bump()
+    return Sg
+
+
+EIGH_MAX_N = 128
+
+
+def eigh_jacobi(A: torch.Tensor, max_sweeps: int = 30):
+    """Batched symmetric eigendecomposition ``A [batch, n, n]`` (n <= 128): ascending clamped eigenvalues, Q columns."""
+    _check(A, name="A")
+    A = A.contiguous()
+    batch, n, _ = A.shape
+    ev = torch.empty(batch, n, device=A.device, dtype=torch.float32)
+    Q = torch.empty(batch, n, n, device=A.device, dtype=torch.float32)
+    _lib.call("lpb_eigh_jacobi", _ptr(A), batch, n, _ptr(ev), _ptr(Q), max_sweeps, _stream())
+    _bump()
+    return ev, Q

@@ -1,0 +1,403 @@
+"""Kronecker-factored containers whose arithmetic runs on the B200 kernels.
+
+``B200Kron`` / ``B200KronDecomposed`` derive from the reference's ``Kron`` / ``KronDecomposed``
+(utils/matrix.py:16-560) when the reference is importable, so ``la.H += H_batch``
+(baselaplace.py:985), ``H_facs.decompose(...)`` (baselaplace.py:1809), ``self.H * self._H_factor +
+self.prior_precision`` (baselaplace.py:1820) and ``posterior_precision.inv_square_form(Js)``
+(baselaplace.py:1834-1835) dispatch here without touching host code:
+
+* ``la.H`` starts as a plain reference ``Kron`` of zeros; the first ``la.H += H_batch`` resolves to
+  the subclass' reflected ``__radd__`` (Python prefers the reflected method of a subclass operand),
+  so ``la.H`` is a ``B200Kron`` from the first batch on and later batches use ``__iadd__`` (one
+  fused in-place add over the flat factor buffer).
+* ``decompose`` -> batched Jacobi kernel for factors up to 128x128, cuSOLVER (``torch.linalg.eigh``,
+  library -- see DESIGN.md) beyond.
+* ``inv_square_form`` -> structured eigenbasis quadratic form (SURVEY App. A "Structure the kernels
+  can exploit") when the Jacobian carries its per-layer factors, dense rotation GEMMs otherwise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import torch
+
+from . import kernels as K
+from .interface import Kron, KronDecomposed
+
+
+def _is_scalar(s) -> bool:
+    if isinstance(s, (int, float)):
+        return True
+    return torch.is_tensor(s) and s.numel() == 1 and s.ndim <= 1
+
+
+def _as_f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+# =========================================================================================
+class B200Kron(Kron):
+    """Per-parameter Kronecker factors (``kfacs[i]`` = ``[B, A]`` for a weight, ``[B]`` for a bias,
+    ``parameters()`` order) stored as views into one flat device buffer."""
+
+    def __init__(self, kfacs, flat: torch.Tensor | None = None):
+        super().__init__(kfacs)
+        self._flat = flat
+
+    # -- construction ---------------------------------------------------------------------
+    @classmethod
+    def zeros(cls, dims: Sequence[Sequence[int]], device, dtype=torch.float32) -> "B200Kron":
+        total = sum(d * d for F in dims for d in F)
+        flat = torch.zeros(total, device=device, dtype=dtype)
+        kfacs, off = [], 0
+        for F in dims:
+            blk = []
+            for d in F:
+                blk.append(flat[off:off + d * d].view(d, d))
+                off += d * d
+            kfacs.append(blk)
+        return cls(kfacs, flat)
+
+    def dims(self):
+        return [[int(H.shape[0]) for H in F] for F in self.kfacs]
+
+    def _same_layout(self, other) -> bool:
+        return (isinstance(other, B200Kron) and self._flat is not None and other._flat is not None
+                and self._flat.shape == other._flat.shape and self._flat.dtype == other._flat.dtype
+                and self.dims() == other.dims())
+
+    # -- reference Kron.__add__ (utils/matrix.py:79-98): zip-aligned factor-wise sum ---------
+    def __add__(self, other):
+        if not isinstance(other, Kron):
+            raise ValueError("Can only add Kron to Kron.")
+        if self._same_layout(other):
+            out = B200Kron.zeros(self.dims(), self._flat.device, self._flat.dtype)
+            torch.add(self._flat, other._flat, out=out._flat)
+            return out
+        kfacs = [[Hi.add(Hj) for Hi, Hj in zip(Fi, Fj)] for Fi, Fj in zip(self.kfacs, other.kfacs)]
+        return B200Kron(kfacs)
+
+    __radd__ = __add__
+
+    def __iadd__(self, other):
+        if not isinstance(other, Kron):
+            raise ValueError("Can only add Kron to Kron.")
+        if self._same_layout(other):
+            self._flat.add_(other._flat)
+        else:
+            for Fi, Fj in zip(self.kfacs, other.kfacs):
+                for Hi, Hj in zip(Fi, Fj):
+                    Hi.add_(Hj)
+        return self
+
+    # -- reference Kron.__mul__ (utils/matrix.py:100-118): scalar ** (1/len(F)) on every factor -
+    def __mul__(self, scalar):
+        if not _is_scalar(scalar):
+            raise ValueError("Input not valid python or torch scalar.")
+        s = float(scalar)
+        return B200Kron([[math.pow(s, 1.0 / len(F)) * Hi for Hi in F] for F in self.kfacs])
+
+    __rmul__ = __mul__
+
+    def __len__(self):
+        return len(self.kfacs)
+
+    # -- reference Kron.decompose (utils/matrix.py:123-150) + symeig (utils/utils.py:193-228) ---
+    def decompose(self, damping: bool = False) -> "B200KronDecomposed":
+        mats = [(i, j, H) for i, F in enumerate(self.kfacs) for j, H in enumerate(F)]
+        eigvecs = [[None] * len(F) for F in self.kfacs]
+        eigvals = [[None] * len(F) for F in self.kfacs]
+        by_size: dict[int, list] = {}
+        for i, j, H in mats:
+            if H.ndim == 1:  # diagonal factor (utils/matrix.py:141-145)
+                eigvals[i][j] = H
+                eigvecs[i][j] = torch.eye(len(H), dtype=H.dtype, device=H.device)
+            else:
+                by_size.setdefault(int(H.shape[0]), []).append((i, j, H))
+        for n, group in by_size.items():
+            dtype = group[0][2].dtype
+            if n <= K.EIGH_MAX_N and group[0][2].is_cuda:
+                stack = torch.stack([_as_f32(H) for _, _, H in group])
+                ev, Q = K.eigh_jacobi(stack)
+                for b, (i, j, _) in enumerate(group):
+                    eigvals[i][j], eigvecs[i][j] = ev[b].to(dtype), Q[b].to(dtype)
+            else:
+                for i, j, H in group:
+                    ev, Q = symeig_large(H)
+                    eigvals[i][j], eigvecs[i][j] = ev, Q
+        return B200KronDecomposed(eigvecs, eigvals, damping=damping)
+
+    # -- cold-path helpers (utils/matrix.py:222-275); plain device tensor algebra --------------
+    def diag(self) -> torch.Tensor:
+        out = []
+        for F in self.kfacs:
+            d0 = F[0].diagonal() if F[0].ndim > 1 else F[0]
+            if len(F) == 1:
+                out.append(d0)
+            else:
+                d1 = F[1].diagonal() if F[1].ndim > 1 else F[1]
+                out.append(torch.outer(d0, d1).reshape(-1))
+        return torch.cat(out)
+
+    def to_matrix(self) -> torch.Tensor:
+        blocks = []
+        for F in self.kfacs:
+            F0 = F[0] if F[0].ndim > 1 else F[0].diag()
+            if len(F) == 1:
+                blocks.append(F0)
+            else:
+                F1 = F[1] if F[1].ndim > 1 else F[1].diag()
+                blocks.append(torch.kron(F0, F1))
+        return torch.block_diag(*blocks)
+
+    def logdet(self) -> torch.Tensor:
+        total = 0
+        for F in self.kfacs:
+            if len(F) == 1:
+                total = total + torch.logdet(F[0])
+            else:
+                total = total + F[1].shape[0] * torch.logdet(F[0]) + F[0].shape[0] * torch.logdet(F[1])
+        return total
+
+
+def symeig_large(H: torch.Tensor):
+    """Factors beyond the Jacobi kernel's limit: cuSOLVER ``syevd`` via ``torch.linalg.eigh`` (LIBRARY call,
+    declared as such in DESIGN.md) with the reference's post-processing (utils/utils.py:207-228): jitter retry,
+    clamp at 0, NaN -> 0; raises ``LinAlgError`` instead of the reference's ``exit()``."""
+    try:
+        L, W = torch.linalg.eigh(H, UPLO="U")
+    except RuntimeError:
+        eye = torch.eye(H.shape[0], device=H.device, dtype=H.dtype)
+        try:
+            L, W = torch.linalg.eigh(H + eye, UPLO="U")
+            L = L - 1.0
+        except RuntimeError as e:  # pragma: no cover
+            raise torch.linalg.LinAlgError(f"symmetric eigendecomposition failed: {e}") from e
+    return torch.nan_to_num(L.clamp(min=0.0)), torch.nan_to_num(W)
+
+
+# =========================================================================================
+class JacobianFactors:
+    """Per-parameter-block structure of a batch of Jacobians, attached to the dense tensor returned by
+    ``B200GGN.jacobians`` as ``Js._lpb_factors``.  ``blocks[i]`` describes parameter block ``i``:
+
+    * ``("outer", g, a)``: ``J[n,c] = g[c,n,:] (x) a[n,:]``  (weight of a layer without weight sharing)
+    * ``("vec", g)``:      ``J[n,c] = g[c,n,:]``             (bias of such a layer)
+    * ``("dense", J)``:    ``J [Nn, C, p]`` fp32 contiguous  (anything else)
+    """
+
+    def __init__(self, blocks, n_batch: int, n_out: int, sizes):
+        self.blocks, self.n_batch, self.n_out, self.sizes = blocks, n_batch, n_out, sizes
+
+
+class B200KronDecomposed(KronDecomposed):
+    """Eigendecomposed Kronecker factors (+ per-block ``deltas``); reference utils/matrix.py:282-560."""
+
+    def __init__(self, eigenvectors, eigenvalues, deltas=None, damping: bool = False):
+        ref = eigenvectors[0][0]
+        if deltas is None:
+            deltas = torch.zeros(len(eigenvalues), device=ref.device, dtype=ref.dtype)
+        else:
+            self._validate(deltas, len(eigenvalues))
+        self.eigenvectors = eigenvectors
+        self.eigenvalues = eigenvalues
+        self.deltas = deltas
+        self.damping = damping
+        self._cache = {}
+
+    @staticmethod
+    def _validate(deltas, n):
+        if not isinstance(deltas, torch.Tensor):
+            raise ValueError("Can only add torch.Tensor to KronDecomposed.")
+        if not (deltas.ndim == 0 or (deltas.ndim == 1 and len(deltas) in (1, n))):
+            raise ValueError("Invalid shape of delta added to KronDecomposed.")
+
+    def detach(self):
+        self.deltas = self.deltas.detach()
+        return self
+
+    def __len__(self):
+        return len(self.eigenvalues)
+
+    # NB: like the reference (utils/matrix.py:355, :376) ``+`` and ``*`` rebuild the object with the
+    # default ``damping=False`` -- reproduced on purpose so results stay identical.
+    def __add__(self, deltas):
+        self._validate(deltas, len(self))
+        out = B200KronDecomposed(self.eigenvectors, self.eigenvalues, self.deltas + deltas)
+        out._cache = self._cache  # rotation operands do not depend on deltas / scaling
+        return out
+
+    __radd__ = __add__
+
+    def __mul__(self, scalar):
+        if not _is_scalar(scalar):
+            raise ValueError("Invalid argument, can only multiply Kron with scalar.")
+        s = float(scalar)
+        ev = [[math.pow(s, 1.0 / len(ls)) * l for l in ls] for ls in self.eigenvalues]
+        out = B200KronDecomposed(self.eigenvectors, ev, self.deltas)
+        out._cache = self._cache
+        return out
+
+    __rmul__ = __mul__
+
+    # -- spectra ---------------------------------------------------------------------------
+    def _delta_list(self):
+        d = self.deltas
+        if d.ndim == 0 or d.numel() == 1:
+            return [d.reshape(())] * len(self)
+        return list(d)
+
+    def _spectrum(self, ls, delta):
+        if len(ls) == 1:
+            return ls[0] + delta
+        if self.damping:
+            sd = torch.sqrt(delta)
+            return torch.outer(ls[0] + sd, ls[1] + sd)
+        return torch.outer(ls[0], ls[1]) + delta
+
+    def logdet(self) -> torch.Tensor:
+        """``log det (Kron + deltas)`` (utils/matrix.py:381-404); plain tensor ops so that it stays
+        differentiable w.r.t. ``deltas`` (marginal-likelihood optimisation, baselaplace.py:363-561)."""
+        total = 0
+        for ls, delta in zip(self.eigenvalues, self._delta_list()):
+            total = total + torch.log(self._spectrum(ls, delta)).sum()
+        return total
+
+    # -- fp32 rotation operands (cached; shared by every scaled / shifted copy) ----------------
+    def _Q32(self, i, j, transposed: bool):
+        key = (i, j, transposed)
+        if key not in self._cache:
+            Q = _as_f32(self.eigenvectors[i][j])
+            self._cache[key] = (Q.t() if transposed else Q).contiguous()
+        return self._cache[key]
+
+    @staticmethod
+    def _gemm(A2d: torch.Tensor, Bnk: torch.Tensor) -> torch.Tensor:
+        """``A2d [M,K] @ Bnk[N,K]^T`` through the fp32 kernel (operands already K-major)."""
+        A2d = A2d.contiguous()
+        out = torch.empty(A2d.shape[0], Bnk.shape[0], device=A2d.device, dtype=torch.float32)
+        pa = K.Packed(A2d, None, K.F32, A2d.shape[0], A2d.shape[1])
+        pb = K.Packed(Bnk, None, K.F32, Bnk.shape[0], Bnk.shape[1])
+        return K.gemm_nt(pa, pb, out, 1.0, accumulate=False)
+
+    def _rotate_in(self, i, Wp: torch.Tensor) -> torch.Tensor:
+        """``Wp [R, p1, p2]`` -> ``Zt [R, p2, p1]`` with ``Zt[r] = (Q1^T Wp[r] Q2)^T``."""
+        R, p1, p2 = Wp.shape
+        Y = self._gemm(Wp.reshape(R * p1, p2), self._Q32(i, 1, True)).view(R, p1, p2)      # Wp Q2
+        Yt = Y.transpose(1, 2).contiguous().view(R * p2, p1)
+        return self._gemm(Yt, self._Q32(i, 0, True)).view(R, p2, p1)                      # (Q1^T Y)^T
+
+    def _rotate_out(self, i, Zt: torch.Tensor) -> torch.Tensor:
+        """inverse of ``_rotate_in``: ``Zt [R, p2, p1]`` -> ``Q1 Z Q2^T`` as ``[R, p1, p2]``."""
+        R, p2, p1 = Zt.shape
+        Y = self._gemm(Zt.reshape(R * p2, p1), self._Q32(i, 0, False)).view(R, p2, p1)     # (Q1 Z)^T
+        Yt = Y.transpose(1, 2).contiguous().view(R * p1, p2)
+        return self._gemm(Yt, self._Q32(i, 1, False)).view(R, p1, p2)
+
+    # -- reference KronDecomposed._bmm (utils/matrix.py:406-456) --------------------------------
+    def _bmm(self, W: torch.Tensor, exponent: float = -1) -> torch.Tensor:
+        assert W.ndim == 3
+        B, Kk, P = W.shape
+        dtype = W.dtype
+        Wf = _as_f32(W).reshape(B * Kk, P)
+        out, cur = [], 0
+        for i, (ls, delta) in enumerate(zip(self.eigenvalues, self._delta_list())):
+            spec = torch.pow(_as_f32(self._spectrum(ls, delta)), exponent)
+            if len(ls) == 1:
+                p = ls[0].numel()
+                Z = self._gemm(Wf[:, cur:cur + p], self._Q32(i, 0, True)) * spec            # (Q^T w)^T * spec
+                out.append(self._gemm(Z, self._Q32(i, 0, False)))
+            else:
+                p1, p2 = ls[0].numel(), ls[1].numel()
+                p = p1 * p2
+                Zt = self._rotate_in(i, Wf[:, cur:cur + p].reshape(-1, p1, p2)) * spec.t()
+                out.append(self._rotate_out(i, Zt).reshape(-1, p))
+            cur += p
+        return torch.cat(out, dim=1).reshape(B, Kk, P).to(dtype)
+
+    def bmm(self, W: torch.Tensor, exponent: float = -1) -> torch.Tensor:
+        if W.ndim == 1:
+            return self._bmm(W.unsqueeze(0).unsqueeze(0), exponent).squeeze()
+        if W.ndim == 2:
+            return self._bmm(W.unsqueeze(1), exponent).squeeze()
+        if W.ndim == 3:
+            return self._bmm(W, exponent)
+        raise ValueError("Invalid shape for W")
+
+    # -- reference KronDecomposed.inv_square_form (utils/matrix.py:458-461) ----------------------
+    def inv_square_form(self, W: torch.Tensor) -> torch.Tensor:
+        fac = getattr(W, "_lpb_factors", None)
+        if fac is not None and len(fac.blocks) == len(self) and not W.requires_grad:
+            return self._structured_isf(fac).to(W.dtype)
+        Wf = _as_f32(W).contiguous()
+        SW = _as_f32(self._bmm(Wf, exponent=-1)).contiguous()
+        out = torch.empty(W.shape[0], W.shape[1], W.shape[1], device=W.device, dtype=torch.float32)
+        K.batched_pair_dot(Wf, SW, None, out)
+        return out.to(W.dtype)
+
+    def _structured_isf(self, fac: JacobianFactors) -> torch.Tensor:
+        """``f_var[n,c,k] = sum_blocks sum_ij Zc[i,j] Zk[i,j] / spec[i,j]`` with the per-layer rank structure:
+        for ``J = g (x) a``: ``sum_i gt_c[i] gt_k[i] m[i]``, ``gt = Q1^T g``, ``m = (Q2^T a)^2 @ (1/spec)^T``."""
+        Nn, C = fac.n_batch, fac.n_out
+        dev = self.eigenvectors[0][0].device
+        out = torch.zeros(Nn, C, C, device=dev, dtype=torch.float32)
+        for i, (blk, ls, delta) in enumerate(zip(fac.blocks, self.eigenvalues, self._delta_list())):
+            inv_spec = torch.reciprocal(_as_f32(self._spectrum(ls, delta))).contiguous()
+            kind = blk[0]
+            if kind == "outer" and len(ls) == 2:
+                g, a = blk[1], blk[2]                                    # [C, Nn, d_out], [Nn, d_in]
+                d_out = g.shape[2]
+                gt = self._gemm(g.reshape(C * Nn, d_out), self._Q32(i, 0, True)).view(C, Nn, d_out)
+                at = self._gemm(a, self._Q32(i, 1, True))
+                m = self._gemm(at * at, inv_spec)                        # [Nn, d_out]
+                gtn = gt.permute(1, 0, 2)                                # [Nn, C, d_out] view
+                K.batched_pair_dot(gtn, gtn, m, out, accumulate=True)
+            elif kind == "vec" and len(ls) == 1:
+                g = blk[1]
+                d_out = g.shape[2]
+                gt = self._gemm(g.reshape(C * Nn, d_out), self._Q32(i, 0, True)).view(C, Nn, d_out)
+                gtn = gt.permute(1, 0, 2)
+                K.batched_pair_dot(gtn, gtn, inv_spec, out, accumulate=True)
+            else:
+                J = blk[1] if kind == "dense" else materialize_block(blk, Nn, C)
+                p = J.shape[2]
+                if len(ls) == 1:
+                    Z = self._gemm(J.reshape(Nn * C, p), self._Q32(i, 0, True)).view(Nn, C, p)
+                    K.batched_pair_dot(Z, Z, inv_spec, out, accumulate=True)
+                else:
+                    p1, p2 = ls[0].numel(), ls[1].numel()
+                    Zt = self._rotate_in(i, J.reshape(Nn * C, p1, p2)).reshape(Nn, C, p)
+                    K.batched_pair_dot(Zt, Zt, inv_spec.t().contiguous().reshape(-1), out, accumulate=True)
+        return out
+
+    # -- cold-path helpers (utils/matrix.py:490-556) ---------------------------------------------
+    def diag(self, exponent: float = 1) -> torch.Tensor:
+        out = []
+        for Qs, ls, delta in zip(self.eigenvectors, self.eigenvalues, self._delta_list()):
+            spec = torch.pow(self._spectrum(ls, delta), exponent)
+            if len(ls) == 1:
+                out.append(((Qs[0] * spec) * Qs[0]).sum(1))
+            else:
+                out.append(((Qs[0] ** 2) @ spec @ (Qs[1] ** 2).T).reshape(-1))
+        return torch.cat(out)
+
+    def to_matrix(self, exponent: float = 1) -> torch.Tensor:
+        blocks = []
+        for Qs, ls, delta in zip(self.eigenvectors, self.eigenvalues, self._delta_list()):
+            spec = torch.pow(self._spectrum(ls, delta), exponent).reshape(-1)
+            Q = Qs[0] if len(ls) == 1 else torch.kron(Qs[0], Qs[1])
+            blocks.append((Q * spec) @ Q.T)
+        return torch.block_diag(*blocks)
+
+
+def materialize_block(blk, Nn: int, C: int) -> torch.Tensor:
+    """Dense ``[Nn, C, p]`` rows of an ``outer`` / ``vec`` block (only reached when a block's factor structure
+    and the decomposed block's structure disagree)."""
+    if blk[0] == "vec":
+        return blk[1].permute(1, 0, 2).contiguous()
+    g, a = blk[1], blk[2]
+    d_out, d_in = g.shape[2], a.shape[1]
+    J = torch.empty(Nn, C, d_out * d_in, device=g.device, dtype=torch.float32)
+    K.jac_linear_write(g, a, J, C * d_out * d_in, d_out * d_in, 0, -1)
+    return J

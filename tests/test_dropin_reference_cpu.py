@@ -1,0 +1,115 @@
+"""Drop-in check: the UNMODIFIED reference front end (``Laplace(...).fit`` / ``la(x, pred_type="glm")``)
+driven with ``backend=B200GGN`` / ``B200EF``.  Needs the reference tree (build container only); kernels
+are replaced by the CPU emulation, so this pins the *boundary wiring* (SURVEY 8(b)): construction through
+``BaseLaplace.backend``, ``la.H += H_batch`` dispatch, ``decompose``, ``posterior_precision`` algebra,
+``functional_variance``."""
+import pytest
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+from oracle import ref_shim
+from tests.fixtures import load, rel_fro
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+@pytest.fixture
+def laplace_mod():
+    import laplace
+    from laplace_b200.interface import HAVE_REFERENCE
+
+    if not HAVE_REFERENCE:
+        pytest.skip("laplace_b200 was imported before the reference became importable")
+    return laplace
+
+
+@pytest.mark.parametrize("kind", ["mlp", "conv"])
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_kron_laplace_fit_and_glm(golden, cpu_kernels, laplace_mod, kind, lik):
+    from laplace.utils.matrix import Kron, KronDecomposed
+
+    from laplace_b200 import B200GGN, B200Kron, B200KronDecomposed
+    from oracle import curvature_oracle as co
+
+    model, X, y, _ = load(golden, kind, lik, dtype=torch.float32)
+    loader = DataLoader(TensorDataset(X, y), batch_size=4)
+    la = laplace_mod.Laplace(model, lik, "all", "kron", backend=B200GGN, prior_precision=0.7)
+    la.fit(loader)
+    assert isinstance(la.H_facs, B200Kron) and isinstance(la.H, B200KronDecomposed)
+    assert isinstance(la.posterior_precision, B200KronDecomposed)
+    # reference algebra on the oracle factors
+    kfs = None
+    for i in range(0, len(X), 4):
+        _, kf = co.kfac_factors(model.double(), lik, X[i:i + 4].double(), y[i:i + 4] if lik == "classification" else y[i:i + 4].double(), N=len(X))
+        kfs = kf if kfs is None else [[a + b for a, b in zip(Fa, Fb)] for Fa, Fb in zip(kfs, kf)]
+    model.float()
+    for F, Fo in zip(la.H_facs.kfacs, kfs):
+        for H, Ho in zip(F, Fo):
+            assert rel_fro(H, Ho) < 1e-4
+    ref = Kron([[H.float() for H in F] for F in kfs]).decompose() * 1.0 + la.prior_precision
+    assert type(ref) is KronDecomposed
+    f_mu, f_var = la._glm_predictive_distribution(X)
+    Js, _ = la.backend.jacobians(X)
+    f_var_ref = ref.inv_square_form(Js.clone())
+    assert torch.allclose(f_var, f_var_ref, rtol=2e-3, atol=1e-6)
+    assert torch.allclose(la.log_det_posterior_precision, ref.logdet(), rtol=1e-4)
+    if lik == "classification":
+        probs = la(X, pred_type="glm", link_approx="probit")
+        assert torch.allclose(probs.sum(-1), torch.ones(len(X)), atol=1e-5)
+    la.log_marginal_likelihood()
+    sd = la.state_dict()
+    assert all(isinstance(h, torch.Tensor) for F in sd["H"] for h in F)
+
+
+@pytest.mark.parametrize("hs", ["full", "diag"])
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_full_and_diag_laplace_match_golden(golden, cpu_kernels, laplace_mod, hs, lik):
+    from laplace_b200 import B200GGN
+
+    model, X, y, rec = load(golden, "mlp", lik)
+    loader = DataLoader(TensorDataset(X, y), batch_size=4)
+    la = laplace_mod.Laplace(model, lik, "all", hs, backend=B200GGN, prior_precision=0.7)
+    la.fit(loader)
+    f_mu, f_var = la._glm_predictive_distribution(X)
+    assert torch.allclose(f_mu, rec[f"la_{hs}_f_mu"], atol=1e-6)
+    assert torch.allclose(f_var, rec[f"la_{hs}_f_var"], rtol=1e-4, atol=1e-7)
+    assert torch.allclose(la.log_marginal_likelihood(), rec[f"la_{hs}_logmarglik"], rtol=1e-5)
+
+
+def test_last_layer_full_laplace(golden, cpu_kernels, laplace_mod):
+    from laplace.curvature import GGNInterface
+
+    from laplace_b200 import B200EF, B200GGN
+
+    model, X, y, rec = load(golden, "mlp", "classification")
+    loader = DataLoader(TensorDataset(X, y), batch_size=4)
+    for be, ref_be in ((B200GGN, GGNInterface),):
+        la = laplace_mod.Laplace(model, "classification", "last_layer", "full", backend=be, prior_precision=0.7)
+        la.fit(loader)
+        lr = laplace_mod.Laplace(model, "classification", "last_layer", "full", backend=ref_be, prior_precision=0.7)
+        lr.fit(loader)
+        assert rel_fro(la.H, lr.H) < 1e-5
+        fm, fv = la._glm_predictive_distribution(X)
+        fm_r, fv_r = lr._glm_predictive_distribution(X)
+        assert torch.allclose(fv, fv_r, rtol=1e-4, atol=1e-8)
+    for hs in ("diag", "kron"):
+        la = laplace_mod.Laplace(model, "classification", "last_layer", hs, backend=B200GGN, prior_precision=0.7)
+        la.fit(loader)
+        la._glm_predictive_distribution(X)
+    la = laplace_mod.Laplace(model, "classification", "last_layer", "full", backend=B200EF)
+    la.fit(loader)
+
+
+def test_subnetwork_laplace(golden, cpu_kernels, laplace_mod):
+    from laplace.curvature import GGNInterface
+
+    from laplace_b200 import B200GGN
+
+    model, X, y, _ = load(golden, "mlp", "classification")
+    loader = DataLoader(TensorDataset(X, y), batch_size=5)
+    idx = torch.tensor([0, 3, 17, 60, 61, 100, 121])
+    la = laplace_mod.Laplace(model, "classification", "subnetwork", "full", subnetwork_indices=idx, backend=B200GGN)
+    la.fit(loader)
+    lr = laplace_mod.Laplace(model, "classification", "subnetwork", "full", subnetwork_indices=idx, backend=GGNInterface)
+    lr.fit(loader)
+    assert rel_fro(la.H, lr.H) < 1e-5

@@ -1,0 +1,126 @@
+"""Host logic of the B200 backend on CPU (kernels replaced by the tests/cpu_kernels.py emulation):
+layer plan, hook capture, curvature columns, scaling conventions, Kron assembly -- checked against the
+CPU oracle and the golden vectors of the unmodified reference."""
+import pytest
+import torch
+
+from laplace_b200 import B200EF, B200GGN, B200Kron
+from oracle import curvature_oracle as co
+from oracle import kron_oracle as ko
+from tests.fixtures import load, rel_fro
+
+CASES = [(k, l) for k in ("mlp", "conv") for l in ("classification", "regression")]
+
+
+@pytest.mark.parametrize("kind,lik", CASES)
+@pytest.mark.parametrize("batched", [True, False])
+def test_jacobians_full_diag(golden, cpu_kernels, kind, lik, batched):
+    model, X, y, rec = load(golden, kind, lik)
+    be = B200GGN(model, lik, batched_backward=batched)
+    Js, f = be.jacobians(X)
+    assert Js.dtype == torch.float64 and rel_fro(Js, rec["Js"]) < 1e-6
+    assert torch.allclose(f, rec["f"], atol=1e-6)
+    loss, H = be.full(X, y)
+    assert torch.allclose(loss, rec["ggn_loss"], rtol=1e-6)
+    assert rel_fro(H, rec["ggn_full"]) < 1e-5
+    loss, d = be.diag(X, y)
+    assert rel_fro(d, rec["ggn_diag"]) < 1e-5
+    ef = B200EF(model, lik, batched_backward=batched)
+    Gs, gl = ef.gradients(X, y)
+    assert rel_fro(Gs, rec["Gs"]) < 1e-6 and torch.allclose(gl, rec["grad_loss"], rtol=1e-6)
+    loss, Hef = ef.full(X, y)
+    assert torch.allclose(loss, rec["ef_loss"], rtol=1e-6)
+    if "ef_full" in rec:
+        assert rel_fro(Hef, rec["ef_full"]) < 1e-5
+    _, de = ef.diag(X, y)
+    assert rel_fro(de, rec["ef_diag"]) < 1e-5
+
+
+@pytest.mark.parametrize("kind,lik", CASES)
+@pytest.mark.parametrize("approx", ["expand", "reduce"])
+def test_kron_matches_oracle(golden, cpu_kernels, kind, lik, approx):
+    model, X, y, _ = load(golden, kind, lik)
+    N = 3 * len(X)
+    loss_o, kf_o = co.kfac_factors(model, lik, X, y, N=N, kfac_approx=approx)
+    loss, kron = B200GGN(model, lik).kron(X, y, N=N, kfac_approx=approx)
+    assert isinstance(kron, B200Kron) and torch.allclose(loss, loss_o, rtol=1e-6)
+    assert len(kron.kfacs) == len(kf_o)
+    for F, Fo in zip(kron.kfacs, kf_o):
+        assert len(F) == len(Fo)
+        for H, Ho in zip(F, Fo):
+            assert H.dtype == torch.float64 and rel_fro(H, Ho) < 1e-5
+    loss_o, kf_o = co.kfac_factors(model, lik, X, y, N=N, fisher="empirical", kfac_approx=approx)
+    loss, kron = B200EF(model, lik).kron(X, y, N=N, kfac_approx=approx)
+    assert torch.allclose(loss, loss_o, rtol=1e-6)
+    for F, Fo in zip(kron.kfacs, kf_o):
+        for H, Ho in zip(F, Fo):
+            assert rel_fro(H, Ho) < 1e-5
+
+
+def test_kron_frozen_params(golden, cpu_kernels):
+    """Blocks are emitted only for trainable parameters, in parameters() order (reference fixture:
+    tests/test_subset_params.py:20-33)."""
+    model, X, y, _ = load(golden, "mlp", "classification")
+    model[0].weight.requires_grad_(False)
+    _, kron = B200GGN(model, "classification").kron(X, y, N=len(X))
+    assert [[h.shape[0] for h in F] for F in kron.kfacs] == [[20], [2, 20], [2]]
+    _, kf_o = co.kfac_factors(model, "classification", X, y, N=len(X))
+    for F, Fo in zip(kron.kfacs, kf_o):
+        for H, Ho in zip(F, Fo):
+            assert rel_fro(H, Ho) < 1e-5
+
+
+def test_kron_mc_statistics(golden, cpu_kernels):
+    model, X, y, _ = load(golden, "mlp", "classification")
+    _, exact = co.kfac_factors(model, "classification", X, y, N=len(X))
+    torch.manual_seed(0)
+    be = B200GGN(model, "classification", stochastic=True)
+    errs = []
+    for s in (1, 200):
+        _, k = be.kron(X, y, N=len(X), mc_samples=s)
+        errs.append(float((k.to_matrix() - co.kfacs_to_matrix(exact)).norm()))
+    assert errs[1] < 0.5 * errs[0]
+
+
+def test_unsupported_module_raises(cpu_kernels):
+    model = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.LayerNorm(4), torch.nn.Linear(4, 2))
+    with pytest.raises(ValueError):
+        B200GGN(model, "classification").kron(torch.randn(2, 3), torch.tensor([0, 1]), N=2)
+
+
+def test_kron_container_algebra(golden, cpu_kernels):
+    rec = golden["kron_algebra"]
+    kfacs, W = rec["kfacs"], rec["W"]
+    kron = B200Kron([[H.clone() for H in F] for F in kfacs])
+    two = kron + kron
+    assert all(torch.allclose(a, 2 * b) for Fa, Fb in zip(two.kfacs, kfacs) for a, b in zip(Fa, Fb))
+    two += kron
+    assert all(torch.allclose(a, 3 * b) for Fa, Fb in zip(two.kfacs, kfacs) for a, b in zip(Fa, Fb))
+    scaled = kron * 0.25
+    assert torch.allclose(scaled.kfacs[0][0], 0.5 * kfacs[0][0]) and torch.allclose(scaled.kfacs[1][0], 0.25 * kfacs[1][0])
+    kd = kron.decompose()
+    for a, b in zip(kd.eigenvalues, rec["plain_eigvals"]):
+        for x, y in zip(a, b):
+            assert torch.allclose(x, y, atol=1e-5)
+    for name in ("scalar", "layer"):
+        P = kd * 1.7 + rec[f"plain_{name}_delta"]
+        assert torch.allclose(P.inv_square_form(W), rec[f"plain_{name}_isf"], rtol=1e-4)
+        assert torch.allclose(P.logdet(), rec[f"plain_{name}_logdet"], rtol=1e-6)
+        assert torch.allclose(P.bmm(W, exponent=-0.5), rec[f"plain_{name}_bmm_m05"], rtol=1e-3, atol=1e-5)
+        assert P.damping is False  # reference quirk: * and + drop damping
+
+
+def test_structured_predictive_matches_dense(golden, cpu_kernels):
+    """inv_square_form through the per-layer factors == dense reference algebra (fp32 model)."""
+    for kind in ("mlp", "conv"):
+        model, X, y, _ = load(golden, kind, "classification", dtype=torch.float32)
+        be = B200GGN(model, "classification")
+        _, kron = be.kron(X, y, N=len(X))
+        P = kron.decompose() * 1.0 + torch.tensor(0.7)
+        Js, f = be.jacobians(X)
+        assert hasattr(Js, "_lpb_factors")
+        fv = P.inv_square_form(Js)
+        Qs = [[q.double() for q in Q] for Q in P.eigenvectors]
+        ls = [[l.double() for l in L] for L in P.eigenvalues]
+        ref = ko.kron_inv_square_form(Qs, ls, torch.tensor(0.7, dtype=torch.float64), Js.double().clone())
+        assert torch.allclose(fv.double(), ref, rtol=1e-3, atol=1e-6)
