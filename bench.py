@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the curvature hot path (BASELINE.json metric: KFAC-GGN fit() samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+                    [--precision bf16x3|bf16|fp32|auto] [--model resnet18|mlp|...]
+
+Workload (N=1 default, configs[1] of BASELINE.json): ResNet-18-shaped CNN (torchvision topology, random
+init, frozen norm affines), 32x32x3 synthetic inputs, C=10, KFAC-GGN over all conv/linear weights.
+A "step" = one pass of the hot path over one batch of B samples: forward + C batched reverse passes,
+packing, the A/B factor SYRKs on the tensor cores and the accumulation into the running factor buffers
+(i.e. one iteration of the ``fit()`` loop, baselaplace.py:969-985).  Multi-GPU: every rank runs the same
+per-batch loop on its own shard (weak scaling) and the factors are all-reduced ONCE after the K steps
+(inside the timed region).
+
+One JSON line is printed by rank 0 (see the task contract): `value` = samples/s with inputs resident in
+HBM, `e2e` = the same through the public API with pinned-host batches copied inside the timed region,
+`roofline` = the tcgen05 SYRK kernel against the measured bf16 peak, `cpu_baseline` = the CPU oracle port of
+the reference's KFAC path timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "kfac_ggn_fit_samples_per_sec"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--precision", default="bf16x3", choices=["auto", "fp32", "bf16", "bf16x3"])
+    ap.add_argument("--model", default="resnet18")
+    ap.add_argument("--cpu-samples", type=int, default=256, help="samples of the bounded CPU-baseline run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--predictive", action="store_true", help="also time the GLM predictive (reported under config)")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return f"{args.model} (torchvision topology, random init, frozen norm), 32x32x3 synthetic, C=10, KFAC-GGN all weights"
+
+
+def make_model(name):
+    from laplace_b200 import models
+
+    return models.make(name)
+
+
+def input_shape(name):
+    return (784,) if name == "mlp" else ((3, 224, 224) if name == "vit_b16" else (3, 32, 32))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(args, steps, warmup, samples_per_step):
+    """The reference's CPU implementation of the path: curvlinops is not installable offline, so this times the
+    oracle PORT of CurvlinopsGGN.kron (oracle/curvature_oracle.py:kfac_factors) with all host threads."""
+    from oracle import curvature_oracle as co
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = make_model(args.model)
+    torch.manual_seed(1)
+    X = torch.randn(samples_per_step, *input_shape(args.model))
+    y = torch.randint(10, (samples_per_step,))
+    acc = None
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, kf = co.kfac_factors(model, "classification", X, y, N=50000)
+        acc = kf if acc is None else [[a.add_(b) for a, b in zip(Fa, Fb)] for Fa, Fb in zip(acc, kf)]
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return steps * samples_per_step / total, total / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spp = max(16, args.cpu_samples // 4)
+    steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    v, ms = cpu_reference_run(args, steps, warmup, spp)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "batch_per_step": spp, "note": "CPU oracle port of CurvlinopsGGN.kron "
+                   "(curvlinops itself is not installable offline); bounded sample per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{steps} steps x {spp} samples"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_burst": p.get("bf16_tflops"), "bf16_sustained": p.get("bf16_tflops_sustained"), "hbm": p.get("hbm_gbs"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from laplace_b200 import B200GGN
+    from laplace_b200 import kernels as K
+    from laplace_b200.distributed import allreduce_curvature
+    from laplace_b200.posterior import B200Laplace
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, Ksteps, W = args.batch, args.steps, max(3, args.warmup)
+    N_total = 50000
+    model = make_model(args.model).to(dev)
+    be = B200GGN(model, "classification", precision=args.precision)
+    shape = input_shape(args.model)
+    torch.manual_seed(1 + rank)
+    n_batches = min(8, W + Ksteps)  # pool of distinct batches; factor buffers (376 MB) dwarf the 126 MB L2 anyway
+    Xs = [torch.randn(B, *shape, device=dev) for _ in range(n_batches)]
+    ys = [torch.randint(10, (B,), device=dev) for _ in range(n_batches)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident run ----------------
+    H = None
+
+    def step(i):
+        nonlocal H
+        _, kr = be.kron(Xs[i % n_batches], ys[i % n_batches], N=N_total)
+        if H is None:
+            H = kr
+        else:
+            H += kr
+
+    for i in range(W):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = K.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(Ksteps):
+        step(W + i)
+    allreduce_curvature(H)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = K.LAUNCHES - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = world * Ksteps * B / (ms_total / 1e3)
+
+    # ---------------- roofline of the dominant kernel (separate short pass, CUDA events around each launch) -----
+    roof = measure_roofline(be, K, Xs, ys, N_total, args, dev)
+
+    # ---------------- end-to-end through the public API with pinned host batches ----------------
+    Xh = [x.cpu().pin_memory() for x in Xs]
+    yh = [y.cpu().pin_memory() for y in ys]
+
+    class HostSet(torch.utils.data.Dataset):
+        def __len__(self):
+            return N_total
+
+    class HostLoader:
+        dataset = HostSet()
+
+        def __init__(self, n, off):
+            self.n, self.off = n, off
+
+        def __iter__(self):
+            for i in range(self.n):
+                j = (self.off + i) % n_batches
+                yield Xh[j], yh[j]
+
+    la = B200Laplace(model, "classification", "all", "kron", backend=B200GGN, backend_kwargs={"precision": args.precision})
+    la.fit(HostLoader(W, 0), decompose=False)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    la.fit(HostLoader(Ksteps, W), decompose=False)
+    allreduce_curvature(la.H_facs)
+    loss_host = float(la.loss)  # device -> host read of the step result
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    e2e_value = world * Ksteps * B / (ms_e2e / 1e3)
+    h2d = Xh[0].numel() * 4 + yh[0].numel() * 8
+
+    extras = {}
+    if rank == 0:
+        t0 = time.perf_counter()
+        la.decompose()
+        torch.cuda.synchronize()
+        extras["decompose_ms_once_per_fit"] = (time.perf_counter() - t0) * 1e3
+        if args.predictive:
+            extras.update(measure_predictive(model, dev, B200Laplace, B200GGN, args))
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, ms = cpu_reference_run(args, 2, 1, max(16, args.cpu_samples // 4))
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"2 steps x {max(16, args.cpu_samples // 4)} samples of the same workload (oracle port of "
+                             "CurvlinopsGGN.kron, all host threads)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ksteps, "warmup": W,
+            "ms_per_step": ms_total / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16x3": "bf16 (hi/lo split, 3 products, fp32 accumulate)", "bf16": "bf16", "fp32": "f32",
+                      "auto": "bf16x3/f32 auto"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "batch_per_gpu": B, "global_batch": B * world, "N_dataset": N_total,
+                       "parallelism": f"dp{world}", "precision": args.precision,
+                       "l2": "distinct batch every step; per-step working set (factor buffers 376 MB + staging) exceeds the 126 MB L2",
+                       "exchange": "one all-reduce of the flat factor buffer after the K steps, inside the timed region",
+                       **extras},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / Ksteps, "loss": loss_host},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_roofline(be, K, Xs, ys, N_total, args, dev):
+    """Times every tensor-core SYRK launch of two steps with CUDA events on the launching stream.
+    achieved = algorithmic FLOPs (2 * d^2 * K_rows per launch, dense convention) / event time."""
+    records = []
+    orig = K.gemm_nt
+
+    def timed(A, Bp, out, alpha=1.0, accumulate=True, symmetric=False):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(A, Bp, out, alpha, accumulate, symmetric)
+        e.record()
+        records.append((A.kind, A.rows, Bp.rows, A.K, s, e))
+        return r
+
+    K.gemm_nt = timed
+    try:
+        for i in range(2):
+            be.kron(Xs[i % len(Xs)], ys[i % len(ys)], N=N_total)
+        torch.cuda.synchronize()
+    finally:
+        K.gemm_nt = orig
+    tc = [(m, n, k, s.elapsed_time(e)) for kind, m, n, k, s, e in records if kind != K.F32]
+    if not tc:
+        return None
+    flops = sum(2.0 * m * n * k for m, n, k, _ in tc)
+    ms = sum(t for *_, t in tc)
+    pk = peaks()
+    peak = pk["bf16_sustained"] or 1400.0
+    achieved = flops / (ms / 1e3) / 1e12
+    top = max(tc, key=lambda r: r[3])
+    return {"bound": "tensor", "kernel": "gemm_nt_tc_kernel (tcgen05 SYRK, all factor launches of a step)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": pk["source"] + ", bf16 sustained", "launches_per_step": len(tc) // 2,
+            "ms_per_step_in_kernel": ms / 2,
+            "largest_launch": {"d": top[0], "k_rows": top[2], "ms": top[3], "tflops": 2.0 * top[0] * top[1] * top[2] / top[3] / 1e9}}
+
+
+def measure_predictive(model, dev, B200Laplace, B200GGN, args):
+    """GLM predictive samples/s of the last-layer full posterior (BASELINE configs[2])."""
+    torch.manual_seed(5)
+    Xf = torch.randn(2048, *input_shape(args.model), device=dev)
+    yf = torch.randint(10, (2048,), device=dev)
+    la = B200Laplace(model, "classification", "last_layer", "full", backend=B200GGN)
+    la.fit(torch.utils.data.DataLoader(torch.utils.data.TensorDataset(Xf, yf), batch_size=512))
+    la(Xf[:512])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(4):
+        la(Xf[i * 512:(i + 1) * 512])
+    torch.cuda.synchronize()
+    return {"glm_predictive_ll_full_samples_per_sec": 2048 / (time.perf_counter() - t0)}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,202 @@
+"""Kernel-level parity on the B200: every C-ABI entry point (called through laplace_b200.kernels) against the
+layout-exact torch emulation in tests/cpu_kernels.py evaluated on the same seeded inputs."""
+import pytest
+import torch
+
+from laplace_b200 import kernels as K
+from tests import cpu_kernels as ck
+from tests.fixtures import rel_fro
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _dense(p):
+    return p.hi[:, :p.K].float().cpu() + (p.lo[:, :p.K].float().cpu() if p.lo is not None else 0)
+
+
+@pytest.mark.parametrize("kind,tol", [(K.F32, 0.0), (K.BF16, 4e-3), (K.BF16X3, 2e-5)])
+@pytest.mark.parametrize("shape", [(1, 1), (37, 5), (64, 64), (1000, 130), (33, 513)])
+def test_pack_rows(kind, tol, shape):
+    torch.manual_seed(0)
+    src = torch.randn(*shape)
+    ref = ck.pack_rows(src, K.F32)
+    out = K.pack_rows(src.to(DEV), kind)
+    assert out.ldk % 8 == 0
+    assert (_dense(out) - ref.hi[:, :ref.K]).abs().max() <= tol * src.abs().max() + 1e-30
+    w = torch.rand(3 * shape[0])
+    ref = ck.pack_rows(src, K.F32, square=True, row_scale=w, nrep=3, scale=0.5)
+    out = K.pack_rows(src.to(DEV), kind, square=True, row_scale=w.to(DEV), nrep=3, scale=0.5)
+    assert rel_fro(_dense(out), ref.hi[:, :ref.K]) <= max(tol, 1e-7)
+
+
+@pytest.mark.parametrize("geom", [(3, 4, 2, 2, 0, 1, 5), (3, 8, 3, 1, 1, 1, 8), (16, 8, 3, 2, 1, 1, 9), (4, 4, 1, 2, 0, 1, 7),
+                                  (2, 4, 3, 1, 2, 2, 9), (3, 64, 7, 2, 3, 1, 32)])
+def test_pack_conv_and_nchw(geom):
+    cin, cout, k, s, p, d, hw = geom
+    torch.manual_seed(1)
+    mod = torch.nn.Conv2d(cin, cout, k, s, p, dilation=d)
+    x = torch.randn(5, cin, hw, hw)
+    for reduce in (False, True):
+        ref, T = ck.pack_conv(x, mod, K.F32, reduce_mean=reduce)
+        out, T2 = K.pack_conv(x.to(DEV), mod, K.F32, reduce_mean=reduce)
+        assert T == T2 and rel_fro(_dense(out), ref.hi[:, :ref.K]) < 1e-6
+    o = mod(x)
+    g = torch.randn(7, cout, o.shape[2] * o.shape[3])
+    for reduce in (False, True):
+        ref = ck.pack_nchw(g, K.F32, reduce_sum=reduce)
+        out = K.pack_nchw(g.to(DEV), K.BF16X3, reduce_sum=reduce)
+        assert rel_fro(_dense(out), ref.hi[:, :ref.K]) < 2e-5
+
+
+GEMM_SHAPES = [(1, 1, 1), (5, 7, 3), (64, 64, 16), (70, 130, 1000), (128, 128, 64), (200, 96, 517), (513, 257, 2048),
+               (300, 300, 40000)]
+
+
+@pytest.mark.parametrize("M,N,Kc", GEMM_SHAPES)
+def test_gemm_nt_f32(M, N, Kc):
+    torch.manual_seed(2)
+    A, B = torch.randn(M, Kc), torch.randn(N, Kc)
+    ref = (A.double() @ B.double().t())
+    pa, pb = K.pack_rows(A.t().contiguous().to(DEV), K.F32), K.pack_rows(B.t().contiguous().to(DEV), K.F32)
+    out = torch.full((M, N), 3.0, device=DEV)
+    K.gemm_nt(pa, pb, out, alpha=0.5, accumulate=True)
+    assert rel_fro(out.cpu().double() - 3.0, 0.5 * ref) < 2e-6
+    K.gemm_nt(pa, pb, out, alpha=1.0, accumulate=False)
+    assert rel_fro(out.cpu(), ref) < 2e-6
+    if M == N:
+        sym = torch.zeros(M, M, device=DEV)
+        K.gemm_nt(pa, pa, sym, alpha=1.0, accumulate=True, symmetric=True)
+        assert rel_fro(sym.cpu(), A.double() @ A.double().t()) < 2e-6
+        assert torch.equal(sym, sym.t())
+
+
+@pytest.mark.parametrize("M,N,Kc", [(128, 128, 64), (128, 128, 4096), (100, 60, 50), (513, 257, 2048), (300, 300, 40000),
+                                    (1000, 1000, 512), (64, 2000, 130)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5)])
+def test_gemm_nt_tensor_core(M, N, Kc, kind, tol):
+    torch.manual_seed(3)
+    A, B = torch.randn(M, Kc), torch.randn(N, Kc)
+    ref = A.double() @ B.double().t()
+    pa, pb = K.pack_rows(A.t().contiguous().to(DEV), kind), K.pack_rows(B.t().contiguous().to(DEV), kind)
+    out = torch.zeros(M, N, device=DEV)
+    K.gemm_nt(pa, pb, out, alpha=2.0, accumulate=True)
+    K.gemm_nt(pa, pb, out, alpha=-1.0, accumulate=True)
+    assert rel_fro(out.cpu(), ref) < tol
+    out.fill_(7.0)
+    K.gemm_nt(pa, pb, out, alpha=1.0, accumulate=False)
+    assert rel_fro(out.cpu(), ref) < tol
+    if M == N:
+        sym = torch.zeros(M, M, device=DEV)
+        K.gemm_nt(pa, pa, sym, alpha=1.0, accumulate=True, symmetric=True)
+        assert rel_fro(sym.cpu(), A.double() @ A.double().t()) < tol
+        assert torch.equal(sym, sym.t())
+        assert (sym.diagonal() >= 0).all()
+
+
+def test_tensor_core_syrk_large_properties():
+    """BASELINE-size SYRK (d=4608, K=8192) through size-independent properties: symmetry, PSD diagonal,
+    trace == sum of squares, linearity in K (two halves add up to the whole)."""
+    torch.manual_seed(4)
+    d, Kc = 4608, 8192
+    X = torch.randn(Kc, d, device=DEV)
+    p = K.pack_rows(X, K.BF16X3)
+    H = torch.zeros(d, d, device=DEV)
+    K.gemm_nt(p, p, H, 1.0, True, symmetric=True)
+    assert torch.equal(H, H.t())
+    assert abs(float(H.diagonal().sum() / (X.double() ** 2).sum()) - 1) < 1e-5
+    H2 = torch.zeros(d, d, device=DEV)
+    for part in (X[:3000], X[3000:]):
+        pp = K.pack_rows(part.contiguous(), K.BF16X3)
+        K.gemm_nt(pp, pp, H2, 1.0, True, symmetric=True)
+    assert rel_fro(H2, H) < 1e-5
+    ref = X[:, :256].double().t() @ X.double()[:, 1000:1300]
+    assert rel_fro(H[:256, 1000:1300].double(), ref) < 3e-5
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("dims", [(4, 12, 4, 5, 2), (70, 100, 17, 3, 3), (64, 64, 64, 2, 1), (130, 27, 9, 6, 10)])
+def test_shared_weight_contract(mode, dims):
+    d_out, d_in, T, Nn, ncols = dims
+    torch.manual_seed(5)
+    G = ck._alloc(d_out, ncols * Nn * T, K.F32, None)
+    G.hi[:, :G.K] = torch.randn(d_out, G.K)
+    A = ck._alloc(d_in, Nn * T, K.F32, None)
+    A.hi[:, :A.K] = torch.randn(d_in, A.K)
+    Gd = K.Packed(G.hi.to(DEV), None, K.F32, G.rows, G.K)
+    Ad = K.Packed(A.hi.to(DEV), None, K.F32, A.rows, A.K)
+    if mode == 0:
+        ref = torch.zeros(d_out, d_in)
+        ck.shared_weight_contract(0, G, A, d_out, d_in, T, Nn, ncols, ref, scale=0.3)
+        out = torch.zeros(d_out, d_in, device=DEV)
+        K.shared_weight_contract(0, Gd, Ad, d_out, d_in, T, Nn, ncols, out, scale=0.3, out_ld=d_in)
+        assert rel_fro(out.cpu(), ref) < 1e-5
+    else:
+        P = d_out * d_in + 3
+        ref = torch.zeros(Nn, ncols, P)
+        ck.shared_weight_contract(1, G, A, d_out, d_in, T, Nn, ncols, ref[..., 2:], js_stride_n=ncols * P, js_stride_c=P)
+        out = torch.zeros(Nn, ncols, P, device=DEV)
+        K.shared_weight_contract(1, Gd, Ad, d_out, d_in, T, Nn, ncols, out[..., 2:], js_stride_n=ncols * P, js_stride_c=P)
+        assert rel_fro(out.cpu(), ref) < 1e-5
+
+
+def test_jacobian_writers_and_pair_dot():
+    torch.manual_seed(6)
+    C, Nn, d_out, d_in = 3, 5, 7, 11
+    g, a = torch.randn(C, Nn, d_out), torch.randn(Nn, d_in)
+    P = d_out * d_in + d_out + 4
+    ref = torch.zeros(Nn, C, P)
+    ck.jac_linear_write(g, a, ref, C * P, P, 4, 4 + d_out * d_in)
+    out = torch.zeros(Nn, C, P, device=DEV)
+    K.jac_linear_write(g.to(DEV), a.to(DEV), out, C * P, P, 4, 4 + d_out * d_in)
+    assert torch.allclose(out.cpu(), ref, atol=1e-6)
+    phi = torch.randn(6, 9)
+    for hb in (True, False):
+        assert torch.equal(K.ll_jacobian_write(phi.to(DEV), 4, hb).cpu(), ck.ll_jacobian_write(phi, 4, hb))
+    X, Z, m = torch.randn(Nn, C, 40), torch.randn(Nn, 2, 40), torch.rand(Nn, 40)
+    for mm in (None, m, m[0].contiguous()):
+        ref = ck.batched_pair_dot(X, Z, mm, torch.ones(Nn, C, 2), accumulate=True)
+        out = K.batched_pair_dot(X.to(DEV), Z.to(DEV), None if mm is None else mm.to(DEV), torch.ones(Nn, C, 2, device=DEV),
+                                 accumulate=True)
+        assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+    Xp = torch.randn(C, Nn, 40)  # permuted view (c-major storage)
+    ref = ck.batched_pair_dot(Xp.permute(1, 0, 2), Xp.permute(1, 0, 2), None, torch.zeros(Nn, C, C))
+    out = K.batched_pair_dot(Xp.to(DEV).permute(1, 0, 2), Xp.to(DEV).permute(1, 0, 2), None, torch.zeros(Nn, C, C, device=DEV))
+    assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,D,hb", [(2, 3, True), (3, 5, False), (10, 33, True)])
+def test_last_layer_block_kernels(C, D, hb):
+    torch.manual_seed(7)
+    Dt, npairs = D + int(hb), C * (C + 1) // 2
+    G = torch.randn(Dt, npairs * Dt)
+    P = C * D + (C if hb else 0)
+    ref = torch.ones(P, P)
+    ck.ll_ggn_expand(G, C, D, hb, ref, accumulate=True)
+    out = torch.ones(P, P, device=DEV)
+    K.ll_ggn_expand(G.to(DEV), C, D, hb, out, accumulate=True)
+    assert torch.allclose(out.cpu(), ref)
+    S = torch.randn(P, P)
+    assert torch.equal(K.ll_sigma_gather(S.to(DEV), C, D, hb).cpu(), ck.ll_sigma_gather(S, C, D, hb))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 20, 63, 64, 127, 128])
+def test_eigh_jacobi(n):
+    torch.manual_seed(8)
+    Z = torch.randn(4, n, 3 * n)
+    A = Z @ Z.transpose(1, 2) / (3 * n)
+    A[3] = torch.diag(torch.rand(n))            # already diagonal
+    if n > 2:
+        A[2, :, 0] = 0; A[2, 0, :] = 0          # a zero row/col (rank deficient)
+    ev, Q = K.eigh_jacobi(A.to(DEV))
+    ev, Q = ev.cpu().double(), Q.cpu().double()
+    ref = torch.linalg.eigvalsh(A.double()).clamp(min=0)
+    assert torch.allclose(ev, ref, rtol=1e-4, atol=1e-5 * float(ref.max()))
+    assert (ev[:, 1:] >= ev[:, :-1]).all()
+    rec = Q @ torch.diag_embed(ev) @ Q.transpose(1, 2)
+    assert rel_fro(rec, A) < 1e-5
+    assert rel_fro(Q.transpose(1, 2) @ Q, torch.eye(n).expand(4, n, n)) < 1e-5
+    # only the upper triangle is read (UPLO='U')
+    Au = A.clone(); Au[:, 1:, 0] = 123.0
+    ev2, _ = K.eigh_jacobi(Au.to(DEV))
+    assert torch.allclose(ev2.cpu().double(), ev, atol=1e-6)

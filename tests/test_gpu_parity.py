@@ -1,0 +1,185 @@
+"""Parity of the B200 backend (product path, through the C ABI) against the CPU oracle and the golden vectors
+of the unmodified reference, on the GPU.  Tolerances are BASELINE.json's: 1e-4 rel-fro on GGN/KFAC factors,
+1e-5 on predictive variances (relative to the largest variance)."""
+import pytest
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+from laplace_b200 import B200EF, B200GGN, B200Kron, models
+from laplace_b200.posterior import B200Laplace
+from oracle import curvature_oracle as co
+from oracle import kron_oracle as ko
+from tests.fixtures import load, rel_fro
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CASES = [(k, l) for k in ("mlp", "conv") for l in ("classification", "regression")]
+FACTOR_TOL, VAR_TOL = 1e-4, 1e-5
+
+
+def _to(model, X, y, dtype):
+    return model.to(DEV, dtype), X.to(DEV, dtype), (y.to(DEV) if y.dtype == torch.long else y.to(DEV, dtype))
+
+
+@pytest.mark.parametrize("kind,lik", CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("precision", ["auto", "fp32", "bf16x3"])
+def test_golden_jacobians_full_diag_ef(golden, kind, lik, dtype, precision):
+    model, X, y, rec = load(golden, kind, lik, dtype=dtype)
+    model, X, y = _to(model, X, y, dtype)
+    be = B200GGN(model, lik, precision=precision)
+    Js, f = be.jacobians(X)
+    assert Js.dtype == dtype and Js.is_cuda and rel_fro(Js.cpu(), rec["Js"]) < 1e-5
+    loss, H = be.full(X, y)
+    assert torch.allclose(loss.cpu().double(), rec["ggn_loss"], rtol=1e-5)
+    assert rel_fro(H.cpu(), rec["ggn_full"]) < FACTOR_TOL
+    _, d = be.diag(X, y)
+    assert rel_fro(d.cpu(), rec["ggn_diag"]) < FACTOR_TOL
+    ef = B200EF(model, lik, precision=precision)
+    Gs, gl = ef.gradients(X, y)
+    assert rel_fro(Gs.cpu(), rec["Gs"]) < 1e-5 and torch.allclose(gl.cpu().double(), rec["grad_loss"], rtol=1e-5)
+    loss, Hef = ef.full(X, y)
+    assert torch.allclose(loss.cpu().double(), rec["ef_loss"], rtol=1e-5)
+    if "ef_full" in rec:
+        assert rel_fro(Hef.cpu(), rec["ef_full"]) < FACTOR_TOL
+    _, de = ef.diag(X, y)
+    assert rel_fro(de.cpu(), rec["ef_diag"]) < FACTOR_TOL
+
+
+@pytest.mark.parametrize("kind,lik", CASES)
+@pytest.mark.parametrize("approx", ["expand", "reduce"])
+@pytest.mark.parametrize("precision", ["auto", "fp32", "bf16x3"])
+def test_kfac_vs_oracle(golden, kind, lik, approx, precision):
+    model, X, y, _ = load(golden, kind, lik)
+    N = 3 * len(X)
+    loss_o, kf_o = co.kfac_factors(model, lik, X, y, N=N, kfac_approx=approx)
+    _, kf_e = co.kfac_factors(model, lik, X, y, N=N, fisher="empirical", kfac_approx=approx)
+    model, X, y = _to(model, X, y, torch.float32)
+    loss, kron = B200GGN(model, lik, precision=precision).kron(X, y, N=N, kfac_approx=approx)
+    assert isinstance(kron, B200Kron) and torch.allclose(loss.cpu().double(), loss_o, rtol=1e-5)
+    for F, Fo in zip(kron.kfacs, kf_o):
+        assert len(F) == len(Fo)
+        for H, Ho in zip(F, Fo):
+            assert H.is_cuda and rel_fro(H.cpu(), Ho) < FACTOR_TOL
+    _, kron = B200EF(model, lik, precision=precision).kron(X, y, N=N, kfac_approx=approx)
+    for F, Fo in zip(kron.kfacs, kf_e):
+        for H, Ho in zip(F, Fo):
+            assert rel_fro(H.cpu(), Ho) < FACTOR_TOL
+
+
+@pytest.mark.parametrize("name,kw,B", [("mlp", {}, 256), ("resnet18", {"width": 16}, 64), ("wrn28_10", {"depth": 10, "widen": 2}, 32),
+                                       ("vit_b16", {"image": 32, "patch": 8, "dim": 64, "depth": 2, "heads": 4, "mlp_dim": 128}, 16)])
+@pytest.mark.parametrize("precision", ["auto", "bf16x3"])
+def test_kfac_model_zoo_vs_oracle(name, kw, B, precision):
+    """Reduced-width versions of every BASELINE config shape (the oracle needs seconds on CPU), batched over two
+    batches so that the tensor-core path (K >= 256 rows) and the accumulation across batches are exercised."""
+    model = models.make(name, **kw)
+    torch.manual_seed(1)
+    shape = (784,) if name == "mlp" else (3, 32, 32)
+    X, y = torch.randn(2 * B, *shape), torch.randint(10, (2 * B,))
+    ref = None
+    md = model.double()
+    for i in (0, B):
+        _, kf = co.kfac_factors(md, "classification", X[i:i + B].double(), y[i:i + B], N=2 * B)
+        ref = kf if ref is None else [[a + b for a, b in zip(Fa, Fb)] for Fa, Fb in zip(ref, kf)]
+    model = model.float().to(DEV)
+    be = B200GGN(model, "classification", precision=precision)
+    H = None
+    for i in (0, B):
+        _, kr = be.kron(X[i:i + B].to(DEV), y[i:i + B].to(DEV), N=2 * B)
+        if H is None:
+            H = kr
+        else:
+            H += kr
+    worst = max(rel_fro(h.cpu(), ho) for F, Fo in zip(H.kfacs, ref) for h, ho in zip(F, Fo))
+    assert worst < FACTOR_TOL, worst
+
+
+def test_kfac_invariants_at_scale():
+    """Reference invariants (tests/test_curv_backends_curvlinops.py:207-333) at a size the oracle cannot reach:
+    batch additivity, 7x normalisation, symmetry / PSD of every factor, on the full-width ResNet-18 shape."""
+    model = models.make("resnet18").to(DEV)
+    torch.manual_seed(2)
+    X, y = torch.randn(96, 3, 32, 32, device=DEV), torch.randint(10, (96,), device=DEV)
+    be = B200GGN(model, "classification", precision="bf16x3")
+    _, whole = be.kron(X, y, N=96)
+    _, a = be.kron(X[:40], y[:40], N=96)
+    _, b = be.kron(X[40:], y[40:], N=96)
+    parts = a + b
+    for Fw, Fp in zip(whole.kfacs, parts.kfacs):
+        for hw, hp in zip(Fw, Fp):
+            assert rel_fro(hp, hw) < 1e-4
+            assert torch.equal(hw, hw.t()) and float(hw.diagonal().min()) >= 0
+    _, k7 = be.kron(X[:16].repeat(7, 1, 1, 1), y[:16].repeat(7), N=7 * 16)
+    _, k1 = be.kron(X[:16], y[:16], N=16)
+    assert rel_fro(k7.diag(), 7 * k1.diag()) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["mlp", "conv"])
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_kron_posterior_predictive(golden, kind, lik):
+    model, X, y, _ = load(golden, kind, lik)
+    kfs = None
+    for i in range(0, len(X), 5):
+        _, kf = co.kfac_factors(model, lik, X[i:i + 5], y[i:i + 5], N=len(X))
+        kfs = kf if kfs is None else [[a + b for a, b in zip(Fa, Fb)] for Fa, Fb in zip(kfs, kf)]
+    Qs, ls = ko.decompose(kfs)
+    Js, f = co.jacobians(model, X)
+    delta = torch.tensor(0.7, dtype=torch.float64)
+    ref = ko.kron_inv_square_form(Qs, ls, delta, Js)
+    model, Xd, yd = _to(model, X, y, torch.float32)
+    la = B200Laplace(model, lik, "all", "kron", prior_precision=0.7).fit(DataLoader(TensorDataset(Xd, yd), batch_size=5))
+    f_mu, f_var = la.glm_predictive_distribution(Xd)
+    assert torch.allclose(f_mu.cpu().double(), f, atol=1e-5)
+    assert float((f_var.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+    assert torch.allclose(la.log_det_posterior_precision.cpu().double(), ko.kron_logdet(ls, delta), rtol=1e-4)
+    # dense (factor-free) route through the rotation GEMMs gives the same variances
+    Jd, _ = la.backend.jacobians(Xd)
+    dense = la.posterior_precision.inv_square_form(Jd.clone())
+    assert float((dense.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+
+
+@pytest.mark.parametrize("hs", ["full", "diag"])
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_full_diag_posterior_vs_golden(golden, hs, lik):
+    model, X, y, rec = load(golden, "mlp", lik, dtype=torch.float32)
+    model, X, y = _to(model, X, y, torch.float32)
+    la = B200Laplace(model, lik, "all", hs, prior_precision=0.7).fit(DataLoader(TensorDataset(X, y), batch_size=4))
+    f_mu, f_var = la.glm_predictive_distribution(X)
+    ref = rec[f"la_{hs}_f_var"]
+    assert float((f_var.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+    if lik == "classification":
+        assert torch.allclose(la(X).cpu().double(), rec[f"la_{hs}_probit"], atol=1e-5)
+
+
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_last_layer_full_vs_golden(golden, lik):
+    model, X, y, rec = load(golden, "mlp", lik, dtype=torch.float32)
+    model, X, y = _to(model, X, y, torch.float32)
+    la = B200Laplace(model, lik, "last_layer", "full", prior_precision=0.7).fit(DataLoader(TensorDataset(X, y), batch_size=4))
+    assert rel_fro(la.H.cpu(), rec["ll_ggn_full"]) < FACTOR_TOL
+    Js, f = la.backend.last_layer_jacobians(X)
+    assert torch.allclose(Js.cpu().double(), rec["ll_Js"], atol=1e-6)
+    f_mu, f_var = la.glm_predictive_distribution(X)
+    Sigma = ko.full_posterior_covariance(rec["ll_ggn_full"], torch.full((la.n_params,), 0.7, dtype=torch.float64))
+    ref = ko.full_functional_variance(rec["ll_Js"], Sigma)
+    assert float((f_var.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+    ef = B200Laplace(model, lik, "last_layer", "full", backend=B200EF).fit(DataLoader(TensorDataset(X, y), batch_size=4))
+    Gs, fr = co.gradients(rec["ll_Js"], rec["ll_f"], rec["y"], lik)
+    fac = co.likelihood_factor(lik)
+    assert rel_fro(ef.H.cpu(), fac * Gs.T @ Gs) < FACTOR_TOL
+
+
+def test_last_layer_full_resnet_structured_vs_dense():
+    """Config-3 shape (ResNet-18, last layer 512->10, P=5130): structured GGN == dense J^T L J built from the
+    materialised last-layer Jacobians (fp64 on CPU)."""
+    model = models.make("resnet18").to(DEV)
+    torch.manual_seed(3)
+    X, y = torch.randn(64, 3, 32, 32, device=DEV), torch.randint(10, (64,), device=DEV)
+    la = B200Laplace(model, "classification", "last_layer", "full")
+    loss, H = la.backend.full(X, y)
+    Js, f = la.backend.last_layer_jacobians(X)
+    _, Href = co.ggn_full(Js.cpu().double(), f.cpu().double(), y.cpu(), "classification")
+    assert H.shape == (5130, 5130) and rel_fro(H.cpu(), Href) < FACTOR_TOL
+    _, d = la.backend.diag(X, y)
+    assert rel_fro(d.cpu(), Href.diagonal()) < FACTOR_TOL
