@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-samples", type=int, default=256, help="samples of the bounded CPU-baseline run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--predictive", action="store_true", help="also time the GLM predictive (reported under config)")
+    ap.add_argument("--model-tf32", action="store_true", help="let cuDNN/cuBLAS use TF32 in the model's own passes")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = min(cores, 32))")
     return ap.parse_args()
 
 
@@ -118,7 +120,7 @@ def cpu_reference_run(args, steps, warmup, samples_per_step):
     oracle PORT of CurvlinopsGGN.kron (oracle/curvature_oracle.py:kfac_factors) with all host threads."""
     from oracle import curvature_oracle as co
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads(args))
     model = make_model(args.model)
     torch.manual_seed(1)
     X = torch.randn(samples_per_step, *input_shape(args.model))
@@ -135,14 +137,20 @@ def cpu_reference_run(args, steps, warmup, samples_per_step):
     return steps * samples_per_step / total, total / steps * 1e3
 
 
+def cpu_threads(args):
+    """Threads of the CPU arm: more than ~32 threads make the many small ops of the per-class reverse passes
+    slower, not faster (measured on the 128-core GPU host); the count actually used is reported as `cores`."""
+    return args.cpu_threads if args.cpu_threads > 0 else min(os.cpu_count() or 1, 32)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    spp = max(16, args.cpu_samples // 4)
+    spp = 128
     steps, warmup = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
     v, ms = cpu_reference_run(args, steps, warmup, spp)
-    cores = os.cpu_count() or 1
+    cores = cpu_threads(args)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -184,7 +192,7 @@ def run_ours(args):
     B, Ksteps, W = args.batch, args.steps, max(3, args.warmup)
     N_total = 50000
     model = make_model(args.model).to(dev)
-    be = B200GGN(model, "classification", precision=args.precision)
+    be = B200GGN(model, "classification", precision=args.precision, model_tf32=args.model_tf32)
     shape = input_shape(args.model)
     torch.manual_seed(1 + rank)
     n_batches = min(8, W + Ksteps)  # pool of distinct batches; factor buffers (376 MB) dwarf the 126 MB L2 anyway
@@ -214,12 +222,12 @@ def run_ours(args):
         else:
             H += kr
 
-    for i in range(W):
-        step(i)
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for i in range(W):
+        step(i)
+    barrier()
     l0 = K.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -256,7 +264,7 @@ def run_ours(args):
                 j = (self.off + i) % n_batches
                 yield Xh[j], yh[j]
 
-    la = B200Laplace(model, "classification", "all", "kron", backend=B200GGN, backend_kwargs={"precision": args.precision})
+    la = B200Laplace(model, "classification", "all", "kron", backend=B200GGN, backend_kwargs={"precision": args.precision, "model_tf32": args.model_tf32})
     la.fit(HostLoader(W, 0), decompose=False)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -282,10 +290,10 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, ms = cpu_reference_run(args, 2, 1, max(16, args.cpu_samples // 4))
-            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"2 steps x {max(16, args.cpu_samples // 4)} samples of the same workload (oracle port of "
-                             "CurvlinopsGGN.kron, all host threads)"}
+            v, ms = cpu_reference_run(args, 2, 1, 128)
+            cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(args), "kind": "port",
+                   "sample": "2 steps x 128 samples of the same workload (oracle port of CurvlinopsGGN.kron, "
+                             f"{cpu_threads(args)} torch threads of {os.cpu_count()} host cores)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ksteps, "warmup": W,
             "ms_per_step": ms_total / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -294,6 +302,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "batch_per_gpu": B, "global_batch": B * world, "N_dataset": N_total,
                        "parallelism": f"dp{world}", "precision": args.precision,
+                       "model_passes": "tf32 (PyTorch default)" if args.model_tf32 else "fp32 (TF32 disabled in cuDNN/cuBLAS)",
                        "l2": "distinct batch every step; per-step working set (factor buffers 376 MB + staging) exceeds the 126 MB L2",
                        "exchange": "one all-reduce of the flat factor buffer after the K steps, inside the timed region",
                        **extras},

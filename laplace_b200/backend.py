@@ -53,14 +53,28 @@ class _Layer:
             self.d_in, self.d_out = mod.in_features, mod.out_features
 
 
+class _Fp32Model:
+    """Context manager: disable TF32 in cuDNN convolutions and cuBLAS matmuls for the enclosed model passes."""
+
+    def __enter__(self):
+        self._c, self._m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self._c, self._m
+        return False
+
+
 class _B200Mixin:
     """Shared machinery of the GGN and EF flavours."""
 
-    def _b200_init(self, precision: str = "auto", batched_backward: bool = True):
+    def _b200_init(self, precision: str = "auto", batched_backward: bool = True, model_tf32: bool = False):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
         self.batched_backward = batched_backward
+        self.model_tf32 = model_tf32
         self._layers: list[_Layer] | None = None
         self._unsupported: list[str] = []
         self._hooks = []
@@ -127,7 +141,7 @@ class _B200Mixin:
         self._acts, self._outs = {}, {}
         self._capturing = True
         try:
-            with torch.enable_grad():
+            with torch.enable_grad(), self._model_numerics():
                 f = self.model(x)
         finally:
             self._capturing = False
@@ -136,7 +150,20 @@ class _B200Mixin:
         self._device_check(f)
         return f
 
+    def _model_numerics(self):
+        """The network's own forward/reverse passes run in true fp32 unless ``model_tf32=True``: PyTorch's default
+        lets cuDNN use TF32 for convolutions, which perturbs Jacobians by ~1e-3 -- far above the 1e-4 parity gate."""
+        import contextlib
+
+        if self.model_tf32:
+            return contextlib.nullcontext()
+        return _Fp32Model()
+
     def _backward(self, f: torch.Tensor, cols: torch.Tensor) -> list[torch.Tensor]:
+        with self._model_numerics():
+            return self._backward_impl(f, cols)
+
+    def _backward_impl(self, f: torch.Tensor, cols: torch.Tensor) -> list[torch.Tensor]:
         """Gradients of ``sum_n <cols[j, n], f[n]>`` w.r.t. every captured layer output, for all ``j`` at once.
         Returns one fp32 tensor ``[ncols, M, ...]`` per planned layer."""
         outs = [self._outs[L.name] for L in self._layers]
@@ -366,7 +393,7 @@ class _B200Mixin:
         """``CurvatureInterface.last_layer_jacobians`` (curvature/curvature.py:131-167)."""
         if enable_backprop:
             return self._reference_fallback("last_layer_jacobians", x, enable_backprop=True)
-        with torch.no_grad():
+        with torch.no_grad(), self._model_numerics():
             f, phi = self.model.forward_with_features(x)
         self._device_check(f)
         C = int(f.numel() / phi.shape[0])
@@ -405,7 +432,7 @@ class _B200Mixin:
 
     # ------------------------------------------------------------------ last-layer structured curvature
     def _ll_forward(self, x):
-        with torch.no_grad():
+        with torch.no_grad(), self._model_numerics():
             f, phi = self.model.forward_with_features(x)
         self._device_check(f)
         if f.ndim != 2 or phi.ndim != 2:
@@ -461,10 +488,11 @@ class B200GGN(_B200Mixin, GGNInterface):
     """
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
-                 dict_key_y="labels", stochastic=False, num_samples=1, precision="auto", batched_backward=True):
+                 dict_key_y="labels", stochastic=False, num_samples=1, precision="auto", batched_backward=True,
+                 model_tf32=False):
         GGNInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y,
                               stochastic, num_samples)
-        self._b200_init(precision, batched_backward)
+        self._b200_init(precision, batched_backward, model_tf32)
 
     def _ggn_cols(self, f, y=None):
         return self._mc_cols(f, self.num_samples) if self.stochastic else self._hessian_sqrt_cols(f)
@@ -558,9 +586,9 @@ class B200EF(_B200Mixin, EFInterface):
     """Empirical Fisher on B200 (drop-in for ``CurvlinopsEF``, curvature/curvlinops.py:171-180)."""
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
-                 dict_key_y="labels", precision="auto", batched_backward=True):
+                 dict_key_y="labels", precision="auto", batched_backward=True, model_tf32=False):
         EFInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y)
-        self._b200_init(precision, batched_backward)
+        self._b200_init(precision, batched_backward, model_tf32)
 
     def kron(self, x, y, N, **kwargs: Any):
         """``CurvlinopsInterface.kron`` with ``FisherType.EMPIRICAL`` (curvature/curvlinops.py:174-176)."""

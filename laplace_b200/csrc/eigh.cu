@@ -43,10 +43,13 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(const float* __restric
         const float app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
         float c = 1.f, s = 0.f;
         if (fabsf(apq) > 1e-30f && fabsf(apq) > 6e-8f * sqrtf(fabsf(app * aqq))) {
-          const float tau = (aqq - app) / (2.f * apq);
-          const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-          c = rsqrtf(1.f + t * t);
-          s = t * c;
+          // angles in double: a float rsqrt leaves c^2 + s^2 = 1 +- 1e-7 with a systematic sign, which
+          // compounds over the ~2n rotations that touch every element per sweep
+          const double tau = ((double)aqq - (double)app) / (2.0 * (double)apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          const double cd = 1.0 / sqrt(1.0 + t * t);
+          c = (float)cd;
+          s = (float)(t * cd);
           rotated = 1;
         }
         cs[2 * tid] = c; cs[2 * tid + 1] = s;

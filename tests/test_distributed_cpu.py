@@ -1,0 +1,61 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: sharded fit + one all-reduce == single-process fit."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch.utils.data import DataLoader, TensorDataset
+
+
+class _Patch:
+    def setattr(self, obj, name, val):
+        setattr(obj, name, val)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from laplace_b200.distributed import ShardedLoader, fit_distributed
+    from laplace_b200.posterior import B200Laplace
+    from tests import cpu_kernels as ck
+
+    ck.install(_Patch())
+    torch.manual_seed(711)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 2, 2), torch.nn.Flatten(), torch.nn.Tanh(), torch.nn.Linear(16, 2))
+    X, y = torch.randn(22, 3, 5, 5), torch.randint(2, (22,))
+    loader = DataLoader(TensorDataset(X, y), batch_size=4)
+    assert len(ShardedLoader(loader, rank, world).dataset) == 22
+    res = {}
+    for hs in ("kron", "full", "diag"):
+        la = fit_distributed(B200Laplace(model, "classification", "all", hs), loader)
+        H = la.H_facs.to_matrix() if hs == "kron" else la.H
+        res[hs] = (H.clone(), torch.as_tensor(la.loss).clone())
+    if rank == 0:
+        torch.save(res, out_path)
+    dist.destroy_process_group()
+
+
+def test_sharded_fit_equals_single_process(tmp_path, cpu_kernels):
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    from laplace_b200.posterior import B200Laplace
+
+    torch.manual_seed(711)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 2, 2), torch.nn.Flatten(), torch.nn.Tanh(), torch.nn.Linear(16, 2))
+    X, y = torch.randn(22, 3, 5, 5), torch.randint(2, (22,))
+    loader = DataLoader(TensorDataset(X, y), batch_size=4)
+    for hs in ("kron", "full", "diag"):
+        la = B200Laplace(model, "classification", "all", hs).fit(loader)
+        H = la.H_facs.to_matrix() if hs == "kron" else la.H
+        assert torch.allclose(res[hs][0], H, rtol=1e-5, atol=1e-7), hs
+        assert torch.allclose(res[hs][1], torch.as_tensor(la.loss), rtol=1e-5)

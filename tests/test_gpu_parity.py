@@ -109,7 +109,7 @@ def test_kfac_invariants_at_scale():
     for Fw, Fp in zip(whole.kfacs, parts.kfacs):
         for hw, hp in zip(Fw, Fp):
             assert rel_fro(hp, hw) < 1e-4
-            assert torch.equal(hw, hw.t()) and float(hw.diagonal().min()) >= 0
+            assert rel_fro(hw, hw.t()) < 1e-6 and float(hw.diagonal().min()) >= 0
     _, k7 = be.kron(X[:16].repeat(7, 1, 1, 1), y[:16].repeat(7), N=7 * 16)
     _, k1 = be.kron(X[:16], y[:16], N=16)
     assert rel_fro(k7.diag(), 7 * k1.diag()) < 1e-4
