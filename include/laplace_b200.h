@@ -59,6 +59,22 @@ int lpb_pack_conv2d_t(const float* x, int N, int C, int H, int W, int KH, int KW
 int lpb_pack_nchw_t(const float* g, int64_t Nn, int Cc, int HW, float scale, int flags, int reduce_sum, void* dst_hi,
                     void* dst_lo, int out_kind, int64_t ldk, int64_t k0, void* stream);
 
+/* ---- convolution engine operands (forward / backward-data of nn.Conv2d as GEMMs) ----------
+ * Replaces the model-side torch.func / autograd convolution passes the reference runs below
+ * CurvatureInterface.jacobians (curvature/curvature.py:111-117) when fp32-accurate Jacobians are required. */
+/* patch-major im2col: x [N,C,H,W] -> dst[(n,oh,ow), (ci,kh,kw)], row stride ld                      */
+int lpb_pack_conv2d_rows(const float* x, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int DH,
+                         int DW, void* dst_hi, void* dst_lo, int out_kind, int64_t ld, void* stream);
+/* g [Q, Cc, HW] -> dst[(q,hw), ch], row stride ld (channel index contiguous)                            */
+int lpb_pack_nchw_rows(const float* g, int64_t Q, int Cc, int HW, void* dst_hi, void* dst_lo, int out_kind, int64_t ld,
+                       void* stream);
+/* src [rows, cols] fp32 (ld_src) -> same layout in out_kind (row stride ld)                               */
+int lpb_pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst_hi, void* dst_lo, int out_kind,
+                  int64_t ld, void* stream);
+/* col2im gather: Dc [(ci,kh,kw), ldd] with columns (q,oh,ow) -> grad_in [Q, C, H, W] (overwrites)        */
+int lpb_col2im(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,
+               int DH, int DW, float* grad_in, void* stream);
+
 /* ---- contractions ------------------------------------------------------------------------
  * D[M, N] (fp32, ldd)  (+)=  alpha * A[M, K] * B[N, K]^T   on K-major operands.
  * symmetric != 0 (requires A == B, M == N): SYRK -- only tiles on/above the diagonal are

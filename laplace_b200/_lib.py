@@ -20,6 +20,10 @@ SIGNATURES = {
     "lpb_pack_rows_t": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
     "lpb_pack_conv2d_t": [c_vp] + [c_int] * 12 + [c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
     "lpb_pack_nchw_t": [c_vp, c_i64, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
+    "lpb_pack_conv2d_rows": [c_vp] + [c_int] * 12 + [c_vp, c_vp, c_int, c_i64, c_vp],
+    "lpb_pack_nchw_rows": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_vp],
+    "lpb_pack_cast": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_i64, c_vp],
+    "lpb_col2im": [c_vp, c_i64] + [c_int] * 12 + [c_vp, c_vp],
     "lpb_gemm_nt_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_vp],
     "lpb_gemm_nt_bf16": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int,
                          c_vp],

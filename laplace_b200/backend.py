@@ -69,12 +69,14 @@ class _Fp32Model:
 class _B200Mixin:
     """Shared machinery of the GGN and EF flavours."""
 
-    def _b200_init(self, precision: str = "auto", batched_backward: bool = True, model_tf32: bool = False):
+    def _b200_init(self, precision: str = "auto", batched_backward: bool = True, model_tf32: bool = False,
+                   conv_engine: bool = True):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
         self.batched_backward = batched_backward
         self.model_tf32 = model_tf32
+        self.conv_engine = conv_engine and not model_tf32
         self._layers: list[_Layer] | None = None
         self._unsupported: list[str] = []
         self._hooks = []
@@ -141,7 +143,7 @@ class _B200Mixin:
         self._acts, self._outs = {}, {}
         self._capturing = True
         try:
-            with torch.enable_grad(), self._model_numerics():
+            with torch.enable_grad(), self._model_numerics(), self._conv_patch():
                 f = self.model(x)
         finally:
             self._capturing = False
@@ -149,6 +151,17 @@ class _B200Mixin:
             raise ValueError(f"the B200 backend supports (batch, outputs) model outputs, got shape {tuple(f.shape)}")
         self._device_check(f)
         return f
+
+    def _conv_patch(self):
+        """fp32-accurate convolution passes on the tensor cores (laplace_b200/conv_engine.py) instead of cuDNN's
+        fp32 fallback kernels; ``conv_engine=False`` keeps the model's own convolution implementation."""
+        import contextlib
+
+        if not self.conv_engine:
+            return contextlib.nullcontext()
+        from .conv_engine import patched_convs
+
+        return patched_convs(self.model)
 
     def _model_numerics(self):
         """The network's own forward/reverse passes run in true fp32 unless ``model_tf32=True``: PyTorch's default
@@ -171,10 +184,19 @@ class _B200Mixin:
         grads = None
         if self.batched_backward and cols.shape[0] > 1:
             try:
-                grads = torch.autograd.grad(f, outs, grad_outputs=cols, is_grads_batched=True, retain_graph=True,
-                                            allow_unused=True)
-            except (RuntimeError, NotImplementedError):
+                if self.conv_engine:
+                    # functorch vmap over autograd.grad: custom Functions fold the column dim into the batch
+                    def one(col):
+                        return torch.autograd.grad(f, outs, grad_outputs=col, retain_graph=True, allow_unused=True)
+
+                    grads = torch.func.vmap(one)(cols)
+                else:
+                    grads = torch.autograd.grad(f, outs, grad_outputs=cols, is_grads_batched=True, retain_graph=True,
+                                                allow_unused=True)
+                self.last_backward_mode = "batched"
+            except (RuntimeError, NotImplementedError) as e:
                 grads = None  # an op without a batching rule: fall back to one reverse pass per column
+                self.last_backward_mode = f"loop ({type(e).__name__}: {str(e)[:120]})"
         if grads is None:
             per = []
             for j in range(cols.shape[0]):
@@ -489,10 +511,10 @@ class B200GGN(_B200Mixin, GGNInterface):
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
                  dict_key_y="labels", stochastic=False, num_samples=1, precision="auto", batched_backward=True,
-                 model_tf32=False):
+                 model_tf32=False, conv_engine=True):
         GGNInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y,
                               stochastic, num_samples)
-        self._b200_init(precision, batched_backward, model_tf32)
+        self._b200_init(precision, batched_backward, model_tf32, conv_engine)
 
     def _ggn_cols(self, f, y=None):
         return self._mc_cols(f, self.num_samples) if self.stochastic else self._hessian_sqrt_cols(f)
@@ -586,9 +608,9 @@ class B200EF(_B200Mixin, EFInterface):
     """Empirical Fisher on B200 (drop-in for ``CurvlinopsEF``, curvature/curvlinops.py:171-180)."""
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
-                 dict_key_y="labels", precision="auto", batched_backward=True, model_tf32=False):
+                 dict_key_y="labels", precision="auto", batched_backward=True, model_tf32=False, conv_engine=True):
         EFInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y)
-        self._b200_init(precision, batched_backward, model_tf32)
+        self._b200_init(precision, batched_backward, model_tf32, conv_engine)
 
     def kron(self, x, y, N, **kwargs: Any):
         """``CurvlinopsInterface.kron`` with ``FisherType.EMPIRICAL`` (curvature/curvlinops.py:174-176)."""

@@ -33,6 +33,10 @@ int pack_rows_t(const float*, int64_t, int64_t, int64_t, const float*, int, floa
                 int64_t, cudaStream_t);
 int pack_conv2d_t(const float*, const ConvGeom&, float, int, int, void*, void*, int, int64_t, int64_t, cudaStream_t);
 int pack_nchw_t(const float*, int64_t, int, int, float, int, int, void*, void*, int, int64_t, int64_t, cudaStream_t);
+int pack_conv2d_rows(const float*, const ConvGeom&, void*, void*, int, int64_t, cudaStream_t);
+int pack_nchw_rows(const float*, int64_t, int, int, void*, void*, int, int64_t, cudaStream_t);
+int pack_cast(const float*, int64_t, int64_t, int64_t, void*, void*, int, int64_t, cudaStream_t);
+int col2im(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
 int gemm_nt_f32(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float, int, float*, int64_t, int,
                 cudaStream_t);
 int gemm_nt_bf16(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
@@ -102,6 +106,45 @@ int lpb_pack_nchw_t(const float* g, int64_t Nn, int Cc, int HW, float scale, int
   const int64_t K = reduce_sum ? Nn : Nn * HW;
   LPB_REQUIRE(k0 >= 0 && k0 + K <= ldk, "lpb_pack_nchw_t: rows exceed ldk");
   return lpb::pack_nchw_t(g, Nn, Cc, HW, scale, flags, reduce_sum, dst_hi, dst_lo, out_kind, ldk, k0, ST(stream));
+}
+
+static int make_geom(lpb::ConvGeom& g, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int DH,
+                     int DW) {
+  LPB_REQUIRE(N >= 0 && C > 0 && H > 0 && W > 0 && KH > 0 && KW > 0 && SH > 0 && SW > 0 && DH > 0 && DW > 0,
+              "bad convolution geometry");
+  g = lpb::ConvGeom{N, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW, 0, 0};
+  g.OH = (H + 2 * PH - DH * (KH - 1) - 1) / SH + 1;
+  g.OW = (W + 2 * PW - DW * (KW - 1) - 1) / SW + 1;
+  LPB_REQUIRE(g.OH > 0 && g.OW > 0, "empty convolution output");
+  return 0;
+}
+
+int lpb_pack_conv2d_rows(const float* x, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int DH,
+                         int DW, void* dst_hi, void* dst_lo, int out_kind, int64_t ld, void* stream) {
+  lpb::ConvGeom g;
+  if (make_geom(g, N, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW)) return 1;
+  LPB_REQUIRE(ld >= (int64_t)C * KH * KW, "lpb_pack_conv2d_rows: ld too small");
+  return lpb::pack_conv2d_rows(x, g, dst_hi, dst_lo, out_kind, ld, ST(stream));
+}
+
+int lpb_pack_nchw_rows(const float* g, int64_t Q, int Cc, int HW, void* dst_hi, void* dst_lo, int out_kind, int64_t ld,
+                       void* stream) {
+  LPB_REQUIRE(Q >= 0 && Cc > 0 && HW > 0 && ld >= Cc, "lpb_pack_nchw_rows: bad extents");
+  return lpb::pack_nchw_rows(g, Q, Cc, HW, dst_hi, dst_lo, out_kind, ld, ST(stream));
+}
+
+int lpb_pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst_hi, void* dst_lo, int out_kind,
+                  int64_t ld, void* stream) {
+  LPB_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld >= cols, "lpb_pack_cast: bad extents");
+  return lpb::pack_cast(src, rows, cols, ld_src, dst_hi, dst_lo, out_kind, ld, ST(stream));
+}
+
+int lpb_col2im(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,
+               int DH, int DW, float* grad_in, void* stream) {
+  lpb::ConvGeom g;
+  if (make_geom(g, Q, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW)) return 1;
+  LPB_REQUIRE(ldd >= (int64_t)Q * g.OH * g.OW, "lpb_col2im: ldd too small");
+  return lpb::col2im(Dc, ldd, g, grad_in, ST(stream));
 }
 
 int lpb_gemm_nt_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int M, int N,
                   float alpha, float* __restrict__ D, int64_t ldd, int symmetric, int tiles_m, int tiles_n,
-                  int total_kchunks, int kchunks_per_split, int num_stages) {
+                  int total_kchunks, int kchunks_per_split, int num_stages, int store_mode) {
   constexpr int TILES_PER_STAGE = NPROD == 3 ? 4 : 2;
   constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -132,6 +132,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   } else {
     tm = blockIdx.x / tiles_n; tn = blockIdx.x % tiles_n;
   }
+  const bool diag = symmetric && (tm == tn);
   const int kc_begin = blockIdx.y * kchunks_per_split;
   const int kc_end = min(total_kchunks, kc_begin + kchunks_per_split);
   if (kc_begin >= kc_end) return;
@@ -160,12 +161,13 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       for (int kc = kc_begin; kc < kc_end; ++kc) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        // diagonal SYRK tiles use the A tile for both operands: half the TMA traffic
+        mbar_expect_tx(&full_bar[stage], diag ? STAGE_BYTES / 2 : STAGE_BYTES);
         tma_load_2d(&tmA_hi, &full_bar[stage], st, kc * BK, tm * BM);
-        tma_load_2d(&tmB_hi, &full_bar[stage], st + TILE_BYTES, kc * BK, tn * BN);
+        if (!diag) tma_load_2d(&tmB_hi, &full_bar[stage], st + TILE_BYTES, kc * BK, tn * BN);
         if (NPROD == 3) {
           tma_load_2d(&tmA_lo, &full_bar[stage], st + 2 * TILE_BYTES, kc * BK, tm * BM);
-          tma_load_2d(&tmB_lo, &full_bar[stage], st + 3 * TILE_BYTES, kc * BK, tn * BN);
+          if (!diag) tma_load_2d(&tmB_lo, &full_bar[stage], st + 3 * TILE_BYTES, kc * BK, tn * BN);
         }
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
@@ -179,14 +181,15 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + TILE_BYTES);
+        const uint64_t a_hi = make_smem_desc(sbase), b_hi = diag ? a_hi : make_smem_desc(sbase + TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
           umma_f16(tmem_base, a_hi + koff, b_hi + koff, idesc, acc);
           acc = 1;
           if (NPROD == 3) {
-            const uint64_t a_lo = make_smem_desc(sbase + 2 * TILE_BYTES), b_lo = make_smem_desc(sbase + 3 * TILE_BYTES);
+            const uint64_t a_lo = make_smem_desc(sbase + 2 * TILE_BYTES);
+            const uint64_t b_lo = diag ? a_lo : make_smem_desc(sbase + 3 * TILE_BYTES);
             umma_f16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
             umma_f16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);
           }
@@ -211,7 +214,18 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const int col0 = tn * BN + chunk * 32;
       if (row < M) {
         float* drow = D + (int64_t)row * ldd + col0;
-        if (vec_ok && col0 + 32 <= N) {
+        if (store_mode) {
+          // single split, overwrite semantics: plain (vector) stores, no atomics, no pre-zeroing
+          if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(drow + j) = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) drow[j] = alpha * v[j];
+          }
+        } else if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) red_add_v4(drow + j, alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
         } else {
@@ -280,7 +294,13 @@ int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_
                   ((uintptr_t)B_lo % 16) == 0,
               "gemm_nt_bf16: operands must be 16-byte aligned");
   if (M == 0 || N == 0) return 0;
-  if (!accumulate) {
+  const int tiles_m = (int)ceil_div(M, tc::BM), tiles_n = (int)ceil_div(N, tc::BN);
+  const int64_t tiles = symmetric ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
+  const int total_kchunks = (int)ceil_div(K, tc::BK);
+  const int sms = sm_count();
+  // overwrite + enough tiles (or a short K): one split per tile with plain stores
+  const bool store_mode = !accumulate && !symmetric && K > 0 && (tiles >= sms / 2 || total_kchunks <= 16) && total_kchunks <= 128;
+  if (!accumulate && !store_mode) {
     if (check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, N * sizeof(float), M, st), "gemm_nt_bf16 memset"))
       return 1;
   }
@@ -293,14 +313,15 @@ int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_
   } else {
     tA_lo = tA_hi; tB_lo = tB_hi;
   }
-  const int tiles_m = (int)ceil_div(M, tc::BM), tiles_n = (int)ceil_div(N, tc::BN);
-  const int64_t tiles = symmetric ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
-  const int total_kchunks = (int)ceil_div(K, tc::BK);
-  // split K so that about two CTAs per SM exist while each CTA keeps >= 4 k-chunks
-  const int sms = sm_count();
+  // split K so that about two CTAs per SM exist while each CTA keeps >= 4 k-chunks; never accumulate more
+  // than 64 chunks (K = 4096) in one TMEM tile: the tensor-core accumulator truncates, and the bias grows
+  // linearly with the number of chained MMAs (measured 4.5e-5 relative at K = 8192) -- split-K partial sums are
+  // combined with round-to-nearest fp32 reductions instead.
   int64_t splits = imax(1, (2 * (int64_t)sms) / tiles);
   splits = imin(splits, imax(1, total_kchunks / 4));
+  splits = imax(splits, ceil_div(total_kchunks, 64));
   splits = imin(splits, 65535);
+  if (store_mode) splits = 1;
   const int kchunks_per_split = (int)ceil_div(total_kchunks, splits);
   splits = ceil_div(total_kchunks, kchunks_per_split);
   const int stage_bytes = (x3 ? 4 : 2) * tc::TILE_BYTES;
@@ -324,11 +345,11 @@ int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_
   if (x3)
     tc::gemm_nt_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
                                                                   symmetric, tiles_m, tiles_n, total_kchunks,
-                                                                  kchunks_per_split, num_stages);
+                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0);
   else
     tc::gemm_nt_tc_kernel<1><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
                                                                   symmetric, tiles_m, tiles_n, total_kchunks,
-                                                                  kchunks_per_split, num_stages);
+                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0);
   LPB_CHECK_LAUNCH("gemm_nt_bf16");
   return 0;
 }

@@ -178,3 +178,145 @@ int pack_nchw_t(const float* gp, int64_t Nn, int Cc, int HW, float scale, int fl
 }
 
 }  // namespace lpb
+
+// =========================================================================================
+// Operand packers of the convolution engine (forward / backward-data of nn.Conv2d as GEMMs on the
+// tcgen05 kernel, fp32-accurate through the bf16 hi/lo split -- see DESIGN.md section 3b).
+// =========================================================================================
+namespace lpb {
+
+// patch-major im2col: x [N, C, H, W] -> dst[(n, oh, ow), (ci, kh, kw)]   (row length ld >= C*KH*KW)
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_conv2d_rows_kernel(const float* __restrict__ x, ConvGeom g, void* hi, void* lo,
+                                                                int64_t ld) {
+  const int d_in = g.C * g.KH * g.KW;
+  const int64_t rows = (int64_t)g.N * g.OH * g.OW;
+  // one warp per output row chunk: threads run along the patch index (coalesced writes)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < rows; r += (int64_t)gridDim.x * 8) {
+    const int ow = r % g.OW;
+    const int oh = (r / g.OW) % g.OH;
+    const int n = r / ((int64_t)g.OW * g.OH);
+    const float* xn = x + (int64_t)n * g.C * g.H * g.W;
+    for (int j = lane; j < d_in; j += 32) {
+      const int kw = j % g.KW, kh = (j / g.KW) % g.KH, ci = j / (g.KW * g.KH);
+      const int ih = oh * g.SH - g.PH + kh * g.DH, iw = ow * g.SW - g.PW + kw * g.DW;
+      float v = 0.f;
+      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = xn[((int64_t)ci * g.H + ih) * g.W + iw];
+      store_packed<KIND>(hi, lo, r * ld + j, v);
+    }
+  }
+}
+
+// channel-minor rows: g [Q, Cc, HW] -> dst[(q, hw), ch]   (row length ld >= Cc); tiled transpose per q
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_nchw_rows_kernel(const float* __restrict__ g, int Cc, int HW, void* hi, void* lo,
+                                                              int64_t ld) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t q = blockIdx.z;
+  const int hb = blockIdx.x * 32, cb = blockIdx.y * 32;
+  const float* gq = g + q * (int64_t)Cc * HW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = cb + ty + 8 * i, hw = hb + tx;
+    tile[ty + 8 * i][tx] = (ch < Cc && hw < HW) ? gq[(int64_t)ch * HW + hw] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int hw = hb + ty + 8 * i, ch = cb + tx;
+    if (hw < HW && ch < Cc) store_packed<KIND>(hi, lo, (q * HW + hw) * ld + ch, tile[tx][ty + 8 * i]);
+  }
+}
+
+// plain cast of a [rows, cols] fp32 matrix into a K-major operand (no transpose)
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_cast_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
+                                                         int64_t ld_src, void* hi, void* lo, int64_t ld) {
+  const int64_t total = rows * cols;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    store_packed<KIND>(hi, lo, r * ld + c, src[r * ld_src + c]);
+  }
+}
+
+// col2im gather: Dc [(ci,kh,kw), ldd] with columns (q, oh, ow)  ->  grad_in [Q, C, H, W]
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ Dc, int64_t ldd, ConvGeom g,
+                                                      float* __restrict__ out) {
+  const int64_t total = (int64_t)g.N * g.C * g.H * g.W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int iw = e % g.W;
+    const int ih = (e / g.W) % g.H;
+    const int ci = (e / ((int64_t)g.W * g.H)) % g.C;
+    const int64_t q = e / ((int64_t)g.W * g.H * g.C);
+    float acc = 0.f;
+    for (int kh = 0; kh < g.KH; ++kh) {
+      const int th = ih + g.PH - kh * g.DH;
+      if (th < 0 || th % g.SH) continue;
+      const int oh = th / g.SH;
+      if (oh >= g.OH) continue;
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const int tw = iw + g.PW - kw * g.DW;
+        if (tw < 0 || tw % g.SW) continue;
+        const int ow = tw / g.SW;
+        if (ow >= g.OW) continue;
+        acc += Dc[(int64_t)((ci * g.KH + kh) * g.KW + kw) * ldd + (q * g.OH + oh) * g.OW + ow];
+      }
+    }
+    out[e] = acc;
+  }
+}
+
+int pack_conv2d_rows(const float* x, const ConvGeom& g, void* hi, void* lo, int kind, int64_t ld, cudaStream_t st) {
+  const int64_t rows = (int64_t)g.N * g.OH * g.OW;
+  if (rows == 0) return 0;
+  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_conv2d_rows: hi+lo output needs a lo buffer");
+  const int blocks = (int)imin(ceil_div(rows, 8), (int64_t)sm_count() * 32);
+  DISPATCH_KIND(kind, (pack_conv2d_rows_kernel<KIND><<<blocks, 256, 0, st>>>(x, g, hi, lo, ld)));
+  LPB_CHECK_LAUNCH("pack_conv2d_rows");
+  return 0;
+}
+
+int pack_nchw_rows(const float* gp, int64_t Q, int Cc, int HW, void* hi, void* lo, int kind, int64_t ld, cudaStream_t st) {
+  if (Q == 0) return 0;
+  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_nchw_rows: hi+lo output needs a lo buffer");
+  if (HW == 1) {
+    const int64_t total = Q * Cc;
+    const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
+    DISPATCH_KIND(kind, (pack_cast_kernel<KIND><<<blocks, 256, 0, st>>>(gp, Q, Cc, Cc, hi, lo, ld)));
+  } else {
+    // gridDim.z is limited to 65535: fold larger Q into several launches
+    for (int64_t q0 = 0; q0 < Q; q0 += 65535) {
+      const int64_t qn = imin(65535, Q - q0);
+      dim3 grid((unsigned)ceil_div(HW, 32), (unsigned)ceil_div(Cc, 32), (unsigned)qn);
+      const float* src = gp + q0 * (int64_t)Cc * HW;
+      void* h2 = (kind == OUT_F32) ? (void*)((float*)hi + q0 * HW * ld) : (void*)((__nv_bfloat16*)hi + q0 * HW * ld);
+      void* l2 = lo ? (void*)((__nv_bfloat16*)lo + q0 * HW * ld) : nullptr;
+      DISPATCH_KIND(kind, (pack_nchw_rows_kernel<KIND><<<grid, 256, 0, st>>>(src, Cc, HW, h2, l2, ld)));
+    }
+  }
+  LPB_CHECK_LAUNCH("pack_nchw_rows");
+  return 0;
+}
+
+int pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* hi, void* lo, int kind, int64_t ld,
+              cudaStream_t st) {
+  if (rows == 0 || cols == 0) return 0;
+  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_cast: hi+lo output needs a lo buffer");
+  const int blocks = (int)imin(ceil_div(rows * cols, 256), (int64_t)sm_count() * 32);
+  DISPATCH_KIND(kind, (pack_cast_kernel<KIND><<<blocks, 256, 0, st>>>(src, rows, cols, ld_src, hi, lo, ld)));
+  LPB_CHECK_LAUNCH("pack_cast");
+  return 0;
+}
+
+int col2im(const float* Dc, int64_t ldd, const ConvGeom& g, float* out, cudaStream_t st) {
+  const int64_t total = (int64_t)g.N * g.C * g.H * g.W;
+  if (total == 0) return 0;
+  const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
+  col2im_kernel<<<blocks, 256, 0, st>>>(Dc, ldd, g, out);
+  LPB_CHECK_LAUNCH("col2im");
+  return 0;
+}
+
+}  // namespace lpb

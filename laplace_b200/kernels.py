@@ -238,3 +238,61 @@ def eigh_jacobi(A: torch.Tensor, max_sweeps: int = 30):
     _lib.call("lpb_eigh_jacobi", _ptr(A), batch, n, _ptr(ev), _ptr(Q), max_sweeps, _stream())
     _bump()
     return ev, Q
+
+
+# ------------------------------------------------------------------------------ convolution engine operands
+def alloc_rows(rows: int, cols: int, kind: int, device) -> Packed:
+    """Row-major operand ``[rows, ld]`` whose *columns* are the contraction index (ld multiple of 8)."""
+    return alloc_packed(rows, cols, kind, device)
+
+
+def _conv_args(shape, mod):
+    N, C, H, W = shape
+    return (N, C, H, W, mod.kernel_size[0], mod.kernel_size[1], mod.stride[0], mod.stride[1], mod.padding[0],
+            mod.padding[1], mod.dilation[0], mod.dilation[1])
+
+
+def pack_conv_rows(x: torch.Tensor, mod, kind: int) -> Packed:
+    """Patch-major im2col ``[(n,oh,ow), C_in*kh*kw]`` (contraction over the patch index)."""
+    _check(x, name="x")
+    x = x.contiguous()
+    N, Cin, H, W = x.shape
+    OH, OW = conv_out_hw(x.shape, mod)
+    out = alloc_rows(N * OH * OW, Cin * mod.kernel_size[0] * mod.kernel_size[1], kind, x.device)
+    _lib.call("lpb_pack_conv2d_rows", _ptr(x), *_conv_args(x.shape, mod), _ptr(out.hi), _ptr(out.lo), out.kind, out.ldk,
+              _stream())
+    _bump()
+    return out
+
+
+def pack_nchw_rows(g: torch.Tensor, kind: int) -> Packed:
+    """``g [Q, Cc, HW]`` -> ``[(q,hw), Cc]`` (contraction over channels)."""
+    _check(g, name="g")
+    assert g.dim() == 3 and g.is_contiguous()
+    Q, Cc, HW = g.shape
+    out = alloc_rows(Q * HW, Cc, kind, g.device)
+    _lib.call("lpb_pack_nchw_rows", _ptr(g), Q, Cc, HW, _ptr(out.hi), _ptr(out.lo), out.kind, out.ldk, _stream())
+    _bump()
+    return out
+
+
+def pack_cast(src: torch.Tensor, kind: int) -> Packed:
+    """``src [rows, cols]`` fp32 -> same layout as a K-major operand (contraction over ``cols``)."""
+    _check(src, name="src")
+    assert src.dim() == 2 and src.stride(1) == 1
+    rows, cols = src.shape
+    out = alloc_rows(rows, cols, kind, src.device)
+    _lib.call("lpb_pack_cast", _ptr(src), rows, cols, src.stride(0), _ptr(out.hi), _ptr(out.lo), out.kind, out.ldk,
+              _stream())
+    _bump()
+    return out
+
+
+def col2im(Dc: torch.Tensor, in_shape, mod) -> torch.Tensor:
+    """``Dc [C_in*kh*kw, Q*OH*OW]`` -> ``grad_in [Q, C_in, H, W]``."""
+    _check(Dc, name="Dc")
+    assert Dc.dim() == 2 and Dc.stride(1) == 1
+    out = torch.empty(tuple(in_shape), device=Dc.device, dtype=torch.float32)
+    _lib.call("lpb_col2im", _ptr(Dc), Dc.stride(0), *_conv_args(in_shape, mod), _ptr(out), _stream())
+    _bump()
+    return out

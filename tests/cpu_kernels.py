@@ -166,7 +166,41 @@ def install(monkeypatch):
     from laplace_b200 import backend
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
-                 "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi"):
+                 "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
+    monkeypatch.setattr(K, "alloc_rows", _alloc)
     monkeypatch.setattr(backend._B200Mixin, "_device_check", lambda self, t: None)
+    from laplace_b200 import conv_engine
+
+    monkeypatch.setattr(conv_engine, "_ALLOW_CPU", True)
+
+
+# ---- convolution engine operands (emulation) ------------------------------------------------
+def pack_conv_rows(x, mod, kind):
+    cols = F.unfold(x.float(), mod.kernel_size, dilation=mod.dilation, padding=mod.padding, stride=mod.stride)
+    N, d, T = cols.shape
+    out = _alloc(N * T, d, kind, x.device)
+    out.hi[:, :d] = cols.permute(0, 2, 1).reshape(N * T, d)
+    return out
+
+
+def pack_nchw_rows(g, kind):
+    Q, Cc, HW = g.shape
+    out = _alloc(Q * HW, Cc, kind, g.device)
+    out.hi[:, :Cc] = g.float().permute(0, 2, 1).reshape(Q * HW, Cc)
+    return out
+
+
+def pack_cast(src, kind):
+    out = _alloc(src.shape[0], src.shape[1], kind, src.device)
+    out.hi[:, :src.shape[1]] = src.float()
+    return out
+
+
+def col2im(Dc, in_shape, mod):
+    Q, C, H, W = in_shape
+    OH, OW = K.conv_out_hw(in_shape, mod)
+    cols = Dc[:, :Q * OH * OW].reshape(Dc.shape[0], Q, OH * OW).permute(1, 0, 2)
+    return F.fold(cols, (H, W), mod.kernel_size, dilation=mod.dilation, padding=mod.padding, stride=mod.stride)

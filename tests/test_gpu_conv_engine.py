@@ -1,0 +1,86 @@
+"""Convolution engine (forward / backward-data of nn.Conv2d on the tcgen05 GEMM) against fp64 torch convolutions,
+kernel by kernel and through autograd (batched reverse pass over curvature columns)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from laplace_b200 import B200GGN, conv_engine, kernels as K, models
+from tests import cpu_kernels as ck
+from tests.fixtures import rel_fro
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GEOMS = [(3, 64, 7, 2, 3, 1, 32), (64, 64, 3, 1, 1, 1, 8), (64, 128, 3, 2, 1, 1, 8), (64, 128, 1, 2, 0, 1, 8), (256, 512, 3, 2, 1, 1, 2),
+         (512, 512, 3, 1, 1, 1, 1), (5, 7, 3, 1, 2, 2, 9), (4, 6, 2, 2, 0, 1, 5)]
+
+
+def _dense(p, cols):
+    return p.hi[:, :cols].float().cpu() + (p.lo[:, :cols].float().cpu() if p.lo is not None else 0)
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_engine_operand_kernels(geom):
+    cin, cout, k, s, p, d, hw = geom
+    torch.manual_seed(0)
+    mod = torch.nn.Conv2d(cin, cout, k, s, p, dilation=d)
+    x = torch.randn(6, cin, hw, hw)
+    ref = ck.pack_conv_rows(x, mod, K.F32)
+    out = K.pack_conv_rows(x.to(DEV), mod, K.BF16X3)
+    assert rel_fro(_dense(out, ref.K), ref.hi[:, :ref.K]) < 2e-5
+    o = mod(x)
+    g = torch.randn(9, cout, o.shape[2] * o.shape[3])
+    ref = ck.pack_nchw_rows(g, K.F32)
+    out = K.pack_nchw_rows(g.to(DEV), K.BF16X3)
+    assert rel_fro(_dense(out, ref.K), ref.hi[:, :ref.K]) < 2e-5
+    w = torch.randn(cout, cin * k * k)
+    assert rel_fro(_dense(K.pack_cast(w.to(DEV), K.BF16X3), w.shape[1]), w) < 2e-5
+    T = o.shape[2] * o.shape[3]
+    Dc = torch.randn(cin * k * k, 9 * T)
+    refc = ck.col2im(Dc, (9, cin, hw, hw), mod)
+    outc = K.col2im(Dc.to(DEV), (9, cin, hw, hw), mod)
+    assert rel_fro(outc.cpu(), refc) < 1e-6
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_forward_backward_vs_fp64(geom):
+    cin, cout, k, s, p, d, hw = geom
+    torch.manual_seed(1)
+    mod = torch.nn.Conv2d(cin, cout, k, s, p, dilation=d).to(DEV)
+    x = torch.randn(32, cin, hw, hw, device=DEV)
+    ref = F.conv2d(x.double(), mod.weight.double(), mod.bias.double(), s, p, d)
+    out = conv_engine.conv_forward(x, mod)
+    assert rel_fro(out, ref) < 2e-5
+    g = torch.randn(64, *ref.shape[1:], device=DEV)
+    gref = torch.nn.grad.conv2d_input((64, cin, hw, hw), mod.weight.double(), g.double(), s, p, d)
+    gin = conv_engine.conv_backward_data(g, mod, (64, cin, hw, hw))
+    assert rel_fro(gin, gref) < 2e-5
+
+
+def test_store_mode_gemm_nonsymmetric():
+    torch.manual_seed(2)
+    A, B = torch.randn(576, 64), torch.randn(40000, 64)
+    pa, pb = K.pack_cast(A.to(DEV), K.BF16X3), K.pack_cast(B.to(DEV), K.BF16X3)
+    out = torch.full((576, 40000), 5.0, device=DEV)
+    K.gemm_nt(pa, pb, out, 1.0, accumulate=False)
+    assert rel_fro(out.cpu(), A.double() @ B.double().t()) < 2e-5
+
+
+@pytest.mark.parametrize("name,kw", [("resnet18", {"width": 16}), ("wrn28_10", {"depth": 10, "widen": 2})])
+def test_layer_gradients_match_fp64_autograd(name, kw):
+    """The batched reverse pass through the engine reproduces fp64 autograd gradients at every layer output."""
+    model = models.make(name, **kw).to(DEV)
+    torch.manual_seed(3)
+    X = torch.randn(16, 3, 32, 32, device=DEV)
+    be = B200GGN(model, "classification")
+    f = be._forward(X)
+    cols = be._hessian_sqrt_cols(f.detach())
+    grads = be._backward(f, cols)
+    assert be.last_backward_mode == "batched"
+    md = models.make(name, **kw).double().to(DEV)
+    md.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    be64 = B200GGN(md, "classification", conv_engine=False)
+    f64 = be64._forward(X.double())
+    g64 = be64._backward(f64, cols.double())
+    assert rel_fro(f, f64) < 1e-5
+    worst = max(rel_fro(a, b) for a, b in zip(grads, g64))
+    assert worst < 5e-5, worst

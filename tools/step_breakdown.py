@@ -11,10 +11,11 @@ ap.add_argument("--precision", default="bf16x3")
 ap.add_argument("--model", default="resnet18")
 ap.add_argument("--tf32", action="store_true")
 ap.add_argument("--loop-backward", action="store_true")
+ap.add_argument("--no-engine", action="store_true")
 a = ap.parse_args()
 dev = "cuda"
 model = models.make(a.model).to(dev)
-be = B200GGN(model, "classification", precision=a.precision, model_tf32=a.tf32, batched_backward=not a.loop_backward)
+be = B200GGN(model, "classification", precision=a.precision, model_tf32=a.tf32, batched_backward=not a.loop_backward, conv_engine=not a.no_engine)
 X = torch.randn(a.batch, 3, 32, 32, device=dev); y = torch.randint(10, (a.batch,), device=dev)
 rec = collections.defaultdict(list)
 
@@ -26,7 +27,7 @@ def wrap(obj, name, label=None):
         rec[label or name].append((s, e)); return r
     setattr(obj, name, g)
 
-for n in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt"):
+for n in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im"):
     wrap(K, n)
 wrap(be, "_forward"); wrap(be, "_backward")
 for i in range(3):
@@ -40,6 +41,7 @@ for i in range(R):
     be.kron(X, y, N=50000)
 e0.record(); torch.cuda.synchronize()
 wall = (time.perf_counter() - t0) / R * 1e3
+print(be.last_backward_mode)
 print(f"batch {a.batch} precision {a.precision} tf32={a.tf32}: {s0.elapsed_time(e0)/R:.2f} ms/step device, {wall:.2f} ms wall")
 tot = 0
 for k, v in rec.items():
