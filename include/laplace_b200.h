@@ -94,6 +94,14 @@ int lpb_gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void
                      int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd,
                      int symmetric, void* stream);
 
+/* implicit-GEMM convolution, stride 1, same padding, NHWC bf16 (hi/lo) operands, fp32 NHWC output:
+ *   D[(q,h,w), n] = alpha * sum_{kh,kw,k} X[q, h + base_h + sgn*kh, w + base_w + sgn*kw, k] * Wt[(kh*KW+kw)*N + n, k]
+ * X [Q,H,W,ldx] (ldx >= Kc), Wt [KH*KW*N, ldw]; H*W must divide 128; out-of-range taps read zeros (TMA fill).
+ * forward of nn.Conv2d: (base, sgn) = (-pad, +1); backward-data: (+pad, -1) with Wt[(tap), ci, co].          */
+int lpb_conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
+                       const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
+                       float* D, int64_t ldd, void* stream);
+
 /* ---- weight-sharing layers: per-sample layer Jacobians ------------------------------------
  * P_q[i,j] = sum_t G[i, q*T+t] * A[j, (q % Nn)*T + t], q = c*Nn + n over ncols back-propagated columns.
  * mode 0: out[i*out_ld + j] += scale * sum_q P_q[i,j]^2      (diag GGN / EF, curvature.py:429-431, :504)

@@ -207,7 +207,8 @@ class _B200Mixin:
         for L, g, o in zip(self._layers, grads, outs):
             if g is None:
                 g = torch.zeros((cols.shape[0],) + tuple(o.shape), device=o.device, dtype=torch.float32)
-            res.append(g.detach().float().contiguous())
+            g = g.detach().float()
+            res.append(g if (g.dim() == 5 and g.stride(2) == 1 and g.permute(0, 1, 3, 4, 2).is_contiguous()) else g.contiguous())
         self._outs = {}
         return res
 
@@ -272,6 +273,9 @@ class _B200Mixin:
         """K-major output-gradient rows ``[d_out, ncols*M*T]`` (column-major over ``(col, n, t)``)."""
         if L.is_conv:
             nc, M, Co, OH, OW = g.shape
+            if not reduce and g.stride(2) == 1 and g.permute(0, 1, 3, 4, 2).is_contiguous():
+                # channels_last gradients (convolution engine): rows [(col,n,h,w), Co] -> tiled transpose
+                return K.pack_rows(g.permute(0, 1, 3, 4, 2).reshape(nc * M * OH * OW, Co), kind)
             return K.pack_nchw(g.reshape(nc * M, Co, OH * OW), kind, reduce_sum=reduce)
         nc, M = g.shape[:2]
         rows = g.reshape(nc * M, -1, g.shape[-1])

@@ -22,7 +22,10 @@ from torch import nn
 
 from . import kernels as K
 
+import os
+
 KIND = K.BF16X3
+USE_IMPLICIT = os.environ.get("LPB_NO_IMPLICIT") != "1"
 
 
 class _WeightCache:
@@ -40,7 +43,15 @@ class _WeightCache:
             return hit[1]
         w2 = w.detach().reshape(w.shape[0], -1)
         w2 = w2 if w2.dtype == torch.float32 else w2.float()
-        packed = K.pack_cast(w2.contiguous(), KIND) if which == "fwd" else K.pack_rows(w2.contiguous(), KIND)
+        if which == "fwd":
+            packed = K.pack_cast(w2.contiguous(), KIND)
+        elif which == "bwd":
+            packed = K.pack_rows(w2.contiguous(), KIND)
+        else:  # tap-major weights of the implicit-GEMM kernel
+            w4 = w.detach().float()
+            perm = (2, 3, 0, 1) if which == "fwd_taps" else (2, 3, 1, 0)
+            w4 = w4.permute(*perm).reshape(-1, w4.shape[1] if which == "fwd_taps" else w4.shape[0]).contiguous()
+            packed = K.pack_cast(w4, KIND)
         self.store[key] = (tag, packed)
         return packed
 
@@ -48,7 +59,39 @@ class _WeightCache:
 _CACHE = _WeightCache()
 
 
+def implicit_ok(mod: nn.Conv2d, H: int, W: int) -> bool:
+    """Stride-1 'same' convolutions whose images tile a 128-row MMA block: no im2col / col2im at all."""
+    kh, kw = mod.kernel_size
+    if not USE_IMPLICIT:
+        return False
+    return (tuple(mod.stride) == (1, 1) and tuple(mod.dilation) == (1, 1) and 2 * mod.padding[0] == kh - 1
+            and 2 * mod.padding[1] == kw - 1 and H * W <= 128 and 128 % (H * W) == 0)
+
+
+def nhwc_rows(x: torch.Tensor) -> K.Packed:
+    """``x [N, C, H, W]`` (NCHW or channels_last) -> bf16 hi/lo rows ``[(n,h,w), C]``."""
+    N, C, H, W = x.shape
+    if x.stride(1) == 1 and x.permute(0, 2, 3, 1).is_contiguous():
+        return K.pack_cast(x.permute(0, 2, 3, 1).reshape(N * H * W, C), KIND)
+    return K.pack_nchw_rows(x.contiguous().reshape(N, C, H * W), KIND)
+
+
+def _implicit(x: torch.Tensor, mod: nn.Conv2d, which: str, n_out: int, sgn: int) -> torch.Tensor:
+    N, _, H, W = x.shape
+    kh, kw = mod.kernel_size
+    X = nhwc_rows(x)
+    Wt = _CACHE.get(mod, which)
+    out = torch.empty(N * H * W, n_out, device=x.device, dtype=torch.float32)
+    ph, pw = mod.padding
+    K.conv_nhwc(X, N, H, W, Wt, n_out, kh, kw, -sgn * ph, -sgn * pw, sgn, out)
+    return out.view(N, H, W, n_out).permute(0, 3, 1, 2)     # channels_last view, no copy
+
+
 def conv_forward(x: torch.Tensor, mod: nn.Conv2d) -> torch.Tensor:
+    if implicit_ok(mod, x.shape[2], x.shape[3]):
+        out = _implicit(x, mod, "fwd_taps", mod.out_channels, +1)
+        return out if mod.bias is None else out + mod.bias.detach().view(1, -1, 1, 1)
+    x = x.contiguous()
     N = x.shape[0]
     Co = mod.out_channels
     OH, OW = K.conv_out_hw(x.shape, mod)
@@ -63,6 +106,9 @@ def conv_forward(x: torch.Tensor, mod: nn.Conv2d) -> torch.Tensor:
 
 
 def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape) -> torch.Tensor:
+    if implicit_ok(mod, in_shape[2], in_shape[3]):
+        return _implicit(g, mod, "bwd_taps", mod.in_channels, -1)
+    g = g.contiguous()
     Q, Co = g.shape[0], g.shape[1]
     T = g.shape[2] * g.shape[3]
     G = K.pack_nchw_rows(g.reshape(Q, Co, T), KIND)          # [(q,t), Co]
@@ -75,7 +121,6 @@ def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape) -> torch.Tenso
 class _ConvBwdData(torch.autograd.Function):
     @staticmethod
     def forward(g, mod, in_shape):
-        g = g.contiguous()
         return conv_backward_data(g if g.dtype == torch.float32 else g.float(), mod, in_shape)
 
     @staticmethod
@@ -97,7 +142,7 @@ class _ConvBwdData(torch.autograd.Function):
 class _Conv(torch.autograd.Function):
     @staticmethod
     def forward(x, weight, mod):
-        return conv_forward(x.contiguous(), mod)
+        return conv_forward(x, mod)
 
     @staticmethod
     def setup_context(ctx, inputs, output):

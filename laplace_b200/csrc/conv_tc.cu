@@ -1,0 +1,202 @@
+// Implicit-GEMM convolution on the tcgen05 tensor cores (stride 1, "same" padding, NHWC operands):
+//
+//     D[(q,h,w), n] = alpha * sum_{kh,kw} sum_k  X[q, h + bh + s*kh, w + bw + s*kw, k] * Wt[(kh,kw), n, k]
+//
+// forward:        X = layer input,    Wt[(kh,kw), co, ci] = W[co,ci,kh,kw],   (bh,bw,s) = (-p,-p,+1)
+// backward-data:  X = output gradient, Wt[(kh,kw), ci, co] = W[co,ci,kh,kw],   (bh,bw,s) = (+p,+p,-1)
+//
+// No im2col / col2im ever touches HBM: the A operand of every tap is a *shifted 4-D TMA box* of the NHWC
+// tensor ({64 channels, W, H, 128/(H*W) images}, 128B swizzle, out-of-bounds rows zero-filled by the TMA
+// unit = the zero padding of the convolution).  One CTA owns 128 consecutive NHWC output rows x 128 output
+// channels, loops over taps x channel chunks through the same full/empty mbarrier ring as the GEMM kernel,
+// accumulates in TMEM and stores the fp32 tile once.  bf16 hi/lo operands, three products per tile
+// (NPROD = 3) give fp32-level accuracy.
+#include "tc_common.cuh"
+
+namespace lpb {
+namespace tc {
+
+template <int NPROD>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int64_t Mrows,
+                    int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile, int KH, int KW, int base_h,
+                    int base_w, int sgn, int kchunks, int num_stages) {
+  constexpr int TILES_PER_STAGE = NPROD == 3 ? 4 : 2;
+  constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + num_stages;
+  uint64_t* tmem_full_bar = empty_bar + num_stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int tm = blockIdx.x, tn = blockIdx.y;
+  const int q0 = tm * q_per_tile;
+  const int total = KH * KW * kchunks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < total; ++it) {
+        const int tap = it / kchunks, kc = it - tap * kchunks;
+        const int kh = tap / KW, kw = tap - kh * KW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        const int ch = base_h + sgn * kh, cw = base_w + sgn * kw;
+        tma_load_4d(&tmX_hi, &full_bar[stage], st, kc * BK, cw, ch, q0);
+        tma_load_2d(&tmW_hi, &full_bar[stage], st + TILE_BYTES, kc * BK, tap * N + tn * BN);
+        if (NPROD == 3) {
+          tma_load_4d(&tmX_lo, &full_bar[stage], st + 2 * TILE_BYTES, kc * BK, cw, ch, q0);
+          tma_load_2d(&tmW_lo, &full_bar[stage], st + 3 * TILE_BYTES, kc * BK, tap * N + tn * BN);
+        }
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0; uint32_t phase = 0; uint32_t acc = 0;
+      for (int it = 0; it < total; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+          umma_f16(tmem_base, a_hi + koff, b_hi + koff, idesc, acc);
+          acc = 1;
+          if (NPROD == 3) {
+            const uint64_t a_lo = make_smem_desc(sbase + 2 * TILE_BYTES), b_lo = make_smem_desc(sbase + 3 * TILE_BYTES);
+            umma_f16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
+            umma_f16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int64_t row = (int64_t)tm * BM + q * 32 + lane;
+    const bool vec_ok = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), v);
+      const int col0 = tn * BN + chunk * 32;
+      if (row < Mrows && col0 < N) {
+        float* drow = D + row * ldd + col0;
+        if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(drow + j) = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) drow[j] = alpha * v[j];
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tc
+
+static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int64_t Q, int H, int W, int64_t Kc, int64_t ld, int q_per_tile) {
+  PFN_encodeTiled enc = get_tensormap_encoder();
+  LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)Kc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Q};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)W, (cuuint32_t)H, (cuuint32_t)q_per_tile};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed (%d) Q=%lld H=%d W=%d K=%lld ld=%lld", (int)r,
+              (long long)Q, H, W, (long long)Kc, (long long)ld);
+  return 0;
+}
+
+int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
+                   const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
+                   float* D, int64_t ldd, cudaStream_t st) {
+  LPB_REQUIRE(Q > 0 && H > 0 && W > 0 && Kc > 0 && N > 0 && KH > 0 && KW > 0, "conv_nhwc_bf16: bad extents");
+  LPB_REQUIRE(H * W <= 128 && 128 % (H * W) == 0, "conv_nhwc_bf16: H*W must divide 128 (got %dx%d)", H, W);
+  LPB_REQUIRE((ldx % 8) == 0 && (ldw % 8) == 0 && ldx >= Kc && ldw >= Kc, "conv_nhwc_bf16: bad leading dimensions");
+  LPB_REQUIRE((X_lo == nullptr) == (W_lo == nullptr), "conv_nhwc_bf16: lo operands must both be given or both NULL");
+  LPB_REQUIRE(ldd >= N, "conv_nhwc_bf16: ldd too small");
+  const bool x3 = X_lo != nullptr;
+  const int q_per_tile = 128 / (H * W);
+  CUtensorMap tX_hi, tX_lo, tW_hi, tW_lo;
+  if (make_tmap_nhwc(&tX_hi, X_hi, Q, H, W, Kc, ldx, q_per_tile)) return 1;
+  if (make_tmap_2d(&tW_hi, W_hi, (int64_t)KH * KW * N, Kc, ldw)) return 1;
+  if (x3) {
+    if (make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile)) return 1;
+    if (make_tmap_2d(&tW_lo, W_lo, (int64_t)KH * KW * N, Kc, ldw)) return 1;
+  } else {
+    tX_lo = tX_hi; tW_lo = tW_hi;
+  }
+  const int64_t Mrows = Q * H * W;
+  const int64_t tiles_m = ceil_div(Q, q_per_tile);
+  const int tiles_n = (int)ceil_div(N, tc::BN);
+  LPB_REQUIRE(tiles_m <= 2147483647LL && tiles_n <= 65535, "conv_nhwc_bf16: too many tiles");
+  const int kchunks = (int)ceil_div(Kc, tc::BK);
+  const int stage_bytes = (x3 ? 4 : 2) * tc::TILE_BYTES;
+  const int num_stages = x3 ? 3 : 6;
+  const size_t smem = (size_t)num_stages * stage_bytes + (2 * num_stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr1 = false, attr3 = false;
+  if (x3 && !attr3) {
+    if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                   "conv_nhwc_bf16 attr"))
+      return 1;
+    attr3 = true;
+  }
+  if (!x3 && !attr1) {
+    if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                   "conv_nhwc_bf16 attr"))
+      return 1;
+    attr1 = true;
+  }
+  dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
+  if (x3)
+    tc::conv_nhwc_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,
+                                                                    q_per_tile, KH, KW, base_h, base_w, sgn, kchunks,
+                                                                    num_stages);
+  else
+    tc::conv_nhwc_tc_kernel<1><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,
+                                                                    q_per_tile, KH, KW, base_h, base_w, sgn, kchunks,
+                                                                    num_stages);
+  LPB_CHECK_LAUNCH("conv_nhwc_bf16");
+  return 0;
+}
+
+}  // namespace lpb

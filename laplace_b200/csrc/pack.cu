@@ -242,29 +242,32 @@ __global__ void __launch_bounds__(256) pack_cast_kernel(const float* __restrict_
 }
 
 // col2im gather: Dc [(ci,kh,kw), ldd] with columns (q, oh, ow)  ->  grad_in [Q, C, H, W]
+// grid: x over (q, ih, iw) flattened (32-bit), y = ci; consecutive threads -> consecutive iw (coalesced taps)
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ Dc, int64_t ldd, ConvGeom g,
                                                       float* __restrict__ out) {
-  const int64_t total = (int64_t)g.N * g.C * g.H * g.W;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int iw = e % g.W;
-    const int ih = (e / g.W) % g.H;
-    const int ci = (e / ((int64_t)g.W * g.H)) % g.C;
-    const int64_t q = e / ((int64_t)g.W * g.H * g.C);
+  const unsigned HW = g.H * g.W, total = (unsigned)g.N * HW;
+  const int ci = blockIdx.y;
+  const float* base = Dc + (int64_t)ci * g.KH * g.KW * ldd;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const unsigned q = e / HW, r = e - q * HW;
+    const int ih = r / g.W, iw = r - ih * g.W;
+    const unsigned qoff = q * g.OH * g.OW;
     float acc = 0.f;
+#pragma unroll 1
     for (int kh = 0; kh < g.KH; ++kh) {
       const int th = ih + g.PH - kh * g.DH;
       if (th < 0 || th % g.SH) continue;
       const int oh = th / g.SH;
       if (oh >= g.OH) continue;
+      const float* row = base + (int64_t)kh * g.KW * ldd + qoff + oh * g.OW;
       for (int kw = 0; kw < g.KW; ++kw) {
         const int tw = iw + g.PW - kw * g.DW;
         if (tw < 0 || tw % g.SW) continue;
         const int ow = tw / g.SW;
-        if (ow >= g.OW) continue;
-        acc += Dc[(int64_t)((ci * g.KH + kh) * g.KW + kw) * ldd + (q * g.OH + oh) * g.OW + ow];
+        if (ow < g.OW) acc += __ldg(row + (int64_t)kw * ldd + ow);
       }
     }
-    out[e] = acc;
+    out[((int64_t)q * g.C + ci) * HW + r] = acc;
   }
 }
 
@@ -311,10 +314,12 @@ int pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void
 }
 
 int col2im(const float* Dc, int64_t ldd, const ConvGeom& g, float* out, cudaStream_t st) {
-  const int64_t total = (int64_t)g.N * g.C * g.H * g.W;
-  if (total == 0) return 0;
-  const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
-  col2im_kernel<<<blocks, 256, 0, st>>>(Dc, ldd, g, out);
+  const int64_t per_c = (int64_t)g.N * g.H * g.W;
+  if (per_c == 0) return 0;
+  LPB_REQUIRE(per_c < (1LL << 31) && (int64_t)g.N * g.OH * g.OW < (1LL << 31), "col2im: batch too large for 32-bit indexing");
+  LPB_REQUIRE(g.C <= 65535, "col2im: too many channels");
+  dim3 grid((unsigned)imin(ceil_div(per_c, 256), 8192), (unsigned)g.C);
+  col2im_kernel<<<grid, 256, 0, st>>>(Dc, ldd, g, out);
   LPB_CHECK_LAUNCH("col2im");
   return 0;
 }

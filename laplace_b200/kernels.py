@@ -296,3 +296,16 @@ def col2im(Dc: torch.Tensor, in_shape, mod) -> torch.Tensor:
     _lib.call("lpb_col2im", _ptr(Dc), Dc.stride(0), *_conv_args(in_shape, mod), _ptr(out), _stream())
     _bump()
     return out
+
+
+def conv_nhwc(X: Packed, Q: int, H: int, W: int, Wt: Packed, N: int, KH: int, KW: int, base_h: int, base_w: int, sgn: int,
+              out: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """Implicit-GEMM stride-1 convolution on NHWC bf16(hi/lo) rows ``X [(q,h,w), Kc]`` with tap-major weights
+    ``Wt [(tap, n), Kc]``; ``out [(q,h,w), N]`` fp32 is overwritten."""
+    _check(out, name="out")
+    assert X.kind in (BF16, BF16X3) and X.kind == Wt.kind and X.rows == Q * H * W and Wt.rows == KH * KW * N and X.K == Wt.K
+    assert out.shape == (Q * H * W, N) and out.stride(1) == 1
+    _lib.call("lpb_conv_nhwc_bf16", _ptr(X.hi), _ptr(X.lo), Q, H, W, X.K, X.ldk, _ptr(Wt.hi), _ptr(Wt.lo), Wt.ldk, N, KH, KW,
+              base_h, base_w, sgn, alpha, _ptr(out), out.stride(0), _stream())
+    _bump()
+    return out

@@ -115,6 +115,7 @@ class B200Kron(Kron):
                 eigvecs[i][j] = torch.eye(len(H), dtype=H.dtype, device=H.device)
             else:
                 by_size.setdefault(int(H.shape[0]), []).append((i, j, H))
+        large = []
         for n, group in by_size.items():
             dtype = group[0][2].dtype
             if n <= K.EIGH_MAX_N and group[0][2].is_cuda:
@@ -123,9 +124,9 @@ class B200Kron(Kron):
                 for b, (i, j, _) in enumerate(group):
                     eigvals[i][j], eigvecs[i][j] = ev[b].to(dtype), Q[b].to(dtype)
             else:
-                for i, j, H in group:
-                    ev, Q = symeig_large(H)
-                    eigvals[i][j], eigvecs[i][j] = ev, Q
+                large.extend(group)
+        if large:
+            _symeig_concurrent(large, eigvals, eigvecs)
         return B200KronDecomposed(eigvecs, eigvals, damping=damping)
 
     # -- cold-path helpers (utils/matrix.py:222-275); plain device tensor algebra --------------
@@ -159,6 +160,29 @@ class B200Kron(Kron):
             else:
                 total = total + F[1].shape[0] * torch.logdet(F[0]) + F[0].shape[0] * torch.logdet(F[1])
         return total
+
+
+N_EIGH_STREAMS = 4
+
+
+def _symeig_concurrent(items, eigvals, eigvecs):
+    """Large factors: one cuSOLVER ``syevd`` each (a single call leaves most of the GPU idle), spread over a few
+    streams, largest first, so that independent factors overlap."""
+    if not items[0][2].is_cuda or len(items) == 1:
+        for i, j, H in items:
+            eigvals[i][j], eigvecs[i][j] = symeig_large(H)
+        return
+    items = sorted(items, key=lambda t: -t[2].shape[0])
+    cur = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(min(N_EIGH_STREAMS, len(items)))]
+    for s_ in streams:
+        s_.wait_stream(cur)
+    for k, (i, j, H) in enumerate(items):
+        with torch.cuda.stream(streams[k % len(streams)]):
+            eigvals[i][j], eigvecs[i][j] = symeig_large(H)
+            H.record_stream(streams[k % len(streams)])
+    for s_ in streams:
+        cur.wait_stream(s_)
 
 
 def symeig_large(H: torch.Tensor):

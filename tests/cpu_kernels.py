@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -204,3 +204,21 @@ def col2im(Dc, in_shape, mod):
     OH, OW = K.conv_out_hw(in_shape, mod)
     cols = Dc[:, :Q * OH * OW].reshape(Dc.shape[0], Q, OH * OW).permute(1, 0, 2)
     return F.fold(cols, (H, W), mod.kernel_size, dilation=mod.dilation, padding=mod.padding, stride=mod.stride)
+
+
+def conv_nhwc(X, Q, H, W, Wt, N, KH, KW, base_h, base_w, sgn, out, alpha=1.0):
+    Kc = X.K
+    x = X.hi[:, :Kc].reshape(Q, H, W, Kc)
+    w = Wt.hi[:, :Kc].reshape(KH * KW, N, Kc)
+    res = torch.zeros(Q, H, W, N)
+    for kh in range(KH):
+        for kw in range(KW):
+            dh, dw = base_h + sgn * kh, base_w + sgn * kw
+            shifted = torch.zeros_like(x)
+            hs, he = max(0, -dh), min(H, H - dh)
+            ws, we = max(0, -dw), min(W, W - dw)
+            if hs < he and ws < we:
+                shifted[:, hs:he, ws:we] = x[:, hs + dh:he + dh, ws + dw:we + dw]
+            res += torch.einsum("qhwk,nk->qhwn", shifted, w[kh * KW + kw])
+    out.copy_(alpha * res.reshape(Q * H * W, N))
+    return out

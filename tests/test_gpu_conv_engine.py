@@ -11,7 +11,15 @@ from tests.fixtures import rel_fro
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 GEOMS = [(3, 64, 7, 2, 3, 1, 32), (64, 64, 3, 1, 1, 1, 8), (64, 128, 3, 2, 1, 1, 8), (64, 128, 1, 2, 0, 1, 8), (256, 512, 3, 2, 1, 1, 2),
-         (512, 512, 3, 1, 1, 1, 1), (5, 7, 3, 1, 2, 2, 9), (4, 6, 2, 2, 0, 1, 5)]
+         (512, 512, 3, 1, 1, 1, 1), (5, 7, 3, 1, 2, 2, 9), (4, 6, 2, 2, 0, 1, 5),
+         # implicit-GEMM eligible (stride 1, same padding, H*W | 128), incl. ragged channel counts
+         (128, 128, 3, 1, 1, 1, 4), (256, 256, 3, 1, 1, 1, 2), (24, 40, 5, 1, 2, 1, 4), (16, 200, 1, 1, 0, 1, 8), (72, 8, 3, 1, 1, 1, 8)]
+
+
+def test_implicit_path_selected():
+    m = torch.nn.Conv2d(64, 64, 3, 1, 1)
+    assert conv_engine.implicit_ok(m, 8, 8) and conv_engine.implicit_ok(m, 1, 1) and not conv_engine.implicit_ok(m, 16, 16)
+    assert not conv_engine.implicit_ok(torch.nn.Conv2d(64, 64, 3, 2, 1), 8, 8)
 
 
 def _dense(p, cols):
@@ -46,14 +54,16 @@ def test_conv_forward_backward_vs_fp64(geom):
     cin, cout, k, s, p, d, hw = geom
     torch.manual_seed(1)
     mod = torch.nn.Conv2d(cin, cout, k, s, p, dilation=d).to(DEV)
-    x = torch.randn(32, cin, hw, hw, device=DEV)
+    x = torch.randn(33, cin, hw, hw, device=DEV)
     ref = F.conv2d(x.double(), mod.weight.double(), mod.bias.double(), s, p, d)
     out = conv_engine.conv_forward(x, mod)
-    assert rel_fro(out, ref) < 2e-5
-    g = torch.randn(64, *ref.shape[1:], device=DEV)
-    gref = torch.nn.grad.conv2d_input((64, cin, hw, hw), mod.weight.double(), g.double(), s, p, d)
-    gin = conv_engine.conv_backward_data(g, mod, (64, cin, hw, hw))
-    assert rel_fro(gin, gref) < 2e-5
+    assert out.shape == ref.shape and rel_fro(out, ref) < 2e-5
+    out_cl = conv_engine.conv_forward(x.contiguous(memory_format=torch.channels_last), mod)
+    assert rel_fro(out_cl, ref) < 2e-5
+    g = torch.randn(65, *ref.shape[1:], device=DEV)
+    gref = torch.nn.grad.conv2d_input((65, cin, hw, hw), mod.weight.double(), g.double(), s, p, d)
+    gin = conv_engine.conv_backward_data(g, mod, (65, cin, hw, hw))
+    assert gin.shape == gref.shape and rel_fro(gin, gref) < 2e-5
 
 
 def test_store_mode_gemm_nonsymmetric():

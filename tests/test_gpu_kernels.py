@@ -105,7 +105,7 @@ def test_tensor_core_syrk_large_properties():
     H = torch.zeros(d, d, device=DEV)
     K.gemm_nt(p, p, H, 1.0, True, symmetric=True)
     assert rel_fro(H, H.t()) < 1e-6
-    assert abs(float(H.diagonal().sum() / (X.double() ** 2).sum()) - 1) < 1e-5
+    assert abs(float(H.diagonal().sum() / (X.double() ** 2).sum()) - 1) < 2e-5  # accumulator truncation bias, K<=2048 per TMEM tile
     H2 = torch.zeros(d, d, device=DEV)
     for part in (X[:3000], X[3000:]):
         pp = K.pack_rows(part.contiguous(), K.BF16X3)
