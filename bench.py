@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--predictive", action="store_true", help="also time the GLM predictive (reported under config)")
     ap.add_argument("--model-tf32", action="store_true", help="let cuDNN/cuBLAS use TF32 in the model's own passes")
-    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = min(cores, 32))")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = min(cores, 16), the measured optimum)")
     return ap.parse_args()
 
 
@@ -138,9 +138,10 @@ def cpu_reference_run(args, steps, warmup, samples_per_step):
 
 
 def cpu_threads(args):
-    """Threads of the CPU arm: more than ~32 threads make the many small ops of the per-class reverse passes
-    slower, not faster (measured on the 128-core GPU host); the count actually used is reported as `cores`."""
-    return args.cpu_threads if args.cpu_threads > 0 else min(os.cpu_count() or 1, 32)
+    """Threads of the CPU arm: measured on the 128-core GPU host the oracle port peaks at 16 torch threads
+    (8: 240, 16: 293, 32: 193, 64: 85 samples/s) -- more threads make the many small ops of the per-class
+    reverse passes slower; the count actually used is reported as `cores`."""
+    return args.cpu_threads if args.cpu_threads > 0 else min(os.cpu_count() or 1, 16)
 
 
 def run_reference(args):
@@ -280,6 +281,8 @@ def run_ours(args):
 
     extras = {}
     if rank == 0:
+        torch.linalg.eigh(torch.eye(256, device=dev))  # load cuSOLVER once (tens of seconds on a cold box)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         la.decompose()
         torch.cuda.synchronize()
@@ -319,40 +322,77 @@ def run_ours(args):
 
 
 def measure_roofline(be, K, Xs, ys, N_total, args, dev):
-    """Times every tensor-core SYRK launch of two steps with CUDA events on the launching stream.
-    achieved = algorithmic FLOPs (2 * d^2 * K_rows per launch, dense convention) / event time."""
-    records = []
-    orig = K.gemm_nt
+    """Times every native kernel family of two steps with CUDA events on the launching stream and reports the
+    roofline of the DOMINANT one (largest share of device time), plus a per-family table under `families`.
 
-    def timed(A, Bp, out, alpha=1.0, accumulate=True, symmetric=False):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig(A, Bp, out, alpha, accumulate, symmetric)
-        e.record()
-        records.append((A.kind, A.rows, Bp.rows, A.K, s, e))
-        return r
+    Algorithmic work per launch (dense conventions of SURVEY 8(d), stated in DESIGN.md section 3):
+      gemm_nt (factor SYRKs / engine GEMMs)  2*M*N*K FLOPs (SYRK counted dense: 2*d^2*K_rows)
+      conv_nhwc (implicit-GEMM convolution)  2*rows*N*K*taps FLOPs
+      pack_* / col2im                        bytes read + written once
+    """
+    rec = {}
 
-    K.gemm_nt = timed
+    def wrap(name, work):
+        orig = getattr(K, name)
+
+        def timed(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(*a, **kw)
+            e.record()
+            rec.setdefault(name, []).append((work(r, a, kw), s, e))
+            return r
+
+        setattr(K, name, timed)
+        return orig
+
+    def bytes_packed(p):
+        per = {K.F32: 4, K.BF16: 2, K.BF16X3: 4}[p.kind]
+        return p.rows * p.K * (4 + per)
+
+    works = {
+        "gemm_nt": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[1].rows * a[0].K, a[0].kind != K.F32),
+        "conv_nhwc": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[5] * a[0].K * a[6] * a[7], True),
+        "pack_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
+        "pack_conv": lambda r, a, kw: ("bytes", bytes_packed(r[0]), False),
+        "pack_nchw": lambda r, a, kw: ("bytes", bytes_packed(r), False),
+        "pack_conv_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
+        "pack_nchw_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
+        "pack_cast": lambda r, a, kw: ("bytes", bytes_packed(r), False),
+        "col2im": lambda r, a, kw: ("bytes", 4.0 * (a[0].shape[0] * a[0].shape[1] + r.numel()), False),
+    }
+    origs = {n: wrap(n, w) for n, w in works.items()}
     try:
         for i in range(2):
             be.kron(Xs[i % len(Xs)], ys[i % len(ys)], N=N_total)
         torch.cuda.synchronize()
     finally:
-        K.gemm_nt = orig
-    tc = [(m, n, k, s.elapsed_time(e)) for kind, m, n, k, s, e in records if kind != K.F32]
-    if not tc:
-        return None
-    flops = sum(2.0 * m * n * k for m, n, k, _ in tc)
-    ms = sum(t for *_, t in tc)
+        for n, o in origs.items():
+            setattr(K, n, o)
     pk = peaks()
-    peak = pk["bf16_sustained"] or 1400.0
-    achieved = flops / (ms / 1e3) / 1e12
-    top = max(tc, key=lambda r: r[3])
-    return {"bound": "tensor", "kernel": "gemm_nt_tc_kernel (tcgen05 SYRK, all factor launches of a step)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": pk["source"] + ", bf16 sustained", "launches_per_step": len(tc) // 2,
-            "ms_per_step_in_kernel": ms / 2,
-            "largest_launch": {"d": top[0], "k_rows": top[2], "ms": top[3], "tflops": 2.0 * top[0] * top[1] * top[2] / top[3] / 1e9}}
+    fam = {}
+    for name, lst in rec.items():
+        ms = sum(s.elapsed_time(e) for _, s, e in lst) / 2
+        unit = lst[0][0][0]
+        work = sum(w[1] for w, _, _ in lst) / 2
+        fam[name] = {"ms_per_step": ms, "launches_per_step": len(lst) // 2, "kind": unit,
+                     "achieved": (work / (ms / 1e3) / 1e12) if unit == "flops" else (work / (ms / 1e3) / 1e9),
+                     "unit": "TFLOP/s" if unit == "flops" else "GB/s"}
+    if not fam:
+        return None
+    dom = max(fam, key=lambda n: fam[n]["ms_per_step"])
+    d = fam[dom]
+    tensor = d["kind"] == "flops"
+    peak = (pk["bf16_sustained"] or 1400.0) if tensor else (pk["hbm"] or 6650.0)
+    names = {"gemm_nt": "tc::gemm_nt_tc_kernel (tcgen05 GEMM-NT/SYRK: KFAC factor contractions + explicit-engine GEMMs)",
+             "conv_nhwc": "tc::conv_nhwc_tc_kernel (tcgen05 implicit-GEMM convolution, forward + backward-data)"}
+    return {"bound": "tensor" if tensor else "hbm", "kernel": names.get(dom, "lpb::" + dom + "_kernel"),
+            "achieved": d["achieved"], "peak": peak, "unit": d["unit"], "frac": d["achieved"] / peak, "traffic": None,
+            "peak_source": pk["source"] + (", bf16 sustained" if tensor else ", copy bandwidth"),
+            "note": "algorithmic FLOPs (one product per MAC) over CUDA-event time; precision bf16x3 issues 3 tensor-core "
+                    "products per algorithmic MAC, so the tensor pipe does 3x the counted work" if tensor and args.precision == "bf16x3" else "",
+            "launches_per_step": d["launches_per_step"], "ms_per_step_in_kernel": d["ms_per_step"],
+            "families": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in fam.items()}}
 
 
 def measure_predictive(model, dev, B200Laplace, B200GGN, args):

@@ -30,6 +30,7 @@ extern "C" {
 #define LPB_OUT_F32 0
 #define LPB_OUT_BF16 1
 #define LPB_OUT_BF16_HILO 2
+#define LPB_OUT_F16_HILO 3 /* fp16 hi + fp16 lo: 22 significant bits, operands must stay inside fp16 range */
 #define LPB_PACK_SQUARE 1
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -87,20 +88,20 @@ int lpb_col2im(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH,
 int lpb_gemm_nt_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
                     float alpha, int accumulate, float* D, int64_t ldd, int symmetric, void* stream);
 
-/* tcgen05 tensor-core path: bf16 operands (TMA -> smem -> tcgen05.mma, fp32 accumulation in TMEM).
- * A_lo/B_lo non-NULL: error-compensated 3-product mode hi*hi + hi*lo + lo*hi.
- * Requirements: lda, ldb multiples of 8 elements, operand base pointers 16-byte aligned.      */
-int lpb_gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
-                     int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd,
-                     int symmetric, void* stream);
+/* tcgen05 tensor-core path: 16-bit operands (TMA -> smem -> tcgen05.mma, fp32 accumulation in TMEM);
+ * fp16_operands = 0: bf16, 1: fp16 (both operands).  A_lo/B_lo non-NULL: error-compensated 3-product mode
+ * hi*hi + hi*lo + lo*hi.  Requirements: lda, ldb multiples of 8 elements, operand pointers 16-byte aligned. */
+int lpb_gemm_nt_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                   int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                   int fp16_operands, void* stream);
 
-/* implicit-GEMM convolution, stride 1, same padding, NHWC bf16 (hi/lo) operands, fp32 NHWC output:
+/* implicit-GEMM convolution, stride 1, same padding, NHWC bf16 / fp16 (hi/lo) operands, fp32 NHWC output:
  *   D[(q,h,w), n] = alpha * sum_{kh,kw,k} X[q, h + base_h + sgn*kh, w + base_w + sgn*kw, k] * Wt[(kh*KW+kw)*N + n, k]
  * X [Q,H,W,ldx] (ldx >= Kc), Wt [KH*KW*N, ldw]; H*W must divide 128; out-of-range taps read zeros (TMA fill).
  * forward of nn.Conv2d: (base, sgn) = (-pad, +1); backward-data: (+pad, -1) with Wt[(tap), ci, co].          */
-int lpb_conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
-                       const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
-                       float* D, int64_t ldd, void* stream);
+int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
+                     const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
+                     float* D, int64_t ldd, int fp16_operands, void* stream);
 
 /* ---- weight-sharing layers: per-sample layer Jacobians ------------------------------------
  * P_q[i,j] = sum_t G[i, q*T+t] * A[j, (q % Nn)*T + t], q = c*Nn + n over ncols back-propagated columns.

@@ -25,10 +25,10 @@ SIGNATURES = {
     "lpb_pack_cast": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_i64, c_vp],
     "lpb_col2im": [c_vp, c_i64] + [c_int] * 12 + [c_vp, c_vp],
     "lpb_gemm_nt_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_vp],
-    "lpb_gemm_nt_bf16": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int,
-                         c_vp],
-    "lpb_conv_nhwc_bf16": [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int,
-                           c_int, c_f32, c_vp, c_i64, c_vp],
+    "lpb_gemm_nt_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
+                       c_vp],
+    "lpb_conv_nhwc_tc": [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int,
+                         c_int, c_f32, c_vp, c_i64, c_int, c_vp],
     "lpb_shared_weight_contract": [c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp,
                                    c_i64, c_i64, c_i64, c_vp],
     "lpb_jac_linear_write": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],

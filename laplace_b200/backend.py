@@ -150,6 +150,9 @@ class _B200Mixin:
         if f.ndim != 2:
             raise ValueError(f"the B200 backend supports (batch, outputs) model outputs, got shape {tuple(f.shape)}")
         self._device_check(f)
+        if self.conv_engine and f.is_cuda:
+            # the engine's forward uses fp16 hi/lo operands: an activation beyond +-65504 would surface here
+            torch._assert_async(torch.isfinite(f).all())
         return f
 
     def _conv_patch(self):

@@ -24,7 +24,10 @@ from . import kernels as K
 
 import os
 
-KIND = K.BF16X3
+KIND = K.BF16X3       # reverse pass: gradients span many orders of magnitude -> bf16 hi/lo (8-bit exponent)
+KIND_FWD = K.F16X3    # forward pass: activations / weights sit inside fp16 range -> fp16 hi/lo (22 bits); the
+                      # ~2e-7 forward error keeps ReLU masks identical to an fp32 forward (a 1e-5 error flips a
+                      # few masks per 10^5 units, each flip is a 100 % error on that unit's gradient)
 USE_IMPLICIT = os.environ.get("LPB_NO_IMPLICIT") != "1"
 
 
@@ -44,14 +47,14 @@ class _WeightCache:
         w2 = w.detach().reshape(w.shape[0], -1)
         w2 = w2 if w2.dtype == torch.float32 else w2.float()
         if which == "fwd":
-            packed = K.pack_cast(w2.contiguous(), KIND)
+            packed = K.pack_cast(w2.contiguous(), KIND_FWD)
         elif which == "bwd":
             packed = K.pack_rows(w2.contiguous(), KIND)
         else:  # tap-major weights of the implicit-GEMM kernel
             w4 = w.detach().float()
             perm = (2, 3, 0, 1) if which == "fwd_taps" else (2, 3, 1, 0)
             w4 = w4.permute(*perm).reshape(-1, w4.shape[1] if which == "fwd_taps" else w4.shape[0]).contiguous()
-            packed = K.pack_cast(w4, KIND)
+            packed = K.pack_cast(w4, KIND_FWD if which == "fwd_taps" else KIND)
         self.store[key] = (tag, packed)
         return packed
 
@@ -68,18 +71,18 @@ def implicit_ok(mod: nn.Conv2d, H: int, W: int) -> bool:
             and 2 * mod.padding[1] == kw - 1 and H * W <= 128 and 128 % (H * W) == 0)
 
 
-def nhwc_rows(x: torch.Tensor) -> K.Packed:
-    """``x [N, C, H, W]`` (NCHW or channels_last) -> bf16 hi/lo rows ``[(n,h,w), C]``."""
+def nhwc_rows(x: torch.Tensor, kind: int) -> K.Packed:
+    """``x [N, C, H, W]`` (NCHW or channels_last) -> 16-bit hi/lo rows ``[(n,h,w), C]``."""
     N, C, H, W = x.shape
     if x.stride(1) == 1 and x.permute(0, 2, 3, 1).is_contiguous():
-        return K.pack_cast(x.permute(0, 2, 3, 1).reshape(N * H * W, C), KIND)
-    return K.pack_nchw_rows(x.contiguous().reshape(N, C, H * W), KIND)
+        return K.pack_cast(x.permute(0, 2, 3, 1).reshape(N * H * W, C), kind)
+    return K.pack_nchw_rows(x.contiguous().reshape(N, C, H * W), kind)
 
 
 def _implicit(x: torch.Tensor, mod: nn.Conv2d, which: str, n_out: int, sgn: int) -> torch.Tensor:
     N, _, H, W = x.shape
     kh, kw = mod.kernel_size
-    X = nhwc_rows(x)
+    X = nhwc_rows(x, KIND_FWD if sgn > 0 else KIND)
     Wt = _CACHE.get(mod, which)
     out = torch.empty(N * H * W, n_out, device=x.device, dtype=torch.float32)
     ph, pw = mod.padding
@@ -95,7 +98,7 @@ def conv_forward(x: torch.Tensor, mod: nn.Conv2d) -> torch.Tensor:
     N = x.shape[0]
     Co = mod.out_channels
     OH, OW = K.conv_out_hw(x.shape, mod)
-    P = K.pack_conv_rows(x, mod, KIND)                       # [(n,t), d_in]
+    P = K.pack_conv_rows(x, mod, KIND_FWD)                   # [(n,t), d_in]
     Wk = _CACHE.get(mod, "fwd")                              # [Co, d_in]
     out = torch.empty(Co, N * OH * OW, device=x.device, dtype=torch.float32)
     K.gemm_nt(Wk, P, out, 1.0, accumulate=False)
@@ -161,13 +164,34 @@ def supported(mod: nn.Module) -> bool:
             and mod.padding_mode == "zeros")
 
 
+def _frozen_eval_bn(m: nn.Module) -> bool:
+    """BatchNorm2d in eval mode with running statistics and no trainable affine: a fixed per-channel affine map."""
+    return (isinstance(m, nn.BatchNorm2d) and not m.training and m.track_running_stats and m.running_mean is not None
+            and not any(p.requires_grad for p in m.parameters(recurse=False)))
+
+
+def _bn_affine(m: nn.BatchNorm2d):
+    invstd = torch.rsqrt(m.running_var + m.eps)
+    scale = invstd if m.weight is None else m.weight.detach() * invstd
+    shift = -m.running_mean * scale
+    if m.bias is not None:
+        shift = shift + m.bias.detach()
+    return scale.view(1, -1, 1, 1), shift.view(1, -1, 1, 1)
+
+
 class patched_convs:
     """Context manager: route the forward (and thereby the reverse pass) of every supported ``nn.Conv2d`` of
     ``model`` through the engine.  ``weight`` is passed to the Function so that the output joins the autograd
-    graph even when the input does not require grad (first layer)."""
+    graph even when the input does not require grad (first layer).
+
+    Frozen eval-mode ``BatchNorm2d`` layers are evaluated as the per-channel affine map they are
+    (``x * scale + shift``): identical values, but the reverse pass becomes one broadcast multiply instead of
+    ``native_batch_norm_backward``, whose vmap rule folds the column dimension into channels with two physical
+    copies of the C-times-batched gradient (19 % of a step in profiles/r01_launches_conv_engine_implicit.md)."""
 
     def __init__(self, model: nn.Module):
         self.mods = [m for m in model.modules() if supported(m)]
+        self.bns = [m for m in model.modules() if _frozen_eval_bn(m)]
 
     def __enter__(self):
         for m in self.mods:
@@ -176,10 +200,17 @@ class patched_convs:
                     return nn.Conv2d.forward(m, x)
                 return _Conv.apply(x, m.weight, m)
             m.forward = fwd
+        for m in self.bns:
+            def bn_fwd(x, m=m):
+                if x.dim() != 4:
+                    return nn.BatchNorm2d.forward(m, x)
+                scale, shift = _bn_affine(m)
+                return x * scale.to(x.dtype) + shift.to(x.dtype)
+            m.forward = bn_fwd
         return self
 
     def __exit__(self, *exc):
-        for m in self.mods:
+        for m in self.mods + self.bns:
             m.__dict__.pop("forward", None)
         return False
 

@@ -40,9 +40,9 @@ int col2im(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
 int gemm_nt_f32(const float*, int64_t, const float*, int64_t, int64_t, int64_t, int64_t, float, int, float*, int64_t, int,
                 cudaStream_t);
 int gemm_nt_bf16(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
-                 int, float*, int64_t, int, cudaStream_t);
+                 int, float*, int64_t, int, int, cudaStream_t);
 int conv_nhwc_bf16(const void*, const void*, int64_t, int, int, int64_t, int64_t, const void*, const void*, int64_t, int, int,
-                   int, int, int, int, float, float*, int64_t, cudaStream_t);
+                   int, int, int, int, float, float*, int64_t, int, cudaStream_t);
 int shared_weight_contract(int, const float*, int64_t, const float*, int64_t, int, int, int, int, int, float, float*,
                            int64_t, int64_t, int64_t, cudaStream_t);
 int jac_linear_write(const float*, const float*, int, int, int, int, float*, int64_t, int64_t, int64_t, int64_t,
@@ -155,20 +155,21 @@ int lpb_gemm_nt_f32(const float* A, int64_t lda, const float* B, int64_t ldb, in
   return lpb::gemm_nt_f32(A, lda, B, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, ST(stream));
 }
 
-int lpb_gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
-                     int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd,
-                     int symmetric, void* stream) {
-  LPB_REQUIRE(lda >= K && ldb >= K && ldd >= N, "lpb_gemm_nt_bf16: leading dimension too small");
-  LPB_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "lpb_gemm_nt_bf16: A_lo and B_lo must both be given or both NULL");
-  return lpb::gemm_nt_bf16(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, ST(stream));
+int lpb_gemm_nt_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                   int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                   int fp16_operands, void* stream) {
+  LPB_REQUIRE(lda >= K && ldb >= K && ldd >= N, "lpb_gemm_nt_tc: leading dimension too small");
+  LPB_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "lpb_gemm_nt_tc: A_lo and B_lo must both be given or both NULL");
+  return lpb::gemm_nt_bf16(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, fp16_operands,
+                           ST(stream));
 }
 
-int lpb_conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
-                       const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
-                       float* D, int64_t ldd, void* stream) {
-  LPB_REQUIRE(sgn == 1 || sgn == -1, "lpb_conv_nhwc_bf16: sgn must be +1 or -1");
+int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
+                     const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
+                     float* D, int64_t ldd, int fp16_operands, void* stream) {
+  LPB_REQUIRE(sgn == 1 || sgn == -1, "lpb_conv_nhwc_tc: sgn must be +1 or -1");
   return lpb::conv_nhwc_bf16(X_hi, X_lo, Q, H, W, Kc, ldx, W_hi, W_lo, ldw, N, KH, KW, base_h, base_w, sgn, alpha, D, ldd,
-                             ST(stream));
+                             fp16_operands, ST(stream));
 }
 
 int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const float* A, int64_t lda, int d_out, int d_in,

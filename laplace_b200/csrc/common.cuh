@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -38,7 +39,7 @@ __host__ __device__ inline int64_t imax(int64_t a, int64_t b) { return a > b ? a
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // output element kinds of the pack kernels
-enum OutKind : int { OUT_F32 = 0, OUT_BF16 = 1, OUT_BF16_HILO = 2 };
+enum OutKind : int { OUT_F32 = 0, OUT_BF16 = 1, OUT_BF16_HILO = 2, OUT_F16_HILO = 3 };
 enum PackFlags : int { PACK_SQUARE = 1 };
 
 // store one packed value `v` at element index `idx` of the K-major staging buffers
@@ -46,6 +47,12 @@ template <int KIND>
 __device__ __forceinline__ void store_packed(void* hi, void* lo, int64_t idx, float v) {
   if constexpr (KIND == OUT_F32) {
     reinterpret_cast<float*>(hi)[idx] = v;
+  } else if constexpr (KIND == OUT_F16_HILO) {
+    // fp16 hi + fp16 lo: 22 significant bits (|x - hi - lo| <= 2^-23 |x| while lo stays normal); callers keep
+    // operands inside fp16 range (activations / weights); gradients use the bf16 split (8-bit exponent)
+    const __half h = __float2half_rn(v);
+    reinterpret_cast<__half*>(hi)[idx] = h;
+    reinterpret_cast<__half*>(lo)[idx] = __float2half_rn(v - __half2float(h));
   } else {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     reinterpret_cast<__nv_bfloat16*>(hi)[idx] = h;

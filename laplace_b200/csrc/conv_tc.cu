@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int64_t Mrows,
                     int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile, int KH, int KW, int base_h,
-                    int base_w, int sgn, int kchunks, int num_stages) {
+                    int base_w, int sgn, int kchunks, int num_stages, int fp16_operands) {
   constexpr int TILES_PER_STAGE = NPROD == 3 ? 4 : 2;
   constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -73,7 +73,7 @@ conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_con
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t idesc = make_idesc(BM, BN, fp16_operands);
       int stage = 0; uint32_t phase = 0; uint32_t acc = 0;
       for (int it = 0; it < total; ++it) {
         mbar_wait(&full_bar[stage], phase);
@@ -138,7 +138,7 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int64_t Q, int H, i
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
   cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)W, (cuuint32_t)H, (cuuint32_t)q_per_tile};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed (%d) Q=%lld H=%d W=%d K=%lld ld=%lld", (int)r,
@@ -148,7 +148,7 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int64_t Q, int H, i
 
 int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
                    const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
-                   float* D, int64_t ldd, cudaStream_t st) {
+                   float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
   LPB_REQUIRE(Q > 0 && H > 0 && W > 0 && Kc > 0 && N > 0 && KH > 0 && KW > 0, "conv_nhwc_bf16: bad extents");
   LPB_REQUIRE(H * W <= 128 && 128 % (H * W) == 0, "conv_nhwc_bf16: H*W must divide 128 (got %dx%d)", H, W);
   LPB_REQUIRE((ldx % 8) == 0 && (ldw % 8) == 0 && ldx >= Kc && ldw >= Kc, "conv_nhwc_bf16: bad leading dimensions");
@@ -190,11 +190,11 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
   if (x3)
     tc::conv_nhwc_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,
                                                                     q_per_tile, KH, KW, base_h, base_w, sgn, kchunks,
-                                                                    num_stages);
+                                                                    num_stages, fp16_operands);
   else
     tc::conv_nhwc_tc_kernel<1><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,
                                                                     q_per_tile, KH, KW, base_h, base_w, sgn, kchunks,
-                                                                    num_stages);
+                                                                    num_stages, fp16_operands);
   LPB_CHECK_LAUNCH("conv_nhwc_bf16");
   return 0;
 }

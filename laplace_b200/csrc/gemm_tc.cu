@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int M, int N,
                   float alpha, float* __restrict__ D, int64_t ldd, int symmetric, int tiles_m, int tiles_n,
-                  int total_kchunks, int kchunks_per_split, int num_stages, int store_mode) {
+                  int total_kchunks, int kchunks_per_split, int num_stages, int store_mode, int fp16_operands) {
   constexpr int TILES_PER_STAGE = NPROD == 3 ? 4 : 2;
   constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -85,7 +85,7 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t idesc = make_idesc(BM, BN, fp16_operands);
       int stage = 0; uint32_t phase = 0; uint32_t acc = 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
         mbar_wait(&full_bar[stage], phase);
@@ -183,7 +183,7 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, (long long)rows,
@@ -193,7 +193,7 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int
 
 int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
                  int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
-                 cudaStream_t st) {
+                 int fp16_operands, cudaStream_t st) {
   LPB_REQUIRE(!symmetric || M == N, "gemm_nt_bf16: symmetric needs M == N");
   LPB_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "gemm_nt_bf16: leading dimensions must be multiples of 8 elements");
   LPB_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 &&
@@ -251,11 +251,11 @@ int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_
   if (x3)
     tc::gemm_nt_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
                                                                   symmetric, tiles_m, tiles_n, total_kchunks,
-                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0);
+                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0, fp16_operands);
   else
     tc::gemm_nt_tc_kernel<1><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
                                                                   symmetric, tiles_m, tiles_n, total_kchunks,
-                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0);
+                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0, fp16_operands);
   LPB_CHECK_LAUNCH("gemm_nt_bf16");
   return 0;
 }

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) pack_nchw_sum_t_kernel(const float* __res
     case OUT_F32: { constexpr int KIND = OUT_F32; CALL; } break;           \
     case OUT_BF16: { constexpr int KIND = OUT_BF16; CALL; } break;         \
     case OUT_BF16_HILO: { constexpr int KIND = OUT_BF16_HILO; CALL; } break; \
+    case OUT_F16_HILO: { constexpr int KIND = OUT_F16_HILO; CALL; } break;   \
     default: set_error("bad out_kind %d", kind); return 1;  \
   }
 
@@ -133,7 +134,7 @@ int pack_rows_t(const float* src, int64_t rows, int64_t cols, int64_t ld_src, co
   if (rows == 0 || cols == 0 || nrep <= 0) return 0;
   LPB_REQUIRE(nrep == 1 || row_scale != nullptr, "pack_rows_t: replicas need per-replica row scales");
   LPB_REQUIRE(nrep <= 65535, "pack_rows_t: too many replicas");
-  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_rows_t: hi+lo output needs a lo buffer");
+  LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_rows_t: hi+lo output needs a lo buffer");
   dim3 grid((unsigned)ceil_div(rows, 32), (unsigned)ceil_div(cols, 32), (unsigned)nrep);
   LPB_REQUIRE(grid.y <= 65535, "pack_rows_t: too many columns (%lld)", (long long)cols);
   DISPATCH_KIND(kind, (pack_rows_t_kernel<KIND><<<grid, 256, 0, st>>>(src, rows, cols, ld_src, row_scale, scale, flags,
@@ -146,7 +147,7 @@ int pack_conv2d_t(const float* x, const ConvGeom& g, float scale, int flags, int
                   int kind, int64_t ldk, int64_t k0, cudaStream_t st) {
   const int rows = g.C * g.KH * g.KW;
   LPB_REQUIRE(rows <= 65535, "pack_conv2d_t: too many patch rows (%d)", rows);
-  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_conv2d_t: hi+lo output needs a lo buffer");
+  LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_conv2d_t: hi+lo output needs a lo buffer");
   if (g.N == 0) return 0;
   if (reduce_mean) {
     dim3 grid((unsigned)ceil_div(g.N, 256), rows);
@@ -163,7 +164,7 @@ int pack_conv2d_t(const float* x, const ConvGeom& g, float scale, int flags, int
 int pack_nchw_t(const float* gp, int64_t Nn, int Cc, int HW, float scale, int flags, int reduce_sum, void* hi, void* lo,
                 int kind, int64_t ldk, int64_t k0, cudaStream_t st) {
   LPB_REQUIRE(Cc <= 65535, "pack_nchw_t: too many channels (%d)", Cc);
-  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_nchw_t: hi+lo output needs a lo buffer");
+  LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_nchw_t: hi+lo output needs a lo buffer");
   if (Nn == 0) return 0;
   if (reduce_sum) {
     dim3 grid((unsigned)ceil_div(Nn, 256), Cc);
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ D
 int pack_conv2d_rows(const float* x, const ConvGeom& g, void* hi, void* lo, int kind, int64_t ld, cudaStream_t st) {
   const int64_t rows = (int64_t)g.N * g.OH * g.OW;
   if (rows == 0) return 0;
-  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_conv2d_rows: hi+lo output needs a lo buffer");
+  LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_conv2d_rows: hi+lo output needs a lo buffer");
   const int blocks = (int)imin(ceil_div(rows, 8), (int64_t)sm_count() * 32);
   DISPATCH_KIND(kind, (pack_conv2d_rows_kernel<KIND><<<blocks, 256, 0, st>>>(x, g, hi, lo, ld)));
   LPB_CHECK_LAUNCH("pack_conv2d_rows");
@@ -283,7 +284,7 @@ int pack_conv2d_rows(const float* x, const ConvGeom& g, void* hi, void* lo, int 
 
 int pack_nchw_rows(const float* gp, int64_t Q, int Cc, int HW, void* hi, void* lo, int kind, int64_t ld, cudaStream_t st) {
   if (Q == 0) return 0;
-  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_nchw_rows: hi+lo output needs a lo buffer");
+  LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_nchw_rows: hi+lo output needs a lo buffer");
   if (HW == 1) {
     const int64_t total = Q * Cc;
     const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
@@ -306,7 +307,7 @@ int pack_nchw_rows(const float* gp, int64_t Q, int Cc, int HW, void* hi, void* l
 int pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* hi, void* lo, int kind, int64_t ld,
               cudaStream_t st) {
   if (rows == 0 || cols == 0) return 0;
-  LPB_REQUIRE(kind != OUT_BF16_HILO || lo != nullptr, "pack_cast: hi+lo output needs a lo buffer");
+  LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_cast: hi+lo output needs a lo buffer");
   const int blocks = (int)imin(ceil_div(rows * cols, 256), (int64_t)sm_count() * 32);
   DISPATCH_KIND(kind, (pack_cast_kernel<KIND><<<blocks, 256, 0, st>>>(src, rows, cols, ld_src, hi, lo, ld)));
   LPB_CHECK_LAUNCH("pack_cast");

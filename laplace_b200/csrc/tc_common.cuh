@@ -73,8 +73,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// fp16_operands != 0 selects F16 (format 0) instead of BF16 (format 1) for A and B
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fp16_operands = 0) {
+  return (1u << 4) | ((fp16_operands ? 0u : 1u) << 7) | ((fp16_operands ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {

@@ -13,8 +13,8 @@ import torch
 
 from . import _lib
 
-F32, BF16, BF16X3 = 0, 1, 2  # out_kind of the pack kernels (LPB_OUT_*)
-KIND_OF = {"fp32": F32, "bf16": BF16, "bf16x3": BF16X3}
+F32, BF16, BF16X3, F16X3 = 0, 1, 2, 3  # out_kind of the pack kernels (LPB_OUT_*)
+KIND_OF = {"fp32": F32, "bf16": BF16, "bf16x3": BF16X3, "fp16x3": F16X3}
 
 LAUNCHES = 0  # number of native kernel launches issued through this module (bench.py reads it)
 
@@ -63,8 +63,9 @@ def alloc_packed(rows: int, K: int, kind: int, device) -> Packed:
     ldk = max(round_up(K, 8), 8)
     if kind == F32:
         return Packed(torch.empty(rows, ldk, device=device, dtype=torch.float32), None, kind, rows, K)
-    hi = torch.empty(rows, ldk, device=device, dtype=torch.bfloat16)
-    lo = torch.empty(rows, ldk, device=device, dtype=torch.bfloat16) if kind == BF16X3 else None
+    dt = torch.float16 if kind == F16X3 else torch.bfloat16
+    hi = torch.empty(rows, ldk, device=device, dtype=dt)
+    lo = torch.empty(rows, ldk, device=device, dtype=dt) if kind in (BF16X3, F16X3) else None
     return Packed(hi, lo, kind, rows, K)
 
 
@@ -149,8 +150,9 @@ def gemm_nt(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumul
         _lib.call("lpb_gemm_nt_f32", _ptr(A.hi), A.ldk, _ptr(B.hi), B.ldk, M, N, A.K, alpha, 1 if accumulate else 0,
                   _ptr(out), out.stride(0), 1 if symmetric else 0, _stream())
     else:
-        _lib.call("lpb_gemm_nt_bf16", _ptr(A.hi), _ptr(A.lo), A.ldk, _ptr(B.hi), _ptr(B.lo), B.ldk, M, N, A.K, alpha,
-                  1 if accumulate else 0, _ptr(out), out.stride(0), 1 if symmetric else 0, _stream())
+        _lib.call("lpb_gemm_nt_tc", _ptr(A.hi), _ptr(A.lo), A.ldk, _ptr(B.hi), _ptr(B.lo), B.ldk, M, N, A.K, alpha,
+                  1 if accumulate else 0, _ptr(out), out.stride(0), 1 if symmetric else 0, 1 if A.kind == F16X3 else 0,
+                  _stream())
     _bump()
     return out
 
@@ -303,9 +305,9 @@ def conv_nhwc(X: Packed, Q: int, H: int, W: int, Wt: Packed, N: int, KH: int, KW
     """Implicit-GEMM stride-1 convolution on NHWC bf16(hi/lo) rows ``X [(q,h,w), Kc]`` with tap-major weights
     ``Wt [(tap, n), Kc]``; ``out [(q,h,w), N]`` fp32 is overwritten."""
     _check(out, name="out")
-    assert X.kind in (BF16, BF16X3) and X.kind == Wt.kind and X.rows == Q * H * W and Wt.rows == KH * KW * N and X.K == Wt.K
+    assert X.kind in (BF16, BF16X3, F16X3) and X.kind == Wt.kind and X.rows == Q * H * W and Wt.rows == KH * KW * N and X.K == Wt.K
     assert out.shape == (Q * H * W, N) and out.stride(1) == 1
-    _lib.call("lpb_conv_nhwc_bf16", _ptr(X.hi), _ptr(X.lo), Q, H, W, X.K, X.ldk, _ptr(Wt.hi), _ptr(Wt.lo), Wt.ldk, N, KH, KW,
-              base_h, base_w, sgn, alpha, _ptr(out), out.stride(0), _stream())
+    _lib.call("lpb_conv_nhwc_tc", _ptr(X.hi), _ptr(X.lo), Q, H, W, X.K, X.ldk, _ptr(Wt.hi), _ptr(Wt.lo), Wt.ldk, N, KH, KW,
+              base_h, base_w, sgn, alpha, _ptr(out), out.stride(0), 1 if X.kind == F16X3 else 0, _stream())
     _bump()
     return out

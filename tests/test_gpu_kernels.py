@@ -15,7 +15,7 @@ def _dense(p):
     return p.hi[:, :p.K].float().cpu() + (p.lo[:, :p.K].float().cpu() if p.lo is not None else 0)
 
 
-@pytest.mark.parametrize("kind,tol", [(K.F32, 0.0), (K.BF16, 4e-3), (K.BF16X3, 2e-5)])
+@pytest.mark.parametrize("kind,tol", [(K.F32, 0.0), (K.BF16, 4e-3), (K.BF16X3, 2e-5), (K.F16X3, 5e-7)])
 @pytest.mark.parametrize("shape", [(1, 1), (37, 5), (64, 64), (1000, 130), (33, 513)])
 def test_pack_rows(kind, tol, shape):
     torch.manual_seed(0)
@@ -74,7 +74,7 @@ def test_gemm_nt_f32(M, N, Kc):
 
 @pytest.mark.parametrize("M,N,Kc", [(128, 128, 64), (128, 128, 4096), (100, 60, 50), (513, 257, 2048), (300, 300, 40000),
                                     (1000, 1000, 512), (64, 2000, 130)])
-@pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 2e-6)])
 def test_gemm_nt_tensor_core(M, N, Kc, kind, tol):
     torch.manual_seed(3)
     A, B = torch.randn(M, Kc), torch.randn(N, Kc)
