@@ -347,11 +347,12 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
         return orig
 
     def bytes_packed(p):
-        per = {K.F32: 4, K.BF16: 2, K.BF16X3: 4}[p.kind]
+        per = {K.F32: 4, K.BF16: 2, K.BF16X3: 4, K.F16X3: 4}[p.kind]
         return p.rows * p.K * (4 + per)
 
     works = {
         "gemm_nt": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[1].rows * a[0].K, a[0].kind != K.F32),
+        "gemm_tn": lambda r, a, kw: ("flops", 2.0 * a[0].K * a[1].K * a[0].rows, True),
         "conv_nhwc": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[5] * a[0].K * a[6] * a[7], True),
         "pack_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
         "pack_conv": lambda r, a, kw: ("bytes", bytes_packed(r[0]), False),
@@ -384,7 +385,8 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
     d = fam[dom]
     tensor = d["kind"] == "flops"
     peak = (pk["bf16_sustained"] or 1400.0) if tensor else (pk["hbm"] or 6650.0)
-    names = {"gemm_nt": "tc::gemm_nt_tc_kernel (tcgen05 GEMM-NT/SYRK: KFAC factor contractions + explicit-engine GEMMs)",
+    names = {"gemm_nt": "tc::gemm_nt_tc_kernel<.,false> (tcgen05 GEMM-NT/SYRK, K-major operands: KFAC factor contractions + explicit-engine GEMMs)",
+             "gemm_tn": "tc::gemm_nt_tc_kernel<.,true> (tcgen05 SYRK on row-major operands, MN-major descriptors: KFAC factor contractions)",
              "conv_nhwc": "tc::conv_nhwc_tc_kernel (tcgen05 implicit-GEMM convolution, forward + backward-data)"}
     return {"bound": "tensor" if tensor else "hbm", "kernel": names.get(dom, "lpb::" + dom + "_kernel"),
             "achieved": d["achieved"], "peak": peak, "unit": d["unit"], "frac": d["achieved"] / peak, "traffic": None,

@@ -60,6 +60,13 @@ int lpb_pack_conv2d_t(const float* x, int N, int C, int H, int W, int KH, int KW
 int lpb_pack_nchw_t(const float* g, int64_t Nn, int Cc, int HW, float scale, int flags, int reduce_sum, void* dst_hi,
                     void* dst_lo, int out_kind, int64_t ldk, int64_t k0, void* stream);
 
+/* same contraction on ROW-major operands (sample rows x features, the layout activations and gradients already
+ * have): D[M, N] (+)= alpha * A[K, M]^T * B[K, N]; tcgen05 with MN-major shared-memory descriptors, so X^T X
+ * needs no transposing pack.  lda >= M, ldb >= N (multiples of 8 elements).                                    */
+int lpb_gemm_tn_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                   int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                   int fp16_operands, void* stream);
+
 /* ---- convolution engine operands (forward / backward-data of nn.Conv2d as GEMMs) ----------
  * Replaces the model-side torch.func / autograd convolution passes the reference runs below
  * CurvatureInterface.jacobians (curvature/curvature.py:111-117) when fp32-accurate Jacobians are required. */

@@ -27,6 +27,8 @@ SIGNATURES = {
     "lpb_gemm_nt_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_vp],
     "lpb_gemm_nt_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
                        c_vp],
+    "lpb_gemm_tn_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
+                       c_vp],
     "lpb_conv_nhwc_tc": [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int,
                          c_int, c_f32, c_vp, c_i64, c_int, c_vp],
     "lpb_shared_weight_contract": [c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp,

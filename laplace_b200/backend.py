@@ -141,6 +141,10 @@ class _B200Mixin:
     def _forward(self, x):
         self._plan()
         self._acts, self._outs = {}, {}
+        if self.conv_engine:
+            from . import conv_engine
+
+            conv_engine.STASH.clear()
         self._capturing = True
         try:
             with torch.enable_grad(), self._model_numerics(), self._conv_patch():
@@ -210,8 +214,7 @@ class _B200Mixin:
         for L, g, o in zip(self._layers, grads, outs):
             if g is None:
                 g = torch.zeros((cols.shape[0],) + tuple(o.shape), device=o.device, dtype=torch.float32)
-            g = g.detach().float()
-            res.append(g if (g.dim() == 5 and g.stride(2) == 1 and g.permute(0, 1, 3, 4, 2).is_contiguous()) else g.contiguous())
+            res.append(g.detach().float())   # layout fixed lazily by the consumers (no copy when unused)
         self._outs = {}
         return res
 
@@ -279,7 +282,7 @@ class _B200Mixin:
             if not reduce and g.stride(2) == 1 and g.permute(0, 1, 3, 4, 2).is_contiguous():
                 # channels_last gradients (convolution engine): rows [(col,n,h,w), Co] -> tiled transpose
                 return K.pack_rows(g.permute(0, 1, 3, 4, 2).reshape(nc * M * OH * OW, Co), kind)
-            return K.pack_nchw(g.reshape(nc * M, Co, OH * OW), kind, reduce_sum=reduce)
+            return K.pack_nchw(g.reshape(nc * M, Co, OH * OW).contiguous(), kind, reduce_sum=reduce)
         nc, M = g.shape[:2]
         rows = g.reshape(nc * M, -1, g.shape[-1])
         if reduce and rows.shape[1] > 1:
@@ -310,26 +313,49 @@ class _B200Mixin:
         kron = B200Kron.zeros(dims, fd.device, torch.float32)
         sq = math.sqrt(self.factor)
         idx = 0
+        stash = {}
+        if (self.conv_engine and not reduce and self.precision in ("auto", "bf16x3")
+                and (cols.shape[0] == 1 or getattr(self, "last_backward_mode", "") == "batched")):
+            from . import conv_engine
+
+            stash = conv_engine.STASH   # row-major operands the engine already packed for this batch
         for L, g in zip(self._layers, grads):
             a = acts[L.name]
             ncols = g.shape[0]
-            gk = self._kind(L.d_out, g.numel() // L.d_out)
-            G = self._pack_grad(L, g, gk, reduce)
+            rows = stash.get(id(L.mod), {}) if L.is_conv else {}
+            Grows = rows.get("G")
+            if Grows is not None and Grows.rows != g.numel() // L.d_out:
+                Grows = None
+            if Grows is None:
+                gk = self._kind(L.d_out, g.numel() // L.d_out)
+                G = self._pack_grad(L, g, gk, reduce)
+
+            def syrk_B(out, alpha):
+                if Grows is not None:   # MN-major SYRK straight on the engine's gradient rows
+                    K.gemm_tn(Grows, Grows, out, alpha=alpha, accumulate=True, symmetric=True)
+                else:
+                    K.gemm_nt(G, G, out, alpha=alpha, accumulate=True, symmetric=True)
+
             if L.has_w:
                 Bf, Af = kron.kfacs[idx]
-                k_rows = (g.numel() // (ncols * L.d_out)) if L.is_conv else (a.numel() // a.shape[-1])
-                ak = self._kind(L.d_in, M if reduce else k_rows)
-                A, T = self._pack_act(L, a, ak, reduce)
-                Teff = 1 if reduce else T
-                # A = factor^(1/2) * (M/N) * 1/(M*T) * sum a a^T   (curvlinops.py:46-53, matrix.py:116-118)
-                K.gemm_nt(A, A, Af, alpha=sq / (N * Teff), accumulate=True, symmetric=True)
-                K.gemm_nt(G, G, Bf, alpha=sq * weight, accumulate=True, symmetric=True)
+                Prows = rows.get("P")
+                if Prows is not None:
+                    T = Prows.rows // M
+                    K.gemm_tn(Prows, Prows, Af, alpha=sq / (N * T), accumulate=True, symmetric=True)
+                else:
+                    k_rows = (g.numel() // (ncols * L.d_out)) if L.is_conv else (a.numel() // a.shape[-1])
+                    ak = self._kind(L.d_in, M if reduce else k_rows)
+                    A, T = self._pack_act(L, a, ak, reduce)
+                    Teff = 1 if reduce else T
+                    # A = factor^(1/2) * (M/N) * 1/(M*T) * sum a a^T   (curvlinops.py:46-53, matrix.py:116-118)
+                    K.gemm_nt(A, A, Af, alpha=sq / (N * Teff), accumulate=True, symmetric=True)
+                syrk_B(Bf, sq * weight)
                 idx += 1
                 if L.has_b:
                     kron.kfacs[idx][0].copy_(Bf).mul_(sq)  # bias block: factor * B   (len(F) == 1)
                     idx += 1
             elif L.has_b:
-                K.gemm_nt(G, G, kron.kfacs[idx][0], alpha=self.factor * weight, accumulate=True, symmetric=True)
+                syrk_B(kron.kfacs[idx][0], self.factor * weight)
                 idx += 1
         dtype = next(self.model.parameters()).dtype
         if dtype != torch.float32:
@@ -367,6 +393,7 @@ class _B200Mixin:
             off_w = off if L.has_w else -1
             off_b = (off + (L.d_out * L.d_in if L.has_w else 0)) if L.has_b else -1
             if not shared:
+                g = g.contiguous()
                 K.jac_linear_write(g, a.contiguous(), Z, sn, sc, off_w, off_b)
                 if L.has_w:
                     blocks.append(("outer", g, a.contiguous()))

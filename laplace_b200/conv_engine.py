@@ -22,6 +22,7 @@ from torch import nn
 
 from . import kernels as K
 
+import math
 import os
 
 KIND = K.BF16X3       # reverse pass: gradients span many orders of magnitude -> bf16 hi/lo (8-bit exponent)
@@ -46,20 +47,32 @@ class _WeightCache:
             return hit[1]
         w2 = w.detach().reshape(w.shape[0], -1)
         w2 = w2 if w2.dtype == torch.float32 else w2.float()
+        scale = 1.0
+        if which in ("fwd", "fwd_taps"):
+            # fp16 hi/lo operands: weights are tiny (|w| <= 1/sqrt(fan_in)), their lo halves would fall into the fp16
+            # subnormals -- pre-scale by a power of two so that max|w| sits near 2^10 (one host sync per weight version)
+            amax = float(w2.abs().max())
+            scale = 2.0 ** math.floor(math.log2(1024.0 / amax)) if amax > 0 else 1.0
         if which == "fwd":
-            packed = K.pack_cast(w2.contiguous(), KIND_FWD)
+            packed = K.pack_cast((w2 * scale).contiguous(), KIND_FWD)
         elif which == "bwd":
             packed = K.pack_rows(w2.contiguous(), KIND)
         else:  # tap-major weights of the implicit-GEMM kernel
-            w4 = w.detach().float()
+            w4 = w.detach().float() * scale
             perm = (2, 3, 0, 1) if which == "fwd_taps" else (2, 3, 1, 0)
             w4 = w4.permute(*perm).reshape(-1, w4.shape[1] if which == "fwd_taps" else w4.shape[0]).contiguous()
             packed = K.pack_cast(w4, KIND_FWD if which == "fwd_taps" else KIND)
+        packed.inv_scale = 1.0 / scale
         self.store[key] = (tag, packed)
         return packed
 
 
 _CACHE = _WeightCache()
+
+# Row-major 16-bit operands produced while running the passes of the current batch, keyed by id(module):
+#   "P": patch rows [(n,t), d_in] of explicit-path forwards, "G": output-gradient rows [(col,n,t), C_out].
+# The KFAC factor SYRKs consume them directly through the MN-major GEMM (no second, transposing pack).
+STASH: dict = {}
 
 
 def implicit_ok(mod: nn.Conv2d, H: int, W: int) -> bool:
@@ -79,14 +92,15 @@ def nhwc_rows(x: torch.Tensor, kind: int) -> K.Packed:
     return K.pack_nchw_rows(x.contiguous().reshape(N, C, H * W), kind)
 
 
-def _implicit(x: torch.Tensor, mod: nn.Conv2d, which: str, n_out: int, sgn: int) -> torch.Tensor:
+def _implicit(x: torch.Tensor, mod: nn.Conv2d, which: str, n_out: int, sgn: int, X: K.Packed | None = None) -> torch.Tensor:
     N, _, H, W = x.shape
     kh, kw = mod.kernel_size
-    X = nhwc_rows(x, KIND_FWD if sgn > 0 else KIND)
+    if X is None:
+        X = nhwc_rows(x, KIND_FWD if sgn > 0 else KIND)
     Wt = _CACHE.get(mod, which)
     out = torch.empty(N * H * W, n_out, device=x.device, dtype=torch.float32)
     ph, pw = mod.padding
-    K.conv_nhwc(X, N, H, W, Wt, n_out, kh, kw, -sgn * ph, -sgn * pw, sgn, out)
+    K.conv_nhwc(X, N, H, W, Wt, n_out, kh, kw, -sgn * ph, -sgn * pw, sgn, out, alpha=getattr(Wt, "inv_scale", 1.0))
     return out.view(N, H, W, n_out).permute(0, 3, 1, 2)     # channels_last view, no copy
 
 
@@ -99,22 +113,26 @@ def conv_forward(x: torch.Tensor, mod: nn.Conv2d) -> torch.Tensor:
     Co = mod.out_channels
     OH, OW = K.conv_out_hw(x.shape, mod)
     P = K.pack_conv_rows(x, mod, KIND_FWD)                   # [(n,t), d_in]
+    STASH.setdefault(id(mod), {})["P"] = P
     Wk = _CACHE.get(mod, "fwd")                              # [Co, d_in]
     out = torch.empty(Co, N * OH * OW, device=x.device, dtype=torch.float32)
-    K.gemm_nt(Wk, P, out, 1.0, accumulate=False)
+    K.gemm_nt(Wk, P, out, getattr(Wk, "inv_scale", 1.0), accumulate=False)
     out = out.view(Co, N, OH * OW).permute(1, 0, 2).reshape(N, Co, OH, OW)
     if mod.bias is not None:
         out = out + mod.bias.detach().view(1, -1, 1, 1)
     return out
 
 
-def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape) -> torch.Tensor:
-    if implicit_ok(mod, in_shape[2], in_shape[3]):
-        return _implicit(g, mod, "bwd_taps", mod.in_channels, -1)
-    g = g.contiguous()
+def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape, need_dx: bool = True):
+    """Packs the output-gradient rows (stashed for the B-factor SYRK) and, if ``need_dx``, returns the input gradient."""
     Q, Co = g.shape[0], g.shape[1]
     T = g.shape[2] * g.shape[3]
-    G = K.pack_nchw_rows(g.reshape(Q, Co, T), KIND)          # [(q,t), Co]
+    G = nhwc_rows(g, KIND)                                   # [(q,t), Co]
+    STASH.setdefault(id(mod), {})["G"] = G
+    if not need_dx:
+        return None
+    if implicit_ok(mod, in_shape[2], in_shape[3]):
+        return _implicit(g, mod, "bwd_taps", mod.in_channels, -1, X=G)
     Wt = _CACHE.get(mod, "bwd")                              # [d_in, Co]
     Dc = torch.empty(Wt.rows, Q * T, device=g.device, dtype=torch.float32)
     K.gemm_nt(Wt, G, Dc, 1.0, accumulate=False)
@@ -123,8 +141,9 @@ def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape) -> torch.Tenso
 
 class _ConvBwdData(torch.autograd.Function):
     @staticmethod
-    def forward(g, mod, in_shape):
-        return conv_backward_data(g if g.dtype == torch.float32 else g.float(), mod, in_shape)
+    def forward(g, mod, in_shape, need_dx):
+        out = conv_backward_data(g if g.dtype == torch.float32 else g.float(), mod, in_shape, need_dx)
+        return out if out is not None else g.new_empty(0)
 
     @staticmethod
     def setup_context(ctx, inputs, output):
@@ -135,10 +154,12 @@ class _ConvBwdData(torch.autograd.Function):
         raise NotImplementedError("double backward through the convolution engine is not supported")
 
     @staticmethod
-    def vmap(info, in_dims, g, mod, in_shape):
+    def vmap(info, in_dims, g, mod, in_shape, need_dx):
         g = g.movedim(in_dims[0], 0)
         nb, B = g.shape[0], g.shape[1]
-        out = _ConvBwdData.apply(g.reshape(nb * B, *g.shape[2:]), mod, (nb * B,) + tuple(in_shape[1:]))
+        out = _ConvBwdData.apply(g.reshape(nb * B, *g.shape[2:]), mod, (nb * B,) + tuple(in_shape[1:]), need_dx)
+        if out.numel() == 0:
+            return out, None
         return out.view(nb, B, *out.shape[1:]), 0
 
 
@@ -155,8 +176,8 @@ class _Conv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        gx = _ConvBwdData.apply(g, ctx.mod, ctx.in_shape) if ctx.needs_input_grad[0] else None
-        return gx, None, None
+        gx = _ConvBwdData.apply(g, ctx.mod, ctx.in_shape, bool(ctx.needs_input_grad[0]))
+        return (gx if ctx.needs_input_grad[0] else None), None, None
 
 
 def supported(mod: nn.Module) -> bool:

@@ -41,6 +41,8 @@ int gemm_nt_f32(const float*, int64_t, const float*, int64_t, int64_t, int64_t, 
                 cudaStream_t);
 int gemm_nt_bf16(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
                  int, float*, int64_t, int, int, cudaStream_t);
+int gemm_tn_rows(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
+                 int, float*, int64_t, int, int, cudaStream_t);
 int conv_nhwc_bf16(const void*, const void*, int64_t, int, int, int64_t, int64_t, const void*, const void*, int64_t, int, int,
                    int, int, int, int, float, float*, int64_t, int, cudaStream_t);
 int shared_weight_contract(int, const float*, int64_t, const float*, int64_t, int, int, int, int, int, float, float*,
@@ -161,6 +163,15 @@ int lpb_gemm_nt_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* 
   LPB_REQUIRE(lda >= K && ldb >= K && ldd >= N, "lpb_gemm_nt_tc: leading dimension too small");
   LPB_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "lpb_gemm_nt_tc: A_lo and B_lo must both be given or both NULL");
   return lpb::gemm_nt_bf16(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, fp16_operands,
+                           ST(stream));
+}
+
+int lpb_gemm_tn_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                   int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                   int fp16_operands, void* stream) {
+  LPB_REQUIRE(lda >= M && ldb >= N && ldd >= N, "lpb_gemm_tn_tc: leading dimension too small");
+  LPB_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "lpb_gemm_tn_tc: A_lo and B_lo must both be given or both NULL");
+  return lpb::gemm_tn_rows(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, fp16_operands,
                            ST(stream));
 }
 

@@ -18,7 +18,10 @@ namespace lpb {
 
 namespace tc {
 
-template <int NPROD>
+// MN = false: operands K-major  (A[M, K], B[N, K], contraction index contiguous)          D = A B^T
+// MN = true : operands MN-major (A[K, M], B[K, N], row-major "sample rows x features")   D = A^T B
+//             -- the layout activations / gradients already have, so XᵀX needs no transposing pack.
+template <int NPROD, bool MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int M, int N,
@@ -73,11 +76,19 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
         // diagonal SYRK tiles use the A tile for both operands: half the TMA traffic
         mbar_expect_tx(&full_bar[stage], diag ? STAGE_BYTES / 2 : STAGE_BYTES);
-        tma_load_2d(&tmA_hi, &full_bar[stage], st, kc * BK, tm * BM);
-        if (!diag) tma_load_2d(&tmB_hi, &full_bar[stage], st + TILE_BYTES, kc * BK, tn * BN);
+        auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, int tile) {
+          if (MN) {  // two boxes of 64 features x 64 rows (128 B per row, 8 KiB each)
+            tma_load_2d(map, &full_bar[stage], dst, tile * BM, kc * BK);
+            tma_load_2d(map, &full_bar[stage], dst + TILE_BYTES / 2, tile * BM + 64, kc * BK);
+          } else {
+            tma_load_2d(map, &full_bar[stage], dst, kc * BK, tile * BM);
+          }
+        };
+        load_tile(&tmA_hi, st, tm);
+        if (!diag) load_tile(&tmB_hi, st + TILE_BYTES, tn);
         if (NPROD == 3) {
-          tma_load_2d(&tmA_lo, &full_bar[stage], st + 2 * TILE_BYTES, kc * BK, tm * BM);
-          if (!diag) tma_load_2d(&tmB_lo, &full_bar[stage], st + 3 * TILE_BYTES, kc * BK, tn * BN);
+          load_tile(&tmA_lo, st + 2 * TILE_BYTES, tm);
+          if (!diag) load_tile(&tmB_lo, st + 3 * TILE_BYTES, tn);
         }
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
@@ -85,21 +96,23 @@ gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN, fp16_operands);
+      const uint32_t idesc = make_idesc(BM, BN, fp16_operands, MN ? 1 : 0);
+      auto mk = [](uint32_t saddr) { return MN ? make_smem_desc_mn(saddr, TILE_BYTES / 2) : make_smem_desc(saddr); };
       int stage = 0; uint32_t phase = 0; uint32_t acc = 0;
       for (int kc = kc_begin; kc < kc_end; ++kc) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        const uint64_t a_hi = make_smem_desc(sbase), b_hi = diag ? a_hi : make_smem_desc(sbase + TILE_BYTES);
+        const uint64_t a_hi = mk(sbase), b_hi = diag ? a_hi : mk(sbase + TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+          // K-major: 16 elements = 32 B along the swizzled row; MN-major: 16 rows = two 8-row groups = 2048 B
+          const uint64_t koff = (uint64_t)((MN ? k * UMMA_K * 128 : k * UMMA_K * 2) >> 4);
           umma_f16(tmem_base, a_hi + koff, b_hi + koff, idesc, acc);
           acc = 1;
           if (NPROD == 3) {
-            const uint64_t a_lo = make_smem_desc(sbase + 2 * TILE_BYTES);
-            const uint64_t b_lo = diag ? a_lo : make_smem_desc(sbase + 3 * TILE_BYTES);
+            const uint64_t a_lo = mk(sbase + 2 * TILE_BYTES);
+            const uint64_t b_lo = diag ? a_lo : mk(sbase + 3 * TILE_BYTES);
             umma_f16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
             umma_f16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);
           }
@@ -176,6 +189,22 @@ PFN_encodeTiled get_tensormap_encoder() {
   return fn;
 }
 
+// row-major [rows, cols] matrix, boxes of 64 columns (128 B) x 64 rows: the MN-major operand tiles
+static int make_tmap_rows(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_encodeTiled enc = get_tensormap_encoder();
+  LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)tc::BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rows) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld) {
   PFN_encodeTiled enc = get_tensormap_encoder();
   LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
@@ -191,9 +220,25 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int
   return 0;
 }
 
+static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                   int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                   int fp16_operands, cudaStream_t st);
+
 int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
                  int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
                  int fp16_operands, cudaStream_t st) {
+  return gemm_tc(false, A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, fp16_operands, st);
+}
+
+int gemm_tn_rows(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                 int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                 int fp16_operands, cudaStream_t st) {
+  return gemm_tc(true, A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, fp16_operands, st);
+}
+
+static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
+                   int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
+                   int fp16_operands, cudaStream_t st) {
   LPB_REQUIRE(!symmetric || M == N, "gemm_nt_bf16: symmetric needs M == N");
   LPB_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "gemm_nt_bf16: leading dimensions must be multiples of 8 elements");
   LPB_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 &&
@@ -213,9 +258,12 @@ int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_
   if (K == 0) return 0;
   const bool x3 = A_lo != nullptr;
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
-  if (make_tmap_2d(&tA_hi, A_hi, M, K, lda) || make_tmap_2d(&tB_hi, B_hi, N, K, ldb)) return 1;
+  auto mkmap = [&](CUtensorMap* m, const void* p, int64_t feat, int64_t ld) {
+    return mn ? make_tmap_rows(m, p, K, feat, ld) : make_tmap_2d(m, p, feat, K, ld);
+  };
+  if (mkmap(&tA_hi, A_hi, M, lda) || mkmap(&tB_hi, B_hi, N, ldb)) return 1;
   if (x3) {
-    if (make_tmap_2d(&tA_lo, A_lo, M, K, lda) || make_tmap_2d(&tB_lo, B_lo, N, K, ldb)) return 1;
+    if (mkmap(&tA_lo, A_lo, M, lda) || mkmap(&tB_lo, B_lo, N, ldb)) return 1;
   } else {
     tA_lo = tA_hi; tB_lo = tB_hi;
   }
@@ -233,29 +281,27 @@ int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_
   const int stage_bytes = (x3 ? 4 : 2) * tc::TILE_BYTES;
   const int num_stages = x3 ? 3 : 6;
   const size_t smem = (size_t)num_stages * stage_bytes + (2 * num_stages + 1) * sizeof(uint64_t) + 16 + 1024;
-  static bool attr1 = false, attr3 = false;
-  if (x3 && !attr3) {
-    if (check_cuda(cudaFuncSetAttribute(tc::gemm_nt_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                   "gemm_nt_bf16 attr"))
-      return 1;
-    attr3 = true;
-  }
-  if (!x3 && !attr1) {
-    if (check_cuda(cudaFuncSetAttribute(tc::gemm_nt_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                   "gemm_nt_bf16 attr"))
-      return 1;
-    attr1 = true;
-  }
-  LPB_REQUIRE(tiles <= 2147483647LL, "gemm_nt_bf16: too many tiles");
+  LPB_REQUIRE(tiles <= 2147483647LL, "gemm_tc: too many tiles");
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  if (x3)
-    tc::gemm_nt_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
-                                                                  symmetric, tiles_m, tiles_n, total_kchunks,
-                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0, fp16_operands);
-  else
-    tc::gemm_nt_tc_kernel<1><<<grid, tc::NUM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd,
-                                                                  symmetric, tiles_m, tiles_n, total_kchunks,
-                                                                  kchunks_per_split, num_stages, store_mode ? 1 : 0, fp16_operands);
+#define LPB_LAUNCH_TC(NP, MNV)                                                                                          \
+  do {                                                                                                                  \
+    static bool attr_done = false;                                                                                      \
+    if (!attr_done) {                                                                                                   \
+      if (check_cuda(cudaFuncSetAttribute(tc::gemm_nt_tc_kernel<NP, MNV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          227 * 1024),                                                                  \
+                     "gemm_tc attr"))                                                                                   \
+        return 1;                                                                                                       \
+      attr_done = true;                                                                                                 \
+    }                                                                                                                   \
+    tc::gemm_nt_tc_kernel<NP, MNV><<<grid, tc::NUM_THREADS, smem, st>>>(                                                \
+        tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd, symmetric, tiles_m, tiles_n, total_kchunks,          \
+        kchunks_per_split, num_stages, store_mode ? 1 : 0, fp16_operands);                                              \
+  } while (0)
+  if (x3 && mn) LPB_LAUNCH_TC(3, true);
+  else if (x3) LPB_LAUNCH_TC(3, false);
+  else if (mn) LPB_LAUNCH_TC(1, true);
+  else LPB_LAUNCH_TC(1, false);
+#undef LPB_LAUNCH_TC
   LPB_CHECK_LAUNCH("gemm_nt_bf16");
   return 0;
 }

@@ -73,10 +73,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=128
-// fp16_operands != 0 selects F16 (format 0) instead of BF16 (format 1) for A and B
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fp16_operands = 0) {
-  return (1u << 4) | ((fp16_operands ? 0u : 1u) << 7) | ((fp16_operands ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+// fp16_operands != 0 selects F16 (format 0) instead of BF16 (format 1) for A and B; mn_major != 0 marks both
+// operands MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fp16_operands = 0, int mn_major = 0) {
+  return (1u << 4) | ((fp16_operands ? 0u : 1u) << 7) | ((fp16_operands ? 0u : 1u) << 10) | ((mn_major ? 1u : 0u) << 15) |
+         ((mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// MN-major tile, 128B swizzle: canonical layout ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in 16-bit elements --
+// 64 features contiguous (128 B), successive sample rows 128 B apart, 8-row groups SBO = 1024 B apart,
+// 64-feature blocks LBO = `mn_block_bytes` apart (one TMA box).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset
+  d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {

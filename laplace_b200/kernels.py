@@ -311,3 +311,18 @@ def conv_nhwc(X: Packed, Q: int, H: int, W: int, Wt: Packed, N: int, KH: int, KW
               base_h, base_w, sgn, alpha, _ptr(out), out.stride(0), 1 if X.kind == F16X3 else 0, _stream())
     _bump()
     return out
+
+
+def gemm_tn(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumulate: bool = True,
+            symmetric: bool = False) -> torch.Tensor:
+    """``out[M,N] (+)= alpha * A^T B`` for ROW-major 16-bit operands ``A [K_rows, M]``, ``B [K_rows, N]``
+    (``Packed.rows`` = sample rows, ``Packed.K`` = features): the tcgen05 kernel with MN-major descriptors."""
+    _check(out, name="out")
+    M, N = out.shape
+    assert A.kind in (BF16, BF16X3, F16X3) and A.kind == B.kind and A.K == M and B.K == N and A.rows == B.rows
+    if symmetric:
+        assert A.hi.data_ptr() == B.hi.data_ptr() and M == N
+    _lib.call("lpb_gemm_tn_tc", _ptr(A.hi), _ptr(A.lo), A.ldk, _ptr(B.hi), _ptr(B.lo), B.ldk, M, N, A.rows, alpha,
+              1 if accumulate else 0, _ptr(out), out.stride(0), 1 if symmetric else 0, 1 if A.kind == F16X3 else 0, _stream())
+    _bump()
+    return out

@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc", "gemm_tn"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -221,4 +221,13 @@ def conv_nhwc(X, Q, H, W, Wt, N, KH, KW, base_h, base_w, sgn, out, alpha=1.0):
                 shifted[:, hs:he, ws:we] = x[:, hs + dh:he + dh, ws + dw:we + dw]
             res += torch.einsum("qhwk,nk->qhwn", shifted, w[kh * KW + kw])
     out.copy_(alpha * res.reshape(Q * H * W, N))
+    return out
+
+
+def gemm_tn(A, B, out, alpha=1.0, accumulate=True, symmetric=False):
+    res = alpha * (A.hi[:, :A.K].float().t() @ B.hi[:, :B.K].float())
+    if accumulate:
+        out += res
+    else:
+        out.copy_(res)
     return out

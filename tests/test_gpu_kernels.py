@@ -74,7 +74,7 @@ def test_gemm_nt_f32(M, N, Kc):
 
 @pytest.mark.parametrize("M,N,Kc", [(128, 128, 64), (128, 128, 4096), (100, 60, 50), (513, 257, 2048), (300, 300, 40000),
                                     (1000, 1000, 512), (64, 2000, 130)])
-@pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 2e-6)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 1e-5)])
 def test_gemm_nt_tensor_core(M, N, Kc, kind, tol):
     torch.manual_seed(3)
     A, B = torch.randn(M, Kc), torch.randn(N, Kc)
@@ -201,3 +201,24 @@ def test_eigh_jacobi(n):
     Au = A.clone(); Au[:, 1:, 0] = 123.0
     ev2, _ = K.eigh_jacobi(Au.to(DEV))
     assert torch.allclose(ev2.cpu().double(), ev, atol=1e-6)
+
+
+@pytest.mark.parametrize("Kr,M,N", [(64, 128, 128), (512, 64, 64), (1000, 200, 96), (4096, 128, 128), (5000, 513, 257), (40000, 300, 300), (33, 10, 10)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 1e-5)])
+def test_gemm_tn_rows_operands(Kr, M, N, kind, tol):
+    """MN-major tcgen05 path: D = A^T B on row-major [samples, features] operands (no transposing pack)."""
+    torch.manual_seed(9)
+    A, B = torch.randn(Kr, M), torch.randn(Kr, N)
+    ref = A.double().t() @ B.double()
+    pa, pb = K.pack_cast(A.to(DEV), kind), K.pack_cast(B.to(DEV), kind)
+    out = torch.zeros(M, N, device=DEV)
+    K.gemm_tn(pa, pb, out, alpha=2.0, accumulate=True)
+    K.gemm_tn(pa, pb, out, alpha=-1.0, accumulate=True)
+    assert rel_fro(out.cpu(), ref) < tol
+    out.fill_(3.0)
+    K.gemm_tn(pa, pb, out, alpha=1.0, accumulate=False)
+    assert rel_fro(out.cpu(), ref) < tol
+    if M == N:
+        sym = torch.zeros(M, M, device=DEV)
+        K.gemm_tn(pa, pa, sym, alpha=1.0, accumulate=True, symmetric=True)
+        assert rel_fro(sym.cpu(), A.double().t() @ A.double()) < tol
