@@ -339,6 +339,11 @@ class _B200Mixin:
             if L.has_w:
                 Bf, Af = kron.kfacs[idx]
                 Prows = rows.get("P")
+                if Prows is None and L.is_conv and stash is not None and len(stash) > 0:
+                    # implicit-path convolution: build the patch rows once (row-major pack is ~2x cheaper than the
+                    # transposing K-major one) and contract them with the MN-major SYRK
+                    af = a.float() if a.dtype != torch.float32 else a
+                    Prows = K.pack_conv_rows(af, L.mod, K.BF16X3)
                 if Prows is not None:
                     T = Prows.rows // M
                     K.gemm_tn(Prows, Prows, Af, alpha=sq / (N * T), accumulate=True, symmetric=True)

@@ -314,9 +314,48 @@ int pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void
   return 0;
 }
 
+// small images (H*W <= 64): one thread per (q, ci) accumulates its whole input image in shared memory.  All reads
+// of a warp are contiguous (columns (q, oh, ow) of one Dc row), no modulo / parity tests per element -- the
+// scatter form, which is exact for any stride / dilation.
+__global__ void __launch_bounds__(128) col2im_small_kernel(const float* __restrict__ Dc, int64_t ldd, ConvGeom g,
+                                                            float* __restrict__ out) {
+  extern __shared__ float acc[];  // [H*W][129] (padded: conflict-free in both phases)
+  const int HW = g.H * g.W, T = g.OH * g.OW;
+  const int tid = threadIdx.x, ci = blockIdx.y;
+  const int64_t q0 = (int64_t)blockIdx.x * 128, q = q0 + tid;
+  for (int i = 0; i < HW; ++i) acc[i * 129 + tid] = 0.f;
+  if (q < g.N) {
+    for (int kh = 0; kh < g.KH; ++kh)
+      for (int kw = 0; kw < g.KW; ++kw) {
+        const float* row = Dc + (int64_t)((ci * g.KH + kh) * g.KW + kw) * ldd + q * T;
+        for (int oh = 0; oh < g.OH; ++oh) {
+          const int ih = oh * g.SH - g.PH + kh * g.DH;
+          if (ih < 0 || ih >= g.H) continue;
+          for (int ow = 0; ow < g.OW; ++ow) {
+            const int iw = ow * g.SW - g.PW + kw * g.DW;
+            if (iw >= 0 && iw < g.W) acc[(ih * g.W + iw) * 129 + tid] += __ldg(row + oh * g.OW + ow);
+          }
+        }
+      }
+  }
+  __syncthreads();
+  // coalesced write-out: the block owns rows q0..q0+127 of channel ci
+  const int nq = (int)imin(128, g.N - q0);
+  for (int e = tid; e < nq * HW; e += 128) {
+    const int ql = e / HW, idx = e - ql * HW;
+    out[((q0 + ql) * g.C + ci) * HW + idx] = acc[idx * 129 + ql];
+  }
+}
+
 int col2im(const float* Dc, int64_t ldd, const ConvGeom& g, float* out, cudaStream_t st) {
   const int64_t per_c = (int64_t)g.N * g.H * g.W;
   if (per_c == 0) return 0;
+  if (g.H * g.W <= 64 && g.C <= 65535) {
+    dim3 grid((unsigned)ceil_div(g.N, 128), (unsigned)g.C);
+    col2im_small_kernel<<<grid, 128, (size_t)g.H * g.W * 129 * sizeof(float), st>>>(Dc, ldd, g, out);
+    LPB_CHECK_LAUNCH("col2im_small");
+    return 0;
+  }
   LPB_REQUIRE(per_c < (1LL << 31) && (int64_t)g.N * g.OH * g.OW < (1LL << 31), "col2im: batch too large for 32-bit indexing");
   LPB_REQUIRE(g.C <= 65535, "col2im: too many channels");
   dim3 grid((unsigned)imin(ceil_div(per_c, 256), 8192), (unsigned)g.C);

@@ -57,9 +57,9 @@ def test_conv_forward_backward_vs_fp64(geom):
     x = torch.randn(33, cin, hw, hw, device=DEV)
     ref = F.conv2d(x.double(), mod.weight.double(), mod.bias.double(), s, p, d)
     out = conv_engine.conv_forward(x, mod)
-    assert out.shape == ref.shape and rel_fro(out, ref) < 2e-6      # forward: fp16 hi/lo operands (22 bits)
+    assert out.shape == ref.shape and rel_fro(out, ref) < 5e-6      # forward: fp16 hi/lo operands (22 bits)
     out_cl = conv_engine.conv_forward(x.contiguous(memory_format=torch.channels_last), mod)
-    assert rel_fro(out_cl, ref) < 2e-6
+    assert rel_fro(out_cl, ref) < 5e-6
     g = torch.randn(65, *ref.shape[1:], device=DEV)
     gref = torch.nn.grad.conv2d_input((65, cin, hw, hw), mod.weight.double(), g.double(), s, p, d)
     gin = conv_engine.conv_backward_data(g, mod, (65, cin, hw, hw))
