@@ -272,10 +272,61 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ D
   }
 }
 
+// vectorised variant for 16-bit hi/lo outputs: one thread = 8 consecutive patch entries of one row (16 B stores)
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_conv2d_rows_vec8_kernel(const float* __restrict__ x, ConvGeom g, void* hi,
+                                                                     void* lo, int64_t ld) {
+  const int d_in = g.C * g.KH * g.KW;
+  const int chunks = (d_in + 7) / 8;
+  const int64_t total = (int64_t)g.N * g.OH * g.OW * chunks;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / chunks;
+    const int j0 = (int)(e - r * chunks) * 8;
+    const int ow = r % g.OW;
+    const int oh = (r / g.OW) % g.OH;
+    const int64_t n = r / ((int64_t)g.OW * g.OH);
+    const float* xn = x + n * g.C * g.H * g.W;
+    alignas(16) unsigned short h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = j0 + i;
+      float v = 0.f;
+      if (j < d_in) {
+        const int kw = j % g.KW, kh = (j / g.KW) % g.KH, ci = j / (g.KW * g.KH);
+        const int ih = oh * g.SH - g.PH + kh * g.DH, iw = ow * g.SW - g.PW + kw * g.DW;
+        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = __ldg(xn + ((int64_t)ci * g.H + ih) * g.W + iw);
+      }
+      if constexpr (KIND == OUT_F16_HILO) {
+        const __half hh = __float2half_rn(v);
+        h[i] = __half_as_ushort(hh);
+        l[i] = __half_as_ushort(__float2half_rn(v - __half2float(hh)));
+      } else {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+        h[i] = __bfloat16_as_ushort(hh);
+        l[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hh)));
+      }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(hi) + r * ld + j0) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(lo) + r * ld + j0) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
 int pack_conv2d_rows(const float* x, const ConvGeom& g, void* hi, void* lo, int kind, int64_t ld, cudaStream_t st) {
   const int64_t rows = (int64_t)g.N * g.OH * g.OW;
   if (rows == 0) return 0;
   LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_conv2d_rows: hi+lo output needs a lo buffer");
+  const int d_in = g.C * g.KH * g.KW;
+  if ((kind == OUT_BF16_HILO || kind == OUT_F16_HILO) && ld % 8 == 0 && ld >= (int64_t)((d_in + 7) / 8) * 8 &&
+      ((uintptr_t)hi % 16) == 0 && ((uintptr_t)lo % 16) == 0) {
+    const int64_t total = rows * ((d_in + 7) / 8);
+    const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 64);
+    if (kind == OUT_F16_HILO)
+      pack_conv2d_rows_vec8_kernel<OUT_F16_HILO><<<blocks, 256, 0, st>>>(x, g, hi, lo, ld);
+    else
+      pack_conv2d_rows_vec8_kernel<OUT_BF16_HILO><<<blocks, 256, 0, st>>>(x, g, hi, lo, ld);
+    LPB_CHECK_LAUNCH("pack_conv2d_rows_vec8");
+    return 0;
+  }
   const int blocks = (int)imin(ceil_div(rows, 8), (int64_t)sm_count() * 32);
   DISPATCH_KIND(kind, (pack_conv2d_rows_kernel<KIND><<<blocks, 256, 0, st>>>(x, g, hi, lo, ld)));
   LPB_CHECK_LAUNCH("pack_conv2d_rows");
@@ -304,10 +355,49 @@ int pack_nchw_rows(const float* gp, int64_t Q, int Cc, int HW, void* hi, void* l
   return 0;
 }
 
+// vectorised cast for 16-bit hi/lo outputs: 8 columns per thread (2 x 16 B loads, 2 x 16 B stores)
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_cast_vec8_kernel(const float* __restrict__ src, int64_t rows, int64_t cols8,
+                                                              int64_t ld_src, void* hi, void* lo, int64_t ld) {
+  const int64_t total = rows * cols8;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / cols8, c = (e - r * cols8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+    const float4 b = *reinterpret_cast<const float4*>(src + r * ld_src + c + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    alignas(16) unsigned short h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if constexpr (KIND == OUT_F16_HILO) {
+        const __half hh = __float2half_rn(v[i]);
+        h[i] = __half_as_ushort(hh);
+        l[i] = __half_as_ushort(__float2half_rn(v[i] - __half2float(hh)));
+      } else {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(v[i]);
+        h[i] = __bfloat16_as_ushort(hh);
+        l[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v[i] - __bfloat162float(hh)));
+      }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(hi) + r * ld + c) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(lo) + r * ld + c) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
 int pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* hi, void* lo, int kind, int64_t ld,
               cudaStream_t st) {
   if (rows == 0 || cols == 0) return 0;
   LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_cast: hi+lo output needs a lo buffer");
+  if ((kind == OUT_BF16_HILO || kind == OUT_F16_HILO) && cols % 8 == 0 && ld_src % 4 == 0 && ld % 8 == 0 &&
+      ((uintptr_t)src % 16) == 0 && ((uintptr_t)hi % 16) == 0 && ((uintptr_t)lo % 16) == 0) {
+    const int64_t total = rows * (cols / 8);
+    const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
+    if (kind == OUT_F16_HILO)
+      pack_cast_vec8_kernel<OUT_F16_HILO><<<blocks, 256, 0, st>>>(src, rows, cols / 8, ld_src, hi, lo, ld);
+    else
+      pack_cast_vec8_kernel<OUT_BF16_HILO><<<blocks, 256, 0, st>>>(src, rows, cols / 8, ld_src, hi, lo, ld);
+    LPB_CHECK_LAUNCH("pack_cast_vec8");
+    return 0;
+  }
   const int blocks = (int)imin(ceil_div(rows * cols, 256), (int64_t)sm_count() * 32);
   DISPATCH_KIND(kind, (pack_cast_kernel<KIND><<<blocks, 256, 0, st>>>(src, rows, cols, ld_src, hi, lo, ld)));
   LPB_CHECK_LAUNCH("pack_cast");

@@ -51,6 +51,50 @@ def allreduce_curvature(H, loss=None, group=None):
     return H, loss
 
 
+def decompose_sharded(kron, damping: bool = False, group=None):
+    """``Kron.decompose`` with the factors partitioned over the ranks (greedy balance on ``n^3``): every rank
+    eigendecomposes only its share, one all-reduce of a zero-padded flat ``Q`` buffer (+ eigenvalues) replicates the
+    result (SURVEY 8(e) "exchange v2").  Falls back to the local decomposition for a single process."""
+    from .matrix import B200KronDecomposed
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return kron.decompose(damping=damping)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mats = [(i, j, H) for i, F in enumerate(kron.kfacs) for j, H in enumerate(F)]
+    order = sorted(range(len(mats)), key=lambda k: -mats[k][2].shape[0])
+    load, owner = [0.0] * world, [0] * len(mats)
+    for k in order:
+        r = min(range(world), key=lambda q: load[q])
+        owner[k] = r
+        load[r] += float(mats[k][2].shape[0]) ** 3
+    # local decomposition of the owned factors, through the same code path as the single-process one
+    mine = [k for k in range(len(mats)) if owner[k] == rank]
+    sub = B200Kron([[mats[k][2]] for k in mine]) if mine else None
+    local = sub.decompose(damping=damping) if sub is not None else None
+    dev, dt = mats[0][2].device, mats[0][2].dtype
+    sizes = [m[2].shape[0] for m in mats]
+    Qflat = torch.zeros(sum(n * n for n in sizes), device=dev, dtype=dt)
+    Lflat = torch.zeros(sum(sizes), device=dev, dtype=dt)
+    qoff, loff, offs = 0, 0, []
+    for n in sizes:
+        offs.append((qoff, loff))
+        qoff += n * n
+        loff += n
+    for pos, k in enumerate(mine):
+        n = sizes[k]
+        Qflat[offs[k][0]:offs[k][0] + n * n].copy_(local.eigenvectors[pos][0].reshape(-1))
+        Lflat[offs[k][1]:offs[k][1] + n].copy_(local.eigenvalues[pos][0])
+    dist.all_reduce(Qflat, group=group)
+    dist.all_reduce(Lflat, group=group)
+    eigvecs = [[None] * len(F) for F in kron.kfacs]
+    eigvals = [[None] * len(F) for F in kron.kfacs]
+    for k, (i, j, H) in enumerate(mats):
+        n = sizes[k]
+        eigvecs[i][j] = Qflat[offs[k][0]:offs[k][0] + n * n].view(n, n)
+        eigvals[i][j] = Lflat[offs[k][1]:offs[k][1] + n]
+    return B200KronDecomposed(eigvecs, eigvals, damping=damping)
+
+
 def fit_distributed(la, train_loader, group=None):
     """``B200Laplace.fit`` sharded over the ranks of ``group``: local accumulation, one all-reduce, then the
     (replicated) decomposition.  Returns ``la``."""
@@ -64,7 +108,7 @@ def fit_distributed(la, train_loader, group=None):
         la.loss = loss
     if la.structure == "kron":
         la.H_facs = H
-        la.decompose()
+        la.H = decompose_sharded(H, damping=la.damping, group=group)
     else:
         la.H = H
     return la

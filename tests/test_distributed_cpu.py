@@ -39,6 +39,8 @@ def _worker(rank, world, port, out_path):
         la = fit_distributed(B200Laplace(model, "classification", "all", hs), loader)
         H = la.H_facs.to_matrix() if hs == "kron" else la.H
         res[hs] = (H.clone(), torch.as_tensor(la.loss).clone())
+        if hs == "kron":  # factor-sharded eigendecomposition reproduces the factors
+            res["kron_rec"] = la.H.to_matrix().clone()
     if rank == 0:
         torch.save(res, out_path)
     dist.destroy_process_group()
@@ -59,3 +61,5 @@ def test_sharded_fit_equals_single_process(tmp_path, cpu_kernels):
         H = la.H_facs.to_matrix() if hs == "kron" else la.H
         assert torch.allclose(res[hs][0], H, rtol=1e-5, atol=1e-7), hs
         assert torch.allclose(res[hs][1], torch.as_tensor(la.loss), rtol=1e-5)
+        if hs == "kron":
+            assert torch.allclose(res["kron_rec"], H, rtol=1e-4, atol=1e-6)
