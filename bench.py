@@ -363,6 +363,9 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
         "pack_conv_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
         "pack_nchw_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
         "pack_cast": lambda r, a, kw: ("bytes", bytes_packed(r), False),
+        "scale_channels": lambda r, a, kw: ("bytes", 8.0 * r.numel(), False),
+        "relu_bwd": lambda r, a, kw: ("bytes", 8.0 * r.numel() + 4.0 * a[1].numel(), False),
+        "maxpool2d_bwd": lambda r, a, kw: ("bytes", 4.0 * (r.numel() + a[0].numel()) + 8.0 * a[1].numel(), False),
         "col2im": lambda r, a, kw: ("bytes", 4.0 * (a[0].shape[0] * a[0].shape[1] + r.numel()), False),
     }
     origs = {n: wrap(n, w) for n, w in works.items()}

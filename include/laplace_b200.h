@@ -110,6 +110,15 @@ int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W
                      const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
                      float* D, int64_t ldd, int fp16_operands, void* stream);
 
+/* ---- reverse-pass element-wise maps of the convolution engine (columns folded into the batch) -----------------
+ * out[i] = g[i] * scale[(i / inner) % C]                 frozen BatchNorm as per-channel affine map (backward)   */
+int lpb_scale_channels(const float* g, const float* scale, float* out, int64_t n, int C, int64_t inner, void* stream);
+/* out[r*n + i] = y[i] > 0 ? g[r*n + i] : 0               ReLU backward, forward output y shared by `reps` columns */
+int lpb_relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, void* stream);
+/* max-pool backward (gather form): g [Q,C,OH,OW], idx [Nb,C,OH,OW] argmax (h*W+w) of image q % Nb -> out [Q,C,H,W] */
+int lpb_maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH, int OW,
+                      int k, int s, int p, void* stream);
+
 /* ---- weight-sharing layers: per-sample layer Jacobians ------------------------------------
  * P_q[i,j] = sum_t G[i, q*T+t] * A[j, (q % Nn)*T + t], q = c*Nn + n over ncols back-propagated columns.
  * mode 0: out[i*out_ld + j] += scale * sum_q P_q[i,j]^2      (diag GGN / EF, curvature.py:429-431, :504)

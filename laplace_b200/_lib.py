@@ -27,6 +27,9 @@ SIGNATURES = {
     "lpb_gemm_nt_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_vp],
     "lpb_gemm_nt_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
                        c_vp],
+    "lpb_scale_channels": [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_vp],
+    "lpb_relu_bwd": [c_vp, c_vp, c_vp, c_i64, c_int, c_vp],
+    "lpb_maxpool2d_bwd": [c_vp, c_vp, c_vp, c_i64] + [c_int] * 9 + [c_vp],
     "lpb_gemm_tn_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
                        c_vp],
     "lpb_conv_nhwc_tc": [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int,

@@ -185,6 +185,141 @@ def supported(mod: nn.Module) -> bool:
             and mod.padding_mode == "zeros")
 
 
+def _fold(g, in_dim):
+    """vmap helper: move the column dimension first and fold it into the batch.  Returns (folded, nb, B)."""
+    g = g.movedim(in_dim, 0)
+    nb, B = g.shape[0], g.shape[1]
+    return g.reshape(nb * B, *g.shape[2:]), nb, B
+
+
+class _AffineBwd(torch.autograd.Function):
+    """``g * scale[c]`` -- reverse pass of a frozen BatchNorm2d."""
+
+    @staticmethod
+    def forward(g, scale):
+        return K.scale_channels(g if g.dtype == torch.float32 else g.float(), scale)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, *grads):  # pragma: no cover
+        raise NotImplementedError
+
+    @staticmethod
+    def vmap(info, in_dims, g, scale):
+        g2, nb, B = _fold(g, in_dims[0])
+        out = _AffineBwd.apply(g2, scale)
+        return out.view(nb, B, *out.shape[1:]), 0
+
+
+class _Affine(torch.autograd.Function):
+    @staticmethod
+    def forward(x, scale, shift):
+        return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.save_for_backward(inputs[1])
+
+    @staticmethod
+    def backward(ctx, g):
+        return _AffineBwd.apply(g, ctx.saved_tensors[0]), None, None
+
+
+class _ReluBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(g, y, reps):
+        g = g if g.dtype == torch.float32 else g.float()
+        B = y.shape[0]
+        dense = y.is_contiguous() or (y.dim() == 4 and y.is_contiguous(memory_format=torch.channels_last))
+        if dense and g.shape[0] == reps * B and tuple(g.stride()) == tuple(y.stride()):
+            return K.relu_bwd(g, y, reps)
+        return (g.reshape(reps, B, *y.shape[1:]) * (y > 0)).reshape(g.shape)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, *grads):  # pragma: no cover
+        raise NotImplementedError
+
+    @staticmethod
+    def vmap(info, in_dims, g, y, reps):
+        g2, nb, B = _fold(g, in_dims[0])
+        out = _ReluBwd.apply(g2, y, nb * reps)
+        return out.view(nb, B, *out.shape[1:]), 0
+
+
+class _Relu(torch.autograd.Function):
+    @staticmethod
+    def forward(x):
+        return torch.relu(x)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.save_for_backward(output)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _ReluBwd.apply(g, ctx.saved_tensors[0], 1)
+
+
+class _MaxPoolBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(g, idx, in_shape, k, s, p):
+        return K.maxpool2d_bwd(g if g.dtype == torch.float32 else g.float(), idx, in_shape, k, s, p)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, *grads):  # pragma: no cover
+        raise NotImplementedError
+
+    @staticmethod
+    def vmap(info, in_dims, g, idx, in_shape, k, s, p):
+        g2, nb, B = _fold(g, in_dims[0])
+        out = _MaxPoolBwd.apply(g2, idx, in_shape, k, s, p)
+        return out.view(nb, B, *out.shape[1:]), 0
+
+
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(x, k, s, p):
+        out, idx = torch.nn.functional.max_pool2d(x, k, s, p, return_indices=True)
+        return out, idx
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        x, k, s, p = inputs
+        ctx.save_for_backward(output[1])
+        ctx.mark_non_differentiable(output[1])
+        ctx.geom = (tuple(x.shape), k, s, p)
+
+    @staticmethod
+    def backward(ctx, g, _gidx):
+        in_shape, k, s, p = ctx.geom
+        return _MaxPoolBwd.apply(g, ctx.saved_tensors[0], in_shape, k, s, p), None, None, None
+
+
+def _pool_geom(m: nn.Module):
+    """(k, s, p) of a square, undilated, floor-mode ``nn.MaxPool2d`` -- else ``None`` (left to PyTorch)."""
+    if not isinstance(m, nn.MaxPool2d) or m.ceil_mode or m.return_indices:
+        return None
+    def one(v):
+        if isinstance(v, (tuple, list)):
+            return v[0] if len(set(v)) == 1 else None
+        return v
+    k, s, p, d = one(m.kernel_size), one(m.stride if m.stride is not None else m.kernel_size), one(m.padding), one(m.dilation)
+    if None in (k, s, p, d) or d != 1:
+        return None
+    return int(k), int(s), int(p)
+
+
 def _frozen_eval_bn(m: nn.Module) -> bool:
     """BatchNorm2d in eval mode with running statistics and no trainable affine: a fixed per-channel affine map."""
     return (isinstance(m, nn.BatchNorm2d) and not m.training and m.track_running_stats and m.running_mean is not None
@@ -197,7 +332,7 @@ def _bn_affine(m: nn.BatchNorm2d):
     shift = -m.running_mean * scale
     if m.bias is not None:
         shift = shift + m.bias.detach()
-    return scale.view(1, -1, 1, 1), shift.view(1, -1, 1, 1)
+    return scale.float().contiguous(), shift.float().contiguous()
 
 
 class patched_convs:
@@ -213,6 +348,8 @@ class patched_convs:
     def __init__(self, model: nn.Module):
         self.mods = [m for m in model.modules() if supported(m)]
         self.bns = [m for m in model.modules() if _frozen_eval_bn(m)]
+        self.relus = [m for m in model.modules() if type(m) is nn.ReLU]
+        self.pools = [(m, _pool_geom(m)) for m in model.modules() if _pool_geom(m) is not None]
 
     def __enter__(self):
         for m in self.mods:
@@ -221,17 +358,30 @@ class patched_convs:
                     return nn.Conv2d.forward(m, x)
                 return _Conv.apply(x, m.weight, m)
             m.forward = fwd
+        def usable(x):
+            return x.dtype == torch.float32 and (x.is_cuda or _ALLOW_CPU)
+
         for m in self.bns:
             def bn_fwd(x, m=m):
-                if x.dim() != 4:
+                if x.dim() != 4 or not usable(x):
                     return nn.BatchNorm2d.forward(m, x)
                 scale, shift = _bn_affine(m)
-                return x * scale.to(x.dtype) + shift.to(x.dtype)
+                return _Affine.apply(x, scale, shift)
             m.forward = bn_fwd
+        for m in self.relus:
+            def relu_fwd(x, m=m):
+                return _Relu.apply(x) if usable(x) else nn.ReLU.forward(m, x)
+            m.forward = relu_fwd
+        for m, geom in self.pools:
+            def pool_fwd(x, m=m, geom=geom):
+                if x.dim() != 4 or not usable(x):
+                    return nn.MaxPool2d.forward(m, x)
+                return _MaxPool.apply(x, *geom)[0]
+            m.forward = pool_fwd
         return self
 
     def __exit__(self, *exc):
-        for m in self.mods + self.bns:
+        for m in self.mods + self.bns + self.relus + [p[0] for p in self.pools]:
             m.__dict__.pop("forward", None)
         return False
 

@@ -41,6 +41,9 @@ int gemm_nt_f32(const float*, int64_t, const float*, int64_t, int64_t, int64_t, 
                 cudaStream_t);
 int gemm_nt_bf16(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
                  int, float*, int64_t, int, int, cudaStream_t);
+int scale_channels(const float*, const float*, float*, int64_t, int, int64_t, cudaStream_t);
+int relu_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
+int maxpool2d_bwd(const float*, const int64_t*, float*, int64_t, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int gemm_tn_rows(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
                  int, float*, int64_t, int, int, cudaStream_t);
 int conv_nhwc_bf16(const void*, const void*, int64_t, int, int, int64_t, int64_t, const void*, const void*, int64_t, int, int,
@@ -164,6 +167,19 @@ int lpb_gemm_nt_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* 
   LPB_REQUIRE((A_lo == nullptr) == (B_lo == nullptr), "lpb_gemm_nt_tc: A_lo and B_lo must both be given or both NULL");
   return lpb::gemm_nt_bf16(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, accumulate, D, ldd, symmetric, fp16_operands,
                            ST(stream));
+}
+
+int lpb_scale_channels(const float* g, const float* scale, float* out, int64_t n, int C, int64_t inner, void* stream) {
+  return lpb::scale_channels(g, scale, out, n, C, inner, ST(stream));
+}
+
+int lpb_relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, void* stream) {
+  return lpb::relu_bwd(g, y, out, n, reps, ST(stream));
+}
+
+int lpb_maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH, int OW,
+                      int k, int s, int p, void* stream) {
+  return lpb::maxpool2d_bwd(g, idx, out, Q, Nb, C, H, W, OH, OW, k, s, p, ST(stream));
 }
 
 int lpb_gemm_tn_tc(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,

@@ -1,0 +1,114 @@
+// Reverse-pass element-wise kernels of the convolution engine: with the C curvature columns folded into the batch,
+// PyTorch's vmapped backward formulas for ReLU / frozen BatchNorm / MaxPool run through generic broadcasting kernels
+// (19 % + 10 % of a KFAC step in profiles/r01_launches_final_b2048.md).  These are the same maps as HBM-bound,
+// vectorised kernels: every gradient element is read once and written once.
+#include "common.cuh"
+
+namespace lpb {
+
+// out[i] = g[i] * scale[(i / inner) % C]     (inner = H*W for NCHW, 1 for NHWC rows)
+__global__ void __launch_bounds__(256) scale_channels_kernel(const float* __restrict__ g, const float* __restrict__ scale,
+                                                              float* __restrict__ out, int64_t n4, int C, int64_t inner,
+                                                              int mode) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[e];
+    float4 o;
+    if (mode == 0) {  // 4 consecutive elements share one channel (inner % 4 == 0)
+      const float s = __ldg(scale + ((e * 4) / inner) % C);
+      o = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+    } else {          // inner == 1, C % 4 == 0: 4 consecutive channels
+      const float4 s = *reinterpret_cast<const float4*>(scale + (e * 4) % C);
+      o = make_float4(v.x * s.x, v.y * s.y, v.z * s.z, v.w * s.w);
+    }
+    reinterpret_cast<float4*>(out)[e] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_channels_scalar_kernel(const float* __restrict__ g,
+                                                                     const float* __restrict__ scale,
+                                                                     float* __restrict__ out, int64_t n, int C,
+                                                                     int64_t inner) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = g[e] * __ldg(scale + (e / inner) % C);
+}
+
+int scale_channels(const float* g, const float* scale, float* out, int64_t n, int C, int64_t inner, cudaStream_t st) {
+  if (n == 0) return 0;
+  LPB_REQUIRE(C > 0 && inner > 0, "scale_channels: bad extents");
+  const bool aligned = ((uintptr_t)g % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)scale % 16) == 0 && n % 4 == 0;
+  const int blocks_cap = sm_count() * 16;
+  if (aligned && inner % 4 == 0) {
+    scale_channels_kernel<<<(int)imin(ceil_div(n / 4, 256), blocks_cap), 256, 0, st>>>(g, scale, out, n / 4, C, inner, 0);
+  } else if (aligned && inner == 1 && C % 4 == 0) {
+    scale_channels_kernel<<<(int)imin(ceil_div(n / 4, 256), blocks_cap), 256, 0, st>>>(g, scale, out, n / 4, C, inner, 1);
+  } else {
+    scale_channels_scalar_kernel<<<(int)imin(ceil_div(n, 256), blocks_cap), 256, 0, st>>>(g, scale, out, n, C, inner);
+  }
+  LPB_CHECK_LAUNCH("scale_channels");
+  return 0;
+}
+
+// out[r*n + i] = y[i] > 0 ? g[r*n + i] : 0     (y: forward ReLU output of the B images, shared by all reps)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                        float* __restrict__ out, int64_t n4, int64_t total4) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[e];
+    const float4 m = reinterpret_cast<const float4*>(y)[e % n4];
+    reinterpret_cast<float4*>(out)[e] =
+        make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) relu_bwd_scalar_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                               float* __restrict__ out, int64_t n, int64_t total) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = y[e % n] > 0.f ? g[e] : 0.f;
+}
+
+int relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, cudaStream_t st) {
+  if (n == 0 || reps == 0) return 0;
+  const int64_t total = n * reps;
+  const int blocks_cap = sm_count() * 16;
+  if (n % 4 == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)out % 16) == 0)
+    relu_bwd_kernel<<<(int)imin(ceil_div(total / 4, 256), blocks_cap), 256, 0, st>>>(g, y, out, n / 4, total / 4);
+  else
+    relu_bwd_scalar_kernel<<<(int)imin(ceil_div(total, 256), blocks_cap), 256, 0, st>>>(g, y, out, n, total);
+  LPB_CHECK_LAUNCH("relu_bwd");
+  return 0;
+}
+
+// max-pool backward, gather form (no atomics): one thread per input pixel sums the windows whose argmax it is.
+// g [Q, C, OH, OW], idx [Nb, C, OH, OW] (flattened h*W + w of the argmax, forward of the Nb images; q -> q % Nb),
+// out [Q, C, H, W]; all NCHW-contiguous.
+__global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx,
+                                                             float* __restrict__ out, int64_t total, int Nb, int C, int H,
+                                                             int W, int OH, int OW, int k, int s, int p) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int w = e % W;
+    const int h = (e / W) % H;
+    const int c = (e / ((int64_t)W * H)) % C;
+    const int64_t q = e / ((int64_t)W * H * C);
+    const int64_t nb = q % Nb;
+    const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
+    const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
+    const int64_t me = (int64_t)h * W + w;
+    float acc = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow)
+        if (idx[((nb * C + c) * OH + oh) * OW + ow] == me) acc += g[((q * C + c) * OH + oh) * OW + ow];
+    out[e] = acc;
+  }
+}
+
+int maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH, int OW,
+                  int k, int s, int p, cudaStream_t st) {
+  const int64_t total = Q * C * H * W;
+  if (total == 0) return 0;
+  LPB_REQUIRE(Nb > 0 && k > 0 && s > 0 && p >= 0, "maxpool2d_bwd: bad geometry");
+  maxpool2d_bwd_kernel<<<(int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32), 256, 0, st>>>(g, idx, out, total, Nb, C, H,
+                                                                                                 W, OH, OW, k, s, p);
+  LPB_CHECK_LAUNCH("maxpool2d_bwd");
+  return 0;
+}
+
+}  // namespace lpb

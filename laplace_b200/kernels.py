@@ -326,3 +326,42 @@ def gemm_tn(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumul
               1 if accumulate else 0, _ptr(out), out.stride(0), 1 if symmetric else 0, 1 if A.kind == F16X3 else 0, _stream())
     _bump()
     return out
+
+
+# ------------------------------------------------------------------------------ reverse-pass element-wise maps
+def scale_channels(g: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """``g [Q, C, H, W]`` (NCHW- or channels_last-dense) times a per-channel ``scale [C]``; same layout out."""
+    _check(g, name="g"), _check(scale, name="scale")
+    Q, C, H, W = g.shape
+    if g.is_contiguous():
+        inner = H * W
+    elif g.is_contiguous(memory_format=torch.channels_last):
+        inner = 1
+    else:
+        g, inner = g.contiguous(), H * W
+    out = torch.empty_like(g)
+    _lib.call("lpb_scale_channels", _ptr(g), _ptr(scale.contiguous()), _ptr(out), g.numel(), C, inner, _stream())
+    _bump()
+    return out
+
+
+def relu_bwd(g: torch.Tensor, y: torch.Tensor, reps: int) -> torch.Tensor:
+    """``g [reps*B, ...]`` masked by the forward output ``y [B, ...]`` (same dense layout per image block)."""
+    _check(g, name="g"), _check(y, name="y")
+    out = torch.empty_like(g)
+    _lib.call("lpb_relu_bwd", _ptr(g), _ptr(y), _ptr(out), y.numel(), reps, _stream())
+    _bump()
+    return out
+
+
+def maxpool2d_bwd(g: torch.Tensor, idx: torch.Tensor, in_shape, k: int, s: int, p: int) -> torch.Tensor:
+    """``g [Q, C, OH, OW]``, ``idx [Nb, C, OH, OW]`` int64 argmax -> ``[Q, C, H, W]`` (all NCHW-contiguous)."""
+    _check(g, name="g")
+    g = g.contiguous()
+    idx = idx.contiguous()
+    Q, C, OH, OW = g.shape
+    H, W = in_shape[-2:]
+    out = torch.empty(Q, C, H, W, device=g.device, dtype=torch.float32)
+    _lib.call("lpb_maxpool2d_bwd", _ptr(g), _ptr(idx), _ptr(out), Q, idx.shape[0], C, H, W, OH, OW, k, s, p, _stream())
+    _bump()
+    return out

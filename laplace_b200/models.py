@@ -27,15 +27,16 @@ class BasicBlock(nn.Module):
         self.bn1 = _frozen_bn(cout)
         self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
         self.bn2 = _frozen_bn(cout)
+        self.relu = nn.ReLU()
         self.downsample = None
         if stride != 1 or cin != cout:
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), _frozen_bn(cout))
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
-        out = torch.relu(self.bn1(self.conv1(x)))
+        out = self.relu(self.bn1(self.conv1(x)))
         out = self.bn2(self.conv2(out))
-        return torch.relu(out + idt)
+        return self.relu(out + idt)
 
 
 class ResNet18(nn.Module):
@@ -51,6 +52,7 @@ class ResNet18(nn.Module):
             self.conv1 = nn.Conv2d(3, width, 7, 2, 3, bias=False)
             self.maxpool = nn.MaxPool2d(3, 2, 1)
         self.bn1 = _frozen_bn(width)
+        self.relu = nn.ReLU()
         chans = [width, 2 * width, 4 * width, 8 * width]
         blocks, cin = [], width
         for i, c in enumerate(chans):
@@ -61,7 +63,7 @@ class ResNet18(nn.Module):
         self.fc = nn.Linear(cin, n_out)
 
     def forward(self, x):
-        x = self.maxpool(torch.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
         x = self.layers(x)
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
@@ -74,11 +76,12 @@ class _WideBlock(nn.Module):
         self.bn2 = _frozen_bn(cout)
         self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
         self.short = None if (cin == cout and stride == 1) else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
+        self.relu = nn.ReLU()
 
     def forward(self, x):
-        o = torch.relu(self.bn1(x))
+        o = self.relu(self.bn1(x))
         y = self.conv1(o)
-        y = self.conv2(torch.relu(self.bn2(y)))
+        y = self.conv2(self.relu(self.bn2(y)))
         return y + (x if self.short is None else self.short(o))
 
 
@@ -98,11 +101,12 @@ class WideResNet(nn.Module):
                 cin = w[i + 1]
         self.blocks = nn.Sequential(*blocks)
         self.bn = _frozen_bn(cin)
+        self.relu = nn.ReLU()
         self.fc = nn.Linear(cin, n_out)
 
     def forward(self, x):
         x = self.blocks(self.conv1(x))
-        x = torch.relu(self.bn(x)).mean((2, 3))
+        x = self.relu(self.bn(x)).mean((2, 3))
         return self.fc(x)
 
 

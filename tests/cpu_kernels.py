@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc", "gemm_tn"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -231,3 +231,22 @@ def gemm_tn(A, B, out, alpha=1.0, accumulate=True, symmetric=False):
     else:
         out.copy_(res)
     return out
+
+
+def scale_channels(g, scale):
+    return g * scale.view(1, -1, 1, 1)
+
+
+def relu_bwd(g, y, reps):
+    B = y.shape[0]
+    return (g.reshape(reps, B, *y.shape[1:]) * (y > 0)).reshape(g.shape)
+
+
+def maxpool2d_bwd(g, idx, in_shape, k, s, p):
+    Q, C, OH, OW = g.shape
+    H, W = in_shape[-2:]
+    Nb = idx.shape[0]
+    out = torch.zeros(Q, C, H * W)
+    ii = idx.reshape(Nb, C, OH * OW).repeat(Q // Nb, 1, 1)
+    out.scatter_add_(2, ii, g.reshape(Q, C, OH * OW).float())
+    return out.reshape(Q, C, H, W)

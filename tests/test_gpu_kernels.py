@@ -222,3 +222,33 @@ def test_gemm_tn_rows_operands(Kr, M, N, kind, tol):
         sym = torch.zeros(M, M, device=DEV)
         K.gemm_tn(pa, pa, sym, alpha=1.0, accumulate=True, symmetric=True)
         assert rel_fro(sym.cpu(), A.double().t() @ A.double()) < tol
+
+
+@pytest.mark.parametrize("shape", [(6, 8, 4, 4), (5, 7, 3, 5), (33, 64, 8, 8), (3, 5, 1, 1)])
+def test_elementwise_reverse_pass_kernels(shape):
+    torch.manual_seed(10)
+    Q, C, H, W = shape
+    g = torch.randn(Q, C, H, W, device=DEV)
+    s = torch.rand(C, device=DEV) + 0.5
+    ref = g * s.view(1, -1, 1, 1)
+    assert torch.allclose(K.scale_channels(g, s), ref, rtol=1e-6)
+    gcl = g.contiguous(memory_format=torch.channels_last)
+    out = K.scale_channels(gcl, s)
+    assert out.stride() == gcl.stride() and torch.allclose(out, ref, rtol=1e-6)
+    B = 3 if Q % 3 == 0 else 1
+    y = torch.randn(B, C, H, W, device=DEV).relu()
+    reps = Q // B
+    ref = (g.view(reps, B, C, H, W) * (y > 0)).view(Q, C, H, W)
+    assert torch.equal(K.relu_bwd(g, y, reps), ref)
+
+
+@pytest.mark.parametrize("geom", [(3, 2, 1, 16), (2, 2, 0, 8), (3, 1, 1, 7), (3, 2, 1, 9)])
+def test_maxpool_backward_kernel(geom):
+    k, s, p, hw = geom
+    torch.manual_seed(11)
+    x = torch.randn(4, 6, hw, hw, device=DEV, requires_grad=True)
+    out, idx = torch.nn.functional.max_pool2d(x, k, s, p, return_indices=True)
+    g = torch.randn(3 * 4, 6, *out.shape[2:], device=DEV)          # 3 folded columns
+    ref = torch.stack([torch.autograd.grad(out, x, g[i * 4:(i + 1) * 4], retain_graph=True)[0] for i in range(3)]).reshape(12, 6, hw, hw)
+    got = K.maxpool2d_bwd(g, idx, x.shape, k, s, p)
+    assert torch.allclose(got, ref, atol=1e-6)
