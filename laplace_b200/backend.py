@@ -322,7 +322,7 @@ class _B200Mixin:
         for L, g in zip(self._layers, grads):
             a = acts[L.name]
             ncols = g.shape[0]
-            rows = stash.get(id(L.mod), {}) if L.is_conv else {}
+            rows = stash.get(id(L.mod), {})
             Grows = rows.get("G")
             if Grows is not None and Grows.rows != g.numel() // L.d_out:
                 Grows = None
@@ -344,6 +344,8 @@ class _B200Mixin:
                     # transposing K-major one) and contract them with the MN-major SYRK
                     af = a.float() if a.dtype != torch.float32 else a
                     Prows = K.pack_conv_rows(af, L.mod, K.BF16X3)
+                if Prows is not None and Prows.rows % M != 0:
+                    Prows = None
                 if Prows is not None:
                     T = Prows.rows // M
                     K.gemm_tn(Prows, Prows, Af, alpha=sq / (N * T), accumulate=True, symmetric=True)

@@ -180,6 +180,68 @@ class _Conv(torch.autograd.Function):
         return (gx if ctx.needs_input_grad[0] else None), None, None
 
 
+# ------------------------------------------------------------------------------------------ nn.Linear
+def linear_forward(x2: torch.Tensor, mod: nn.Linear) -> torch.Tensor:
+    """``x2 [rows, d_in] @ W^T`` on the tensor cores (fp16 hi/lo operands); stashes the input rows for the A factor."""
+    X = K.pack_cast(x2, KIND_FWD)
+    STASH.setdefault(id(mod), {})["P"] = X
+    Wk = _CACHE.get(mod, "fwd")                                  # [d_out, d_in], pre-scaled
+    out = torch.empty(x2.shape[0], mod.out_features, device=x2.device, dtype=torch.float32)
+    K.gemm_nt(X, Wk, out, getattr(Wk, "inv_scale", 1.0), accumulate=False)
+    return out
+
+
+def linear_backward_data(g2: torch.Tensor, mod: nn.Linear, need_dx: bool):
+    G = K.pack_cast(g2, KIND)                                    # [rows, d_out] bf16 hi/lo
+    STASH.setdefault(id(mod), {})["G"] = G
+    if not need_dx:
+        return None
+    Wt = _CACHE.get(mod, "bwd")                                  # [d_in, d_out]
+    out = torch.empty(g2.shape[0], mod.in_features, device=g2.device, dtype=torch.float32)
+    K.gemm_nt(G, Wt, out, 1.0, accumulate=False)
+    return out
+
+
+class _LinearBwdData(torch.autograd.Function):
+    @staticmethod
+    def forward(g, mod, need_dx):
+        g = g if g.dtype == torch.float32 else g.float()
+        out = linear_backward_data(g.reshape(-1, g.shape[-1]).contiguous(), mod, need_dx)
+        return out.view(*g.shape[:-1], mod.in_features) if out is not None else g.new_empty(0)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, *grads):  # pragma: no cover
+        raise NotImplementedError
+
+    @staticmethod
+    def vmap(info, in_dims, g, mod, need_dx):
+        g2, nb, B = _fold(g, in_dims[0])
+        out = _LinearBwdData.apply(g2, mod, need_dx)
+        if out.numel() == 0:
+            return out, None
+        return out.view(nb, B, *out.shape[1:]), 0
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(x, weight, mod):
+        out = linear_forward(x.reshape(-1, x.shape[-1]).contiguous(), mod).view(*x.shape[:-1], mod.out_features)
+        return out if mod.bias is None else out + mod.bias.detach()
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.mod = inputs[2]
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = _LinearBwdData.apply(g, ctx.mod, bool(ctx.needs_input_grad[0]))
+        return (gx if ctx.needs_input_grad[0] else None), None, None
+
+
 def supported(mod: nn.Module) -> bool:
     return (isinstance(mod, nn.Conv2d) and mod.groups == 1 and not isinstance(mod.padding, str)
             and mod.padding_mode == "zeros")
@@ -326,7 +388,21 @@ def _frozen_eval_bn(m: nn.Module) -> bool:
             and not any(p.requires_grad for p in m.parameters(recurse=False)))
 
 
+_BN_CACHE: dict = {}
+
+
 def _bn_affine(m: nn.BatchNorm2d):
+    tag = (m.running_var.data_ptr(), m.running_var._version, m.running_mean._version,
+           None if m.weight is None else m.weight._version, None if m.bias is None else m.bias._version, m.running_var.device)
+    hit = _BN_CACHE.get(id(m))
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    out = _bn_affine_compute(m)
+    _BN_CACHE[id(m)] = (tag, out)
+    return out
+
+
+def _bn_affine_compute(m: nn.BatchNorm2d):
     invstd = torch.rsqrt(m.running_var + m.eps)
     scale = invstd if m.weight is None else m.weight.detach() * invstd
     shift = -m.running_mean * scale
@@ -348,6 +424,7 @@ class patched_convs:
     def __init__(self, model: nn.Module):
         self.mods = [m for m in model.modules() if supported(m)]
         self.bns = [m for m in model.modules() if _frozen_eval_bn(m)]
+        self.linears = [m for m in model.modules() if type(m) is nn.Linear and m.in_features >= 16 and m.out_features >= 16]
         self.relus = [m for m in model.modules() if type(m) is nn.ReLU]
         self.pools = [(m, _pool_geom(m)) for m in model.modules() if _pool_geom(m) is not None]
 
@@ -368,6 +445,10 @@ class patched_convs:
                 scale, shift = _bn_affine(m)
                 return _Affine.apply(x, scale, shift)
             m.forward = bn_fwd
+        for m in self.linears:
+            def lin_fwd(x, m=m):
+                return _Linear.apply(x, m.weight, m) if usable(x) else nn.Linear.forward(m, x)
+            m.forward = lin_fwd
         for m in self.relus:
             def relu_fwd(x, m=m):
                 return _Relu.apply(x) if usable(x) else nn.ReLU.forward(m, x)
@@ -381,7 +462,7 @@ class patched_convs:
         return self
 
     def __exit__(self, *exc):
-        for m in self.mods + self.bns + self.relus + [p[0] for p in self.pools]:
+        for m in self.mods + self.bns + self.linears + self.relus + [p[0] for p in self.pools]:
             m.__dict__.pop("forward", None)
         return False
 

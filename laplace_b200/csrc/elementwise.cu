@@ -77,36 +77,55 @@ int relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, cu
   return 0;
 }
 
-// max-pool backward, gather form (no atomics): one thread per input pixel sums the windows whose argmax it is.
+// max-pool backward, gather form (no atomics): one CTA per (q, c) plane; the plane's OH*OW gradients and argmax
+// indices are staged in shared memory, every input pixel then sums the (at most ceil(k/s)^2) windows whose argmax it is.
 // g [Q, C, OH, OW], idx [Nb, C, OH, OW] (flattened h*W + w of the argmax, forward of the Nb images; q -> q % Nb),
 // out [Q, C, H, W]; all NCHW-contiguous.
 __global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx,
-                                                             float* __restrict__ out, int64_t total, int Nb, int C, int H,
-                                                             int W, int OH, int OW, int k, int s, int p) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int w = e % W;
-    const int h = (e / W) % H;
-    const int c = (e / ((int64_t)W * H)) % C;
-    const int64_t q = e / ((int64_t)W * H * C);
-    const int64_t nb = q % Nb;
-    const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
-    const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
-    const int64_t me = (int64_t)h * W + w;
-    float acc = 0.f;
-    for (int oh = oh_lo; oh <= oh_hi; ++oh)
-      for (int ow = ow_lo; ow <= ow_hi; ++ow)
-        if (idx[((nb * C + c) * OH + oh) * OW + ow] == me) acc += g[((q * C + c) * OH + oh) * OW + ow];
-    out[e] = acc;
+                                                             float* __restrict__ out, int64_t planes, int Nb, int C, int H, int W,
+                                                             int OH, int OW, int k, int s, int p) {
+  extern __shared__ unsigned char smem_raw[];
+  const int T = OH * OW, HW = H * W;
+  float* sg = reinterpret_cast<float*>(smem_raw);
+  int* si = reinterpret_cast<int*>(sg + T);
+  for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {   // plane = q * C + c
+    const int64_t q = plane / C;
+    const int c = (int)(plane - q * C);
+    const float* gp = g + plane * T;
+    const int64_t* ip = idx + ((q % Nb) * C + c) * (int64_t)T;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      sg[t] = gp[t];
+      si[t] = (int)ip[t];
+    }
+    __syncthreads();
+    float* op = out + plane * HW;
+    for (int e = threadIdx.x; e < HW; e += blockDim.x) {
+      const int h = e / W, w = e - h * W;
+      const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
+      const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
+      float acc = 0.f;
+      for (int oh = oh_lo; oh <= oh_hi; ++oh)
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+          const int t = oh * OW + ow;
+          if (si[t] == e) acc += sg[t];
+        }
+      op[e] = acc;
+    }
+    __syncthreads();
   }
 }
 
 int maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH, int OW,
                   int k, int s, int p, cudaStream_t st) {
-  const int64_t total = Q * C * H * W;
-  if (total == 0) return 0;
+  const int64_t planes = Q * C;
+  if (planes == 0) return 0;
   LPB_REQUIRE(Nb > 0 && k > 0 && s > 0 && p >= 0, "maxpool2d_bwd: bad geometry");
-  maxpool2d_bwd_kernel<<<(int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32), 256, 0, st>>>(g, idx, out, total, Nb, C, H,
-                                                                                                 W, OH, OW, k, s, p);
+  LPB_REQUIRE(planes < (1LL << 31), "maxpool2d_bwd: too many planes");
+  const size_t smem = (size_t)OH * OW * 8;
+  LPB_REQUIRE(smem <= 48 * 1024, "maxpool2d_bwd: output plane too large for the shared-memory kernel");
+  const int threads = H * W >= 256 ? 256 : (H * W >= 128 ? 128 : 64);
+  const unsigned blocks = (unsigned)imin(planes, (int64_t)sm_count() * 16);
+  maxpool2d_bwd_kernel<<<blocks, threads, smem, st>>>(g, idx, out, planes, Nb, C, H, W, OH, OW, k, s, p);
   LPB_CHECK_LAUNCH("maxpool2d_bwd");
   return 0;
 }

@@ -202,7 +202,7 @@ def test_config1_mlp_parity_anchor():
     la = B200Laplace(model, "classification", "all", "kron", prior_precision=1.0).fit(
         DataLoader(TensorDataset(X.to(DEV), y.to(DEV)), batch_size=128))
     worst = max(rel_fro(h.cpu(), ho) for F, Fo in zip(la.H_facs.kfacs, kfs) for h, ho in zip(F, Fo))
-    assert worst < FACTOR_TOL, worst
+    assert worst < FACTOR_TOL, f"factor error {worst:.2e}"
     Xt = X[:32]
     f_mu, f_var = la.glm_predictive_distribution(Xt.to(DEV))
     Js, f = co.jacobians(md, Xt.double())
@@ -211,9 +211,11 @@ def test_config1_mlp_parity_anchor():
     Qs = [[q.cpu().double() for q in Q] for Q in la.H.eigenvectors]
     ls = [[l.cpu().double() for l in L] for L in la.H.eigenvalues]
     ref_same = ko.kron_inv_square_form(Qs, ls, delta, Js)
-    assert float((f_var.cpu().double() - ref_same).abs().max() / ref_same.abs().max()) < VAR_TOL
+    err_same = float((f_var.cpu().double() - ref_same).abs().max() / ref_same.abs().max())
+    assert err_same < VAR_TOL, f"posterior-side kernels vs oracle algebra on the same decomposition: {err_same:.2e}"
     # (b) end to end against the fp64 oracle's own decomposition
     Qo, lo = ko.decompose(kfs)
     ref = ko.kron_inv_square_form(Qo, lo, delta, Js)
-    assert float((f_var.cpu().double() - ref).abs().max() / ref.abs().max()) < 1e-4
+    err_e2e = float((f_var.cpu().double() - ref).abs().max() / ref.abs().max())
+    assert err_e2e < 1e-4, f"end-to-end predictive variance error {err_e2e:.2e}"
     assert torch.allclose(f_mu.cpu().double(), f, atol=1e-5)

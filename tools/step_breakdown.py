@@ -16,7 +16,7 @@ a = ap.parse_args()
 dev = "cuda"
 model = models.make(a.model).to(dev)
 be = B200GGN(model, "classification", precision=a.precision, model_tf32=a.tf32, batched_backward=not a.loop_backward, conv_engine=not a.no_engine)
-X = torch.randn(a.batch, 3, 32, 32, device=dev); y = torch.randint(10, (a.batch,), device=dev)
+X = torch.randn(a.batch, 3, 224 if a.model == "vit_b16" else 32, 224 if a.model == "vit_b16" else 32, device=dev); y = torch.randint(10, (a.batch,), device=dev)
 rec = collections.defaultdict(list)
 
 def wrap(obj, name, label=None):
