@@ -388,6 +388,10 @@ def _frozen_eval_bn(m: nn.Module) -> bool:
             and not any(p.requires_grad for p in m.parameters(recurse=False)))
 
 
+# The custom element-wise Functions trade ~0.15 ms of host time per call (functorch dispatch of a Python
+# autograd.Function) for 2-4x less device time on the folded C x B gradients: worth it once a step is device-bound.
+ELEMENTWISE_MIN_BATCH = 1024
+
 _BN_CACHE: dict = {}
 
 
@@ -443,6 +447,8 @@ class patched_convs:
                 if x.dim() != 4 or not usable(x):
                     return nn.BatchNorm2d.forward(m, x)
                 scale, shift = _bn_affine(m)
+                if x.shape[0] < ELEMENTWISE_MIN_BATCH:
+                    return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
                 return _Affine.apply(x, scale, shift)
             m.forward = bn_fwd
         for m in self.linears:
@@ -451,11 +457,11 @@ class patched_convs:
             m.forward = lin_fwd
         for m in self.relus:
             def relu_fwd(x, m=m):
-                return _Relu.apply(x) if usable(x) else nn.ReLU.forward(m, x)
+                return _Relu.apply(x) if (usable(x) and x.shape[0] >= ELEMENTWISE_MIN_BATCH) else nn.ReLU.forward(m, x)
             m.forward = relu_fwd
         for m, geom in self.pools:
             def pool_fwd(x, m=m, geom=geom):
-                if x.dim() != 4 or not usable(x):
+                if x.dim() != 4 or not usable(x) or x.shape[0] < ELEMENTWISE_MIN_BATCH:
                     return nn.MaxPool2d.forward(m, x)
                 return _MaxPool.apply(x, *geom)[0]
             m.forward = pool_fwd

@@ -81,35 +81,39 @@ int relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, cu
 // indices are staged in shared memory, every input pixel then sums the (at most ceil(k/s)^2) windows whose argmax it is.
 // g [Q, C, OH, OW], idx [Nb, C, OH, OW] (flattened h*W + w of the argmax, forward of the Nb images; q -> q % Nb),
 // out [Q, C, H, W]; all NCHW-contiguous.
+constexpr int POOL_PLANES = 8;  // planes per iteration: amortises the two barriers and the global-load latency
+
 __global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx,
                                                              float* __restrict__ out, int64_t planes, int Nb, int C, int H, int W,
                                                              int OH, int OW, int k, int s, int p) {
   extern __shared__ unsigned char smem_raw[];
   const int T = OH * OW, HW = H * W;
-  float* sg = reinterpret_cast<float*>(smem_raw);
-  int* si = reinterpret_cast<int*>(sg + T);
-  for (int64_t plane = blockIdx.x; plane < planes; plane += gridDim.x) {   // plane = q * C + c
-    const int64_t q = plane / C;
-    const int c = (int)(plane - q * C);
-    const float* gp = g + plane * T;
-    const int64_t* ip = idx + ((q % Nb) * C + c) * (int64_t)T;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-      sg[t] = gp[t];
-      si[t] = (int)ip[t];
+  float* sg = reinterpret_cast<float*>(smem_raw);          // [POOL_PLANES][T]
+  int* si = reinterpret_cast<int*>(sg + POOL_PLANES * T);  // [POOL_PLANES][T]
+  const int64_t groups = (planes + POOL_PLANES - 1) / POOL_PLANES;
+  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int64_t p0 = grp * POOL_PLANES;
+    const int np = (int)imin(POOL_PLANES, planes - p0);
+    for (int t = threadIdx.x; t < np * T; t += blockDim.x) {
+      const int j = t / T, tt = t - j * T;
+      const int64_t plane = p0 + j, q = plane / C;
+      const int c = (int)(plane - q * C);
+      sg[t] = g[plane * T + tt];
+      si[t] = (int)idx[((q % Nb) * C + c) * (int64_t)T + tt];
     }
     __syncthreads();
-    float* op = out + plane * HW;
-    for (int e = threadIdx.x; e < HW; e += blockDim.x) {
+    for (int e2 = threadIdx.x; e2 < np * HW; e2 += blockDim.x) {
+      const int j = e2 / HW, e = e2 - j * HW;
       const int h = e / W, w = e - h * W;
       const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
       const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
       float acc = 0.f;
       for (int oh = oh_lo; oh <= oh_hi; ++oh)
         for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-          const int t = oh * OW + ow;
+          const int t = j * T + oh * OW + ow;
           if (si[t] == e) acc += sg[t];
         }
-      op[e] = acc;
+      out[(p0 + j) * HW + e] = acc;
     }
     __syncthreads();
   }
@@ -121,10 +125,10 @@ int maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int
   if (planes == 0) return 0;
   LPB_REQUIRE(Nb > 0 && k > 0 && s > 0 && p >= 0, "maxpool2d_bwd: bad geometry");
   LPB_REQUIRE(planes < (1LL << 31), "maxpool2d_bwd: too many planes");
-  const size_t smem = (size_t)OH * OW * 8;
+  const size_t smem = (size_t)OH * OW * 8 * POOL_PLANES;
   LPB_REQUIRE(smem <= 48 * 1024, "maxpool2d_bwd: output plane too large for the shared-memory kernel");
-  const int threads = H * W >= 256 ? 256 : (H * W >= 128 ? 128 : 64);
-  const unsigned blocks = (unsigned)imin(planes, (int64_t)sm_count() * 16);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)imin(ceil_div(planes, POOL_PLANES), (int64_t)sm_count() * 8);
   maxpool2d_bwd_kernel<<<blocks, threads, smem, st>>>(g, idx, out, planes, Nb, C, H, W, OH, OW, k, s, p);
   LPB_CHECK_LAUNCH("maxpool2d_bwd");
   return 0;

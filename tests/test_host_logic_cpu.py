@@ -124,3 +124,27 @@ def test_structured_predictive_matches_dense(golden, cpu_kernels):
         ls = [[l.double() for l in L] for L in P.eigenvalues]
         ref = ko.kron_inv_square_form(Qs, ls, torch.tensor(0.7, dtype=torch.float64), Js.double().clone())
         assert torch.allclose(fv.double(), ref, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,kw", [("resnet18", {"width": 8}), ("wrn28_10", {"depth": 10, "widen": 1}),
+                                     ("vit_b16", {"image": 32, "patch": 8, "dim": 32, "depth": 2, "heads": 4, "mlp_dim": 64})])
+def test_convolution_engine_paths_on_model_zoo(cpu_kernels, monkeypatch, name, kw):
+    """Full engine (implicit/explicit convolutions, Linear layers, frozen-BN affine, ReLU and MaxPool custom reverse
+    passes, functorch-batched columns, factor SYRKs from the stashed rows) == oracle, on reduced model shapes."""
+    from laplace_b200 import conv_engine, models
+
+    monkeypatch.setattr(conv_engine, "ELEMENTWISE_MIN_BATCH", 0)
+    model = models.make(name, **kw)
+    torch.manual_seed(0)
+    X, y = torch.randn(4, 3, 32, 32), torch.randint(10, (4,))
+    be = B200GGN(model, "classification")
+    _, kron = be.kron(X, y, N=4)
+    assert be.last_backward_mode == "batched"
+    _, kf = co.kfac_factors(model, "classification", X, y, N=4)
+    worst = max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo))
+    assert worst < 1e-5, worst
+    # diag / jacobian-based paths run through the same engine
+    _, d = be.diag(X, y)
+    Js, f = co.jacobians(model, X)
+    _, dref = co.ggn_diag(Js, f, y, "classification")
+    assert rel_fro(d, dref) < 1e-4
