@@ -461,7 +461,7 @@ class patched_convs:
             m.forward = relu_fwd
         for m, geom in self.pools:
             def pool_fwd(x, m=m, geom=geom):
-                if x.dim() != 4 or not usable(x) or x.shape[0] < ELEMENTWISE_MIN_BATCH:
+                if x.dim() != 4 or not usable(x) or x.shape[0] < ELEMENTWISE_MIN_BATCH or x.shape[2] * x.shape[3] > 1024:
                     return nn.MaxPool2d.forward(m, x)
                 return _MaxPool.apply(x, *geom)[0]
             m.forward = pool_fwd

@@ -83,6 +83,9 @@ int relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, cu
 // out [Q, C, H, W]; all NCHW-contiguous.
 constexpr int POOL_PLANES = 8;  // planes per iteration: amortises the two barriers and the global-load latency
 
+// The window bounds of a pixel depend only on (h, w): each thread owns a fixed set of pixels and computes their
+// bounds ONCE (the integer divisions by runtime k/s/W dominated the first version: ALU-bound at 0.5 TB/s), the
+// loop over planes then costs <= 4 shared-memory compares per output.
 __global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx,
                                                              float* __restrict__ out, int64_t planes, int Nb, int C, int H, int W,
                                                              int OH, int OW, int k, int s, int p) {
@@ -90,30 +93,47 @@ __global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restr
   const int T = OH * OW, HW = H * W;
   float* sg = reinterpret_cast<float*>(smem_raw);          // [POOL_PLANES][T]
   int* si = reinterpret_cast<int*>(sg + POOL_PLANES * T);  // [POOL_PLANES][T]
+  constexpr int MAXPIX = 4;                                 // pixels per thread (H*W <= 1024)
+  int pe[MAXPIX], t00[MAXPIX], noh[MAXPIX], now_[MAXPIX];
+  int npix = 0;
+  for (int e = threadIdx.x; e < HW && npix < MAXPIX; e += blockDim.x, ++npix) {
+    const int h = e / W, w = e - h * W;
+    const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
+    const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
+    pe[npix] = e; t00[npix] = oh_lo * OW + ow_lo; noh[npix] = oh_hi - oh_lo + 1; now_[npix] = ow_hi - ow_lo + 1;
+  }
   const int64_t groups = (planes + POOL_PLANES - 1) / POOL_PLANES;
   for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const int64_t p0 = grp * POOL_PLANES;
     const int np = (int)imin(POOL_PLANES, planes - p0);
-    for (int t = threadIdx.x; t < np * T; t += blockDim.x) {
-      const int j = t / T, tt = t - j * T;
-      const int64_t plane = p0 + j, q = plane / C;
-      const int c = (int)(plane - q * C);
-      sg[t] = g[plane * T + tt];
-      si[t] = (int)idx[((q % Nb) * C + c) * (int64_t)T + tt];
+    {
+      int j = 0, tt = threadIdx.x;                          // (plane-in-group, element) without divisions
+      while (tt >= T) { tt -= T; ++j; }
+      for (; j < np;) {
+        const int64_t plane = p0 + j, q = plane / C;
+        const int c = (int)(plane - q * C);
+        sg[j * T + tt] = g[plane * T + tt];
+        si[j * T + tt] = (int)idx[((q % Nb) * C + c) * (int64_t)T + tt];
+        tt += blockDim.x;
+        while (tt >= T) { tt -= T; ++j; }
+      }
     }
     __syncthreads();
-    for (int e2 = threadIdx.x; e2 < np * HW; e2 += blockDim.x) {
-      const int j = e2 / HW, e = e2 - j * HW;
-      const int h = e / W, w = e - h * W;
-      const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
-      const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
-      float acc = 0.f;
-      for (int oh = oh_lo; oh <= oh_hi; ++oh)
-        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-          const int t = j * T + oh * OW + ow;
-          if (si[t] == e) acc += sg[t];
-        }
-      out[(p0 + j) * HW + e] = acc;
+    for (int j = 0; j < np; ++j) {
+      const float* gj = sg + j * T;
+      const int* ij = si + j * T;
+      float* op = out + (p0 + j) * HW;
+#pragma unroll
+      for (int u = 0; u < MAXPIX; ++u) {
+        if (u >= npix) break;
+        float acc = 0.f;
+        for (int a = 0; a < noh[u]; ++a)
+          for (int b = 0; b < now_[u]; ++b) {
+            const int t = t00[u] + a * OW + b;
+            if (ij[t] == pe[u]) acc += gj[t];
+          }
+        op[pe[u]] = acc;
+      }
     }
     __syncthreads();
   }
@@ -126,7 +146,7 @@ int maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int
   LPB_REQUIRE(Nb > 0 && k > 0 && s > 0 && p >= 0, "maxpool2d_bwd: bad geometry");
   LPB_REQUIRE(planes < (1LL << 31), "maxpool2d_bwd: too many planes");
   const size_t smem = (size_t)OH * OW * 8 * POOL_PLANES;
-  LPB_REQUIRE(smem <= 48 * 1024, "maxpool2d_bwd: output plane too large for the shared-memory kernel");
+  LPB_REQUIRE(smem <= 48 * 1024 && (int64_t)H * W <= 1024, "maxpool2d_bwd: plane too large for the shared-memory kernel");
   const int threads = 256;
   const unsigned blocks = (unsigned)imin(ceil_div(planes, POOL_PLANES), (int64_t)sm_count() * 8);
   maxpool2d_bwd_kernel<<<blocks, threads, smem, st>>>(g, idx, out, planes, Nb, C, H, W, OH, OW, k, s, p);
