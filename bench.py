@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=2048)
+    ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--precision", default="bf16x3", choices=["auto", "fp32", "bf16", "bf16x3"])
     ap.add_argument("--model", default="resnet18")
     ap.add_argument("--cpu-samples", type=int, default=256, help="samples of the bounded CPU-baseline run")
