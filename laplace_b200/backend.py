@@ -456,7 +456,7 @@ class _B200Mixin:
         """``CurvatureInterface.last_layer_jacobians`` (curvature/curvature.py:131-167)."""
         if enable_backprop:
             return self._reference_fallback("last_layer_jacobians", x, enable_backprop=True)
-        with torch.no_grad(), self._model_numerics():
+        with torch.no_grad(), self._model_numerics(), self._conv_patch():
             f, phi = self.model.forward_with_features(x)
         self._device_check(f)
         C = int(f.numel() / phi.shape[0])
@@ -495,7 +495,7 @@ class _B200Mixin:
 
     # ------------------------------------------------------------------ last-layer structured curvature
     def _ll_forward(self, x):
-        with torch.no_grad(), self._model_numerics():
+        with torch.no_grad(), self._model_numerics(), self._conv_patch():
             f, phi = self.model.forward_with_features(x)
         self._device_check(f)
         if f.ndim != 2 or phi.ndim != 2:

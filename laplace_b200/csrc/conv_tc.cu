@@ -21,9 +21,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                     const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, int64_t Mrows,
                     int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile, int KH, int KW, int base_h,
-                    int base_w, int sgn, int kchunks, int num_stages, int fp16_operands) {
-  constexpr int TILES_PER_STAGE = NPROD == 3 ? 4 : 2;
-  constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
+                    int base_w, int sgn, int kchunks, int num_stages, int fp16_operands, int bn) {
+  // bn = MMA N extent (64 or 128): layers with <= 64 output channels would waste half of a 128-wide tile
+  const int B_BYTES = bn * BK * 2;
+  const int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (TILE_BYTES + B_BYTES);
+  const int OFF_B_HI = TILE_BYTES, OFF_A_LO = TILE_BYTES + B_BYTES, OFF_B_LO = 2 * TILE_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
@@ -63,30 +65,30 @@ conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_con
         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
         const int ch = base_h + sgn * kh, cw = base_w + sgn * kw;
         tma_load_4d(&tmX_hi, &full_bar[stage], st, kc * BK, cw, ch, q0);
-        tma_load_2d(&tmW_hi, &full_bar[stage], st + TILE_BYTES, kc * BK, tap * N + tn * BN);
+        tma_load_2d(&tmW_hi, &full_bar[stage], st + OFF_B_HI, kc * BK, tap * N + tn * bn);
         if (NPROD == 3) {
-          tma_load_4d(&tmX_lo, &full_bar[stage], st + 2 * TILE_BYTES, kc * BK, cw, ch, q0);
-          tma_load_2d(&tmW_lo, &full_bar[stage], st + 3 * TILE_BYTES, kc * BK, tap * N + tn * BN);
+          tma_load_4d(&tmX_lo, &full_bar[stage], st + OFF_A_LO, kc * BK, cw, ch, q0);
+          tma_load_2d(&tmW_lo, &full_bar[stage], st + OFF_B_LO, kc * BK, tap * N + tn * bn);
         }
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BM, BN, fp16_operands);
+      const uint32_t idesc = make_idesc(BM, bn, fp16_operands);
       int stage = 0; uint32_t phase = 0; uint32_t acc = 0;
       for (int it = 0; it < total; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + TILE_BYTES);
+        const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + OFF_B_HI);
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
           umma_f16(tmem_base, a_hi + koff, b_hi + koff, idesc, acc);
           acc = 1;
           if (NPROD == 3) {
-            const uint64_t a_lo = make_smem_desc(sbase + 2 * TILE_BYTES), b_lo = make_smem_desc(sbase + 3 * TILE_BYTES);
+            const uint64_t a_lo = make_smem_desc(sbase + OFF_A_LO), b_lo = make_smem_desc(sbase + OFF_B_LO);
             umma_f16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1);
             umma_f16(tmem_base, a_lo + koff, b_hi + koff, idesc, 1);
           }
@@ -103,10 +105,10 @@ conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_con
     const int64_t row = (int64_t)tm * BM + q * 32 + lane;
     const bool vec_ok = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
 #pragma unroll 1
-    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+    for (int chunk = 0; chunk < bn / 32; ++chunk) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), v);
-      const int col0 = tn * BN + chunk * 32;
+      const int col0 = tn * bn + chunk * 32;
       if (row < Mrows && col0 < N) {
         float* drow = D + row * ldd + col0;
         if (vec_ok && col0 + 32 <= N) {
@@ -157,21 +159,22 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
   const bool x3 = X_lo != nullptr;
   const int q_per_tile = 128 / (H * W);
   CUtensorMap tX_hi, tX_lo, tW_hi, tW_lo;
+  const int bn = N <= 64 ? 64 : 128;
   if (make_tmap_nhwc(&tX_hi, X_hi, Q, H, W, Kc, ldx, q_per_tile)) return 1;
-  if (make_tmap_2d(&tW_hi, W_hi, (int64_t)KH * KW * N, Kc, ldw)) return 1;
+  if (make_tmap_2d(&tW_hi, W_hi, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
   if (x3) {
     if (make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile)) return 1;
-    if (make_tmap_2d(&tW_lo, W_lo, (int64_t)KH * KW * N, Kc, ldw)) return 1;
+    if (make_tmap_2d(&tW_lo, W_lo, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
   } else {
     tX_lo = tX_hi; tW_lo = tW_hi;
   }
   const int64_t Mrows = Q * H * W;
   const int64_t tiles_m = ceil_div(Q, q_per_tile);
-  const int tiles_n = (int)ceil_div(N, tc::BN);
+  const int tiles_n = (int)ceil_div(N, bn);
   LPB_REQUIRE(tiles_m <= 2147483647LL && tiles_n <= 65535, "conv_nhwc_bf16: too many tiles");
   const int kchunks = (int)ceil_div(Kc, tc::BK);
-  const int stage_bytes = (x3 ? 4 : 2) * tc::TILE_BYTES;
-  const int num_stages = x3 ? 3 : 6;
+  const int stage_bytes = (x3 ? 2 : 1) * (tc::TILE_BYTES + bn * tc::BK * 2);
+  const int num_stages = (int)imin(8, (200 * 1024) / stage_bytes);
   const size_t smem = (size_t)num_stages * stage_bytes + (2 * num_stages + 1) * sizeof(uint64_t) + 16 + 1024;
   static bool attr1 = false, attr3 = false;
   if (x3 && !attr3) {
@@ -190,11 +193,11 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
   if (x3)
     tc::conv_nhwc_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,
                                                                     q_per_tile, KH, KW, base_h, base_w, sgn, kchunks,
-                                                                    num_stages, fp16_operands);
+                                                                    num_stages, fp16_operands, bn);
   else
     tc::conv_nhwc_tc_kernel<1><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,
                                                                     q_per_tile, KH, KW, base_h, base_w, sgn, kchunks,
-                                                                    num_stages, fp16_operands);
+                                                                    num_stages, fp16_operands, bn);
   LPB_CHECK_LAUNCH("conv_nhwc_bf16");
   return 0;
 }

@@ -205,12 +205,12 @@ static int make_tmap_rows(CUtensorMap* map, const void* ptr, int64_t rows, int64
   return 0;
 }
 
-int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld) {
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
   PFN_encodeTiled enc = get_tensormap_encoder();
   LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+  cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -287,15 +287,17 @@ __global__ void __launch_bounds__(256) pack_conv2d_rows_vec8_kernel(const float*
     const int64_t n = r / ((int64_t)g.OW * g.OH);
     const float* xn = x + n * g.C * g.H * g.W;
     alignas(16) unsigned short h[8], l[8];
+    // decode (ci, kh, kw) of the first entry once, then step it (integer divisions dominated the first version)
+    int kw = j0 % g.KW, kh = (j0 / g.KW) % g.KH, ci = j0 / (g.KW * g.KH);
+    const int ih0 = oh * g.SH - g.PH, iw0 = ow * g.SW - g.PW;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int j = j0 + i;
       float v = 0.f;
-      if (j < d_in) {
-        const int kw = j % g.KW, kh = (j / g.KW) % g.KH, ci = j / (g.KW * g.KH);
-        const int ih = oh * g.SH - g.PH + kh * g.DH, iw = ow * g.SW - g.PW + kw * g.DW;
+      if (j0 + i < d_in) {
+        const int ih = ih0 + kh * g.DH, iw = iw0 + kw * g.DW;
         if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = __ldg(xn + ((int64_t)ci * g.H + ih) * g.W + iw);
       }
+      if (++kw == g.KW) { kw = 0; if (++kh == g.KH) { kh = 0; ++ci; } }
       if constexpr (KIND == OUT_F16_HILO) {
         const __half hh = __float2half_rn(v);
         h[i] = __half_as_ushort(hh);

@@ -128,6 +128,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_tensormap_encoder();
-int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld);
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows = 128);
 
 }  // namespace lpb

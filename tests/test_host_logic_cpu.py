@@ -148,3 +148,28 @@ def test_convolution_engine_paths_on_model_zoo(cpu_kernels, monkeypatch, name, k
     Js, f = co.jacobians(model, X)
     _, dref = co.ggn_diag(Js, f, y, "classification")
     assert rel_fro(d, dref) < 1e-4
+
+
+def test_mapping_inputs_and_dtype_propagation(golden, cpu_kernels):
+    """HF-style MutableMapping batches (baselaplace.py:969-974, curvlinops.py:84-85) and model-dtype outputs
+    (reference tests/test_baselaplace.py:895-934)."""
+    class DictModel(torch.nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+
+        def forward(self, batch):
+            return self.net(batch["input_ids"])
+
+    model, X, y, _ = load(golden, "mlp", "classification", dtype=torch.float32)
+    ref_loss, ref = B200GGN(model, "classification").kron(X, y, N=len(X))
+    wrapped = DictModel(model)
+    loss, kron = B200GGN(wrapped, "classification").kron({"input_ids": X, "labels": y}, y, N=len(X))
+    assert torch.allclose(loss, ref_loss)
+    for F, Fr in zip(kron.kfacs, ref.kfacs):
+        for H, Hr in zip(F, Fr):
+            assert H.dtype == torch.float32 and torch.allclose(H, Hr)
+    m64, X64, y64, _ = load(golden, "mlp", "regression", dtype=torch.float64)
+    be = B200GGN(m64, "regression")
+    assert be.jacobians(X64)[0].dtype == torch.float64 and be.full(X64, y64)[1].dtype == torch.float64
+    assert be.diag(X64, y64)[1].dtype == torch.float64 and be.kron(X64, y64, N=10)[1].kfacs[0][0].dtype == torch.float64
