@@ -416,7 +416,28 @@ def measure_predictive(model, dev, B200Laplace, B200GGN, args):
     for i in range(4):
         la(Xf[i * 512:(i + 1) * 512])
     torch.cuda.synchronize()
-    return {"glm_predictive_ll_full_samples_per_sec": 2048 / (time.perf_counter() - t0)}
+    out = {"glm_predictive_ll_full_samples_per_sec": 2048 / (time.perf_counter() - t0)}
+    # BASELINE configs[0]: MLP 784->128->10, N = 1000, KFAC-GGN fit + GLM predictive over the same 1000 points
+    from laplace_b200 import models
+
+    mlp = models.make("mlp").to(dev)
+    torch.manual_seed(6)
+    Xm, ym = torch.randn(1000, 784, device=dev), torch.randint(10, (1000,), device=dev)
+    lam = B200Laplace(mlp, "classification", "all", "kron", backend=B200GGN)
+    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(Xm, ym), batch_size=128)
+    lam.fit(loader)
+    lam(Xm[:500])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lam.fit(loader)
+    torch.cuda.synchronize()
+    out["mlp_kron_fit_1k_samples_per_sec_incl_decompose"] = 1000 / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for i in range(0, 1000, 500):
+        lam(Xm[i:i + 500])
+    torch.cuda.synchronize()
+    out["mlp_kron_glm_predictive_samples_per_sec"] = 1000 / (time.perf_counter() - t0)
+    return out
 
 
 if __name__ == "__main__":

@@ -463,8 +463,9 @@ class _B200Mixin:
         has_bias = self.model.last_layer.bias is not None
         Js = K.ll_jacobian_write(phi.detach().float(), C, has_bias)
         dtype = next(self.model.parameters()).dtype
-        Js = Js.to(dtype)
-        Js._lpb_ll = (phi.detach().float().contiguous(), C, has_bias)
+        from .predictive import StructuredJacobian
+
+        Js = StructuredJacobian.wrap(Js.to(dtype), (phi.detach().float().contiguous(), C, has_bias))
         return Js, f.detach()
 
     def gradients(self, x, y):

@@ -161,6 +161,11 @@ class B200Laplace:
         if self.structure == "kron":
             return self.posterior_precision.inv_square_form(Js)
         if self.structure == "diag":
+            ll = getattr(Js, "_lpb_ll", None)
+            if ll is not None:
+                from .predictive import ll_diag_variance
+
+                return ll_diag_variance(ll[0], ll[1], ll[2], 1.0 / self.posterior_precision).to(Js.dtype)
             Jf = Js.float().contiguous()
             var = (1.0 / self.posterior_precision).float().contiguous()
             out = torch.empty(Js.shape[0], Js.shape[1], Js.shape[1], device=Js.device, dtype=torch.float32)
@@ -178,20 +183,11 @@ class B200Laplace:
         return K.batched_pair_dot(Y.view(Bc, C, P), Jf.view(Bc, C, P), None, out).to(Js.dtype)
 
     def _ll_full_variance(self, phi, C, has_bias):
-        """``f_var[n,c,k] = [phi;1]^T Sigma_(c,.),(k,.) [phi;1]``: one GEMM-NT against the gathered covariance
-        blocks + a per-sample reduction (structured form of baselaplace.py:1683-1684 for last-layer J)."""
-        M, D = phi.shape
-        phit = torch.cat([phi, torch.ones(M, 1, device=phi.device)], 1).contiguous() if has_bias else phi
-        Dt = phit.shape[1]
-        if self._ll_cache is None:
-            self._ll_cache = K.ll_sigma_gather(self.posterior_covariance.float(), C, D, has_bias)  # [(c,k,et), dt]
-        Sg = self._ll_cache
-        Y = torch.empty(M, C * C * Dt, device=phi.device, dtype=torch.float32)
-        K.gemm_nt(K.Packed(phit, None, K.F32, M, Dt), K.Packed(Sg, None, K.F32, Sg.shape[0], Dt), Y, 1.0,
-                  accumulate=False)
-        out = torch.empty(M, C * C, 1, device=phi.device, dtype=torch.float32)
-        K.batched_pair_dot(Y.view(M, C * C, Dt), phit.view(M, 1, Dt), None, out)
-        return out.view(M, C, C)
+        """Structured last-layer form of baselaplace.py:1683-1684 (``laplace_b200/predictive.py``)."""
+        from .predictive import ll_full_variance
+
+        out, self._ll_cache = ll_full_variance(phi, C, has_bias, self.posterior_covariance, self._ll_cache)
+        return out
 
     def glm_predictive_distribution(self, X):
         if self.last_layer:

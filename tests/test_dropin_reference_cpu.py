@@ -81,6 +81,12 @@ def test_last_layer_full_laplace(golden, cpu_kernels, laplace_mod):
 
     from laplace_b200 import B200EF, B200GGN
 
+    from laplace_b200 import predictive
+
+    calls = {"full": 0, "diag": 0}
+    orig_full, orig_diag = predictive.ll_full_variance, predictive.ll_diag_variance
+    predictive.ll_full_variance = lambda *a, **k: (calls.__setitem__("full", calls["full"] + 1), orig_full(*a, **k))[1]
+    predictive.ll_diag_variance = lambda *a, **k: (calls.__setitem__("diag", calls["diag"] + 1), orig_diag(*a, **k))[1]
     model, X, y, rec = load(golden, "mlp", "classification")
     loader = DataLoader(TensorDataset(X, y), batch_size=4)
     for be, ref_be in ((B200GGN, GGNInterface),):
@@ -95,9 +101,16 @@ def test_last_layer_full_laplace(golden, cpu_kernels, laplace_mod):
     for hs in ("diag", "kron"):
         la = laplace_mod.Laplace(model, "classification", "last_layer", hs, backend=B200GGN, prior_precision=0.7)
         la.fit(loader)
-        la._glm_predictive_distribution(X)
+        _, fv = la._glm_predictive_distribution(X)
+        if hs == "diag":
+            lr = laplace_mod.Laplace(model, "classification", "last_layer", hs, backend=GGNInterface, prior_precision=0.7)
+            lr.fit(loader)
+            assert torch.allclose(fv, lr._glm_predictive_distribution(X)[1], rtol=1e-4, atol=1e-8)
     la = laplace_mod.Laplace(model, "classification", "last_layer", "full", backend=B200EF)
     la.fit(loader)
+    predictive.ll_full_variance, predictive.ll_diag_variance = orig_full, orig_diag
+    # the reference's own einsums (baselaplace.py:1683-1684, :2115) were routed into the structured kernels
+    assert calls["full"] >= 1 and calls["diag"] >= 1, calls
 
 
 def test_subnetwork_laplace(golden, cpu_kernels, laplace_mod):
