@@ -81,61 +81,33 @@ int relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, cu
 // indices are staged in shared memory, every input pixel then sums the (at most ceil(k/s)^2) windows whose argmax it is.
 // g [Q, C, OH, OW], idx [Nb, C, OH, OW] (flattened h*W + w of the argmax, forward of the Nb images; q -> q % Nb),
 // out [Q, C, H, W]; all NCHW-contiguous.
-constexpr int POOL_PLANES = 8;  // planes per iteration: amortises the two barriers and the global-load latency
+constexpr int POOL_PLANES = 8;  // planes per CTA
 
-// The window bounds of a pixel depend only on (h, w): each thread owns a fixed set of pixels and computes their
-// bounds ONCE (the integer divisions by runtime k/s/W dominated the first version: ALU-bound at 0.5 TB/s), the
-// loop over planes then costs <= 4 shared-memory compares per output.
-__global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx,
-                                                             float* __restrict__ out, int64_t planes, int Nb, int C, int H, int W,
-                                                             int OH, int OW, int k, int s, int p) {
-  extern __shared__ unsigned char smem_raw[];
-  const int T = OH * OW, HW = H * W;
-  float* sg = reinterpret_cast<float*>(smem_raw);          // [POOL_PLANES][T]
-  int* si = reinterpret_cast<int*>(sg + POOL_PLANES * T);  // [POOL_PLANES][T]
-  constexpr int MAXPIX = 4;                                 // pixels per thread (H*W <= 1024)
-  int pe[MAXPIX], t00[MAXPIX], noh[MAXPIX], now_[MAXPIX];
-  int npix = 0;
-  for (int e = threadIdx.x; e < HW && npix < MAXPIX; e += blockDim.x, ++npix) {
-    const int h = e / W, w = e - h * W;
-    const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
-    const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
-    pe[npix] = e; t00[npix] = oh_lo * OW + ow_lo; noh[npix] = oh_hi - oh_lo + 1; now_[npix] = ow_hi - ow_lo + 1;
-  }
-  const int64_t groups = (planes + POOL_PLANES - 1) / POOL_PLANES;
-  for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    const int64_t p0 = grp * POOL_PLANES;
-    const int np = (int)imin(POOL_PLANES, planes - p0);
-    {
-      int j = 0, tt = threadIdx.x;                          // (plane-in-group, element) without divisions
-      while (tt >= T) { tt -= T; ++j; }
-      for (; j < np;) {
-        const int64_t plane = p0 + j, q = plane / C;
-        const int c = (int)(plane - q * C);
-        sg[j * T + tt] = g[plane * T + tt];
-        si[j * T + tt] = (int)idx[((q % Nb) * C + c) * (int64_t)T + tt];
-        tt += blockDim.x;
-        while (tt >= T) { tt -= T; ++j; }
+// Block = one (W x H) thread per input pixel; its <= ceil(k/s)^2 candidate windows are fixed by (h, w) and computed
+// once.  The CTA then walks POOL_PLANES planes: argmax indices / gradients come through L1 (each is read by the up to
+// four pixels whose windows overlap), the output store is fully coalesced.  No shared memory, no barriers, no
+// per-element integer division (earlier versions were ALU-bound on runtime divisions at 0.3-0.8 TB/s).
+__global__ void maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx, float* __restrict__ out,
+                                     int planes, int Nb, int C, int H, int W, int OH, int OW, int k, int s, int p) {
+  const int w = threadIdx.x, h = threadIdx.y;
+  const int T = OH * OW, HW = H * W, me = h * W + w;
+  const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
+  const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
+  const int p0 = blockIdx.x * POOL_PLANES;
+#pragma unroll 1
+  for (int j = 0; j < POOL_PLANES; ++j) {
+    const int plane = p0 + j;
+    if (plane >= planes) break;
+    const int q = plane / C, c = plane - q * C;
+    const float* gp = g + (int64_t)plane * T;
+    const int64_t* ip = idx + ((int64_t)(q % Nb) * C + c) * T;
+    float acc = 0.f;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const int t = oh * OW + ow;
+        if ((int)__ldg(ip + t) == me) acc += __ldg(gp + t);
       }
-    }
-    __syncthreads();
-    for (int j = 0; j < np; ++j) {
-      const float* gj = sg + j * T;
-      const int* ij = si + j * T;
-      float* op = out + (p0 + j) * HW;
-#pragma unroll
-      for (int u = 0; u < MAXPIX; ++u) {
-        if (u >= npix) break;
-        float acc = 0.f;
-        for (int a = 0; a < noh[u]; ++a)
-          for (int b = 0; b < now_[u]; ++b) {
-            const int t = t00[u] + a * OW + b;
-            if (ij[t] == pe[u]) acc += gj[t];
-          }
-        op[pe[u]] = acc;
-      }
-    }
-    __syncthreads();
+    out[(int64_t)plane * HW + me] = acc;
   }
 }
 
@@ -145,11 +117,10 @@ int maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int
   if (planes == 0) return 0;
   LPB_REQUIRE(Nb > 0 && k > 0 && s > 0 && p >= 0, "maxpool2d_bwd: bad geometry");
   LPB_REQUIRE(planes < (1LL << 31), "maxpool2d_bwd: too many planes");
-  const size_t smem = (size_t)OH * OW * 8 * POOL_PLANES;
-  LPB_REQUIRE(smem <= 48 * 1024 && (int64_t)H * W <= 1024, "maxpool2d_bwd: plane too large for the shared-memory kernel");
-  const int threads = 256;
-  const unsigned blocks = (unsigned)imin(ceil_div(planes, POOL_PLANES), (int64_t)sm_count() * 8);
-  maxpool2d_bwd_kernel<<<blocks, threads, smem, st>>>(g, idx, out, planes, Nb, C, H, W, OH, OW, k, s, p);
+  LPB_REQUIRE((int64_t)H * W <= 1024, "maxpool2d_bwd: plane larger than one thread block (H*W <= 1024)");
+  dim3 block(W, H);
+  const unsigned blocks = (unsigned)ceil_div(planes, POOL_PLANES);
+  maxpool2d_bwd_kernel<<<blocks, block, 0, st>>>(g, idx, out, (int)planes, Nb, C, H, W, OH, OW, k, s, p);
   LPB_CHECK_LAUNCH("maxpool2d_bwd");
   return 0;
 }
