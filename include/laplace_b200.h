@@ -38,6 +38,9 @@ int lpb_version(void);
 const char* lpb_last_error(void);
 /* sm count / compute capability of the current device */
 int lpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Tile shape of lpb_gemm_nt_tc / lpb_gemm_tn_tc: -1 automatic (default), 0 always 128 x 128 single-CTA tiles,
+ * 1 256 x 256 CTA-pair tiles (tcgen05 cta_group::2) whenever M, N >= 256.  Results agree to fp32 rounding. */
+int lpb_set_gemm_tile_mode(int mode);
 
 /* ---- pack: layer inputs / output gradients -> K-major staging ----------------------------
  * Front end of the KFAC factor contractions that curvlinops performs as einsum("b i,b j->i j")
@@ -82,6 +85,9 @@ int lpb_pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, 
 /* col2im gather: Dc [(ci,kh,kw), ldd] with columns (q,oh,ow) -> grad_in [Q, C, H, W] (overwrites)        */
 int lpb_col2im(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,
                int DH, int DW, float* grad_in, void* stream);
+/* channels-last form: Dc [(q,oh,ow), ldd] with columns (kh,kw,ci) -> grad_in [Q, H, W, C] (overwrites)     */
+int lpb_col2im_nhwc(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,
+                    int DH, int DW, float* grad_in, void* stream);
 
 /* ---- contractions ------------------------------------------------------------------------
  * D[M, N] (fp32, ldd)  (+)=  alpha * A[M, K] * B[N, K]^T   on K-major operands.
@@ -118,6 +124,9 @@ int lpb_relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps
 /* max-pool backward (gather form): g [Q,C,OH,OW], idx [Nb,C,OH,OW] argmax (h*W+w) of image q % Nb -> out [Q,C,H,W] */
 int lpb_maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH, int OW,
                       int k, int s, int p, void* stream);
+/* the same on channels-last memory: g [Q,OH,OW,C], idx [Nb,OH,OW,C] -> out [Q,H,W,C]                                  */
+int lpb_maxpool2d_bwd_nhwc(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH,
+                           int OW, int k, int s, int p, void* stream);
 
 /* ---- weight-sharing layers: per-sample layer Jacobians ------------------------------------
  * P_q[i,j] = sum_t G[i, q*T+t] * A[j, (q % Nn)*T + t], q = c*Nn + n over ncols back-propagated columns.

@@ -17,6 +17,7 @@ c_i64, c_int, c_f32, c_vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 # name -> argtypes ; every entry point of include/laplace_b200.h returning int
 SIGNATURES = {
     "lpb_device_info": [C.POINTER(c_int)] * 3,
+    "lpb_set_gemm_tile_mode": [c_int],
     "lpb_pack_rows_t": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
     "lpb_pack_conv2d_t": [c_vp] + [c_int] * 12 + [c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
     "lpb_pack_nchw_t": [c_vp, c_i64, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
@@ -24,12 +25,14 @@ SIGNATURES = {
     "lpb_pack_nchw_rows": [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_vp],
     "lpb_pack_cast": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_i64, c_vp],
     "lpb_col2im": [c_vp, c_i64] + [c_int] * 12 + [c_vp, c_vp],
+    "lpb_col2im_nhwc": [c_vp, c_i64] + [c_int] * 12 + [c_vp, c_vp],
     "lpb_gemm_nt_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_vp],
     "lpb_gemm_nt_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
                        c_vp],
     "lpb_scale_channels": [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_vp],
     "lpb_relu_bwd": [c_vp, c_vp, c_vp, c_i64, c_int, c_vp],
     "lpb_maxpool2d_bwd": [c_vp, c_vp, c_vp, c_i64] + [c_int] * 9 + [c_vp],
+    "lpb_maxpool2d_bwd_nhwc": [c_vp, c_vp, c_vp, c_i64] + [c_int] * 9 + [c_vp],
     "lpb_gemm_tn_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
                        c_vp],
     "lpb_conv_nhwc_tc": [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int,

@@ -326,6 +326,11 @@ class _B200Mixin:
             Grows = rows.get("G")
             if Grows is not None and Grows.rows != g.numel() // L.d_out:
                 Grows = None
+            if Grows is None and L.is_conv and stash is not None and len(stash) > 0 and g.dim() == 5:
+                # a convolution whose reverse node never ran (the first layer: nothing upstream needs its input
+                # gradient): pack the output-gradient rows here, channels-last, for the same MN-major SYRK
+                g4 = g.reshape(g.shape[0] * g.shape[1], *g.shape[2:])
+                Grows = conv_engine.nhwc_rows(g4 if g4.dtype == torch.float32 else g4.float(), K.BF16X3)
             if Grows is None:
                 gk = self._kind(L.d_out, g.numel() // L.d_out)
                 G = self._pack_grad(L, g, gk, reduce)

@@ -115,9 +115,9 @@ def conv_forward(x: torch.Tensor, mod: nn.Conv2d) -> torch.Tensor:
     P = K.pack_conv_rows(x, mod, KIND_FWD)                   # [(n,t), d_in]
     STASH.setdefault(id(mod), {})["P"] = P
     Wk = _CACHE.get(mod, "fwd")                              # [Co, d_in]
-    out = torch.empty(Co, N * OH * OW, device=x.device, dtype=torch.float32)
-    K.gemm_nt(Wk, P, out, getattr(Wk, "inv_scale", 1.0), accumulate=False)
-    out = out.view(Co, N, OH * OW).permute(1, 0, 2).reshape(N, Co, OH, OW)
+    out = torch.empty(N * OH * OW, Co, device=x.device, dtype=torch.float32)
+    K.gemm_nt(P, Wk, out, getattr(Wk, "inv_scale", 1.0), accumulate=False)
+    out = out.view(N, OH, OW, Co).permute(0, 3, 1, 2)        # channels-last view like the implicit path
     if mod.bias is not None:
         out = out + mod.bias.detach().view(1, -1, 1, 1)
     return out
@@ -133,10 +133,10 @@ def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape, need_dx: bool 
         return None
     if implicit_ok(mod, in_shape[2], in_shape[3]):
         return _implicit(g, mod, "bwd_taps", mod.in_channels, -1, X=G)
-    Wt = _CACHE.get(mod, "bwd")                              # [d_in, Co]
-    Dc = torch.empty(Wt.rows, Q * T, device=g.device, dtype=torch.float32)
-    K.gemm_nt(Wt, G, Dc, 1.0, accumulate=False)
-    return K.col2im(Dc, (Q,) + tuple(in_shape[1:]), mod)
+    Wt = _CACHE.get(mod, "bwd_taps")                         # [(kh,kw,ci), Co]
+    Dc = torch.empty(Q * T, Wt.rows, device=g.device, dtype=torch.float32)
+    K.gemm_nt(G, Wt, Dc, 1.0, accumulate=False)              # [(q,t), (kh,kw,ci)]
+    return K.col2im_nhwc(Dc, (Q,) + tuple(in_shape[1:]), mod)   # channels-last view: every gradient stays NHWC
 
 
 class _ConvBwdData(torch.autograd.Function):

@@ -59,6 +59,9 @@ int ll_ggn_expand(const float*, int, int, int, int, float*, cudaStream_t);
 int ll_sigma_gather(const float*, int, int, int, float*, cudaStream_t);
 int eigh_jacobi(const float*, int, int, float*, float*, int, cudaStream_t);
 
+void set_gemm_pair_mode(int mode);
+int col2im_nhwc(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
+int maxpool2d_bwd_nhwc(const float*, const int64_t*, float*, int64_t, int, int, int, int, int, int, int, int, int, cudaStream_t);
 }  // namespace lpb
 
 using lpb::set_error;
@@ -69,6 +72,11 @@ extern "C" {
 int lpb_version(void) { return 100; }
 
 const char* lpb_last_error(void) { return lpb::get_error(); }
+
+int lpb_set_gemm_tile_mode(int mode) {
+  lpb::set_gemm_pair_mode(mode);
+  return 0;
+}
 
 int lpb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
@@ -152,6 +160,19 @@ int lpb_col2im(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH,
   if (make_geom(g, Q, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW)) return 1;
   LPB_REQUIRE(ldd >= (int64_t)Q * g.OH * g.OW, "lpb_col2im: ldd too small");
   return lpb::col2im(Dc, ldd, g, grad_in, ST(stream));
+}
+
+int lpb_col2im_nhwc(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,
+                    int DH, int DW, float* grad_in, void* stream) {
+  lpb::ConvGeom g;
+  if (make_geom(g, Q, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW)) return 1;
+  LPB_REQUIRE(ldd >= (int64_t)KH * KW * C, "lpb_col2im_nhwc: ldd too small");
+  return lpb::col2im_nhwc(Dc, ldd, g, grad_in, ST(stream));
+}
+
+int lpb_maxpool2d_bwd_nhwc(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH,
+                           int OW, int k, int s, int p, void* stream) {
+  return lpb::maxpool2d_bwd_nhwc(g, idx, out, Q, Nb, C, H, W, OH, OW, k, s, p, ST(stream));
 }
 
 int lpb_gemm_nt_f32(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,

@@ -81,46 +81,125 @@ int relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, cu
 // indices are staged in shared memory, every input pixel then sums the (at most ceil(k/s)^2) windows whose argmax it is.
 // g [Q, C, OH, OW], idx [Nb, C, OH, OW] (flattened h*W + w of the argmax, forward of the Nb images; q -> q % Nb),
 // out [Q, C, H, W]; all NCHW-contiguous.
-constexpr int POOL_PLANES = 8;  // planes per CTA
-
-// Block = one (W x H) thread per input pixel; its <= ceil(k/s)^2 candidate windows are fixed by (h, w) and computed
-// once.  The CTA then walks POOL_PLANES planes: argmax indices / gradients come through L1 (each is read by the up to
-// four pixels whose windows overlap), the output store is fully coalesced.  No shared memory, no barriers, no
-// per-element integer division (earlier versions were ALU-bound on runtime divisions at 0.3-0.8 TB/s).
+// MaxPool backward for `cols` stacked gradient columns that share one argmax map (the vmapped reverse pass:
+// q = col * Nb + n).  One CTA per (n, c) plane, one thread per input pixel (block = W x H).  The pixel's candidate
+// windows -- at most NC x NC, fixed by (h, w) -- and whether each window's argmax IS this pixel are evaluated once
+// from the int64 argmax map; the column loop then only issues independent gradient loads (served by L1: each plane of
+// gradients is read by the <= NC^2 pixels sharing a window) and one coalesced store per column.  The argmax map is
+// read once instead of once per column, and no load depends on another (the previous version chained
+// idx -> compare -> gradient per plane and ran at ~1 TB/s).
+template <int NC>
 __global__ void maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx, float* __restrict__ out,
-                                     int planes, int Nb, int C, int H, int W, int OH, int OW, int k, int s, int p) {
+                                     int cols, int planes_per_col, int H, int W, int OH, int OW, int k, int s, int p) {
   const int w = threadIdx.x, h = threadIdx.y;
   const int T = OH * OW, HW = H * W, me = h * W + w;
+  const int plane = blockIdx.x;
   const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
   const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
-  const int p0 = blockIdx.x * POOL_PLANES;
-#pragma unroll 1
-  for (int j = 0; j < POOL_PLANES; ++j) {
-    const int plane = p0 + j;
-    if (plane >= planes) break;
-    const int q = plane / C, c = plane - q * C;
-    const float* gp = g + (int64_t)plane * T;
-    const int64_t* ip = idx + ((int64_t)(q % Nb) * C + c) * T;
+  const int64_t* ip = idx + (int64_t)plane * T;
+  int tpos[NC * NC];
+  float sel[NC * NC];
+#pragma unroll
+  for (int a = 0; a < NC; ++a)
+#pragma unroll
+    for (int b = 0; b < NC; ++b) {
+      const int oh = oh_lo + a, ow = ow_lo + b;
+      const bool in = oh <= oh_hi && ow <= ow_hi;
+      const int t = in ? oh * OW + ow : 0;
+      tpos[a * NC + b] = t;
+      sel[a * NC + b] = (in && (int)__ldg(ip + t) == me) ? 1.f : 0.f;
+    }
+  const int64_t gstride = (int64_t)planes_per_col * T, ostride = (int64_t)planes_per_col * HW;
+  const float* gp = g + (int64_t)plane * T;
+  float* op = out + (int64_t)plane * HW + me;
+#pragma unroll 4
+  for (int col = 0; col < cols; ++col) {
     float acc = 0.f;
-    for (int oh = oh_lo; oh <= oh_hi; ++oh)
-      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-        const int t = oh * OW + ow;
-        if ((int)__ldg(ip + t) == me) acc += __ldg(gp + t);
-      }
-    out[(int64_t)plane * HW + me] = acc;
+#pragma unroll
+    for (int i = 0; i < NC * NC; ++i) acc = fmaf(sel[i], __ldg(gp + tpos[i]), acc);
+    *op = acc;
+    gp += gstride;
+    op += ostride;
   }
+}
+
+// Channels-last form of the same reverse pass: g [Q, OH, OW, C], argmax map [Nb, OH, OW, C] (values h * W + w),
+// out [Q, H, W, C].  One thread per (n, h, w, c); consecutive threads walk the channels, so the argmax loads, the
+// gradient loads and the stores are all coalesced; window membership is evaluated once and reused by every column.
+template <int NC>
+__global__ void __launch_bounds__(256) maxpool2d_bwd_nhwc_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx,
+                                                                 float* __restrict__ out, int cols, int Nb, int C, int H,
+                                                                 int W, int OH, int OW, int k, int s, int p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per_col = (int64_t)Nb * H * W * C;
+  if (i >= per_col) return;
+  const int c = (int)(i % C);
+  int64_t pix = i / C;
+  const int w = (int)(pix % W);
+  pix /= W;
+  const int h = (int)(pix % H);
+  const int64_t n = pix / H;
+  const int me = h * W + w;
+  const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
+  const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
+  int64_t tpos[NC * NC];
+  float sel[NC * NC];
+#pragma unroll
+  for (int a = 0; a < NC; ++a)
+#pragma unroll
+    for (int b = 0; b < NC; ++b) {
+      const int oh = oh_lo + a, ow = ow_lo + b;
+      const bool in = oh <= oh_hi && ow <= ow_hi;
+      const int64_t t = in ? ((n * OH + oh) * OW + ow) * C + c : (n * OH * OW) * C + c;
+      tpos[a * NC + b] = t;
+      sel[a * NC + b] = (in && (int)__ldg(idx + t) == me) ? 1.f : 0.f;
+    }
+  const int64_t gstride = (int64_t)Nb * OH * OW * C;
+  float* op = out + i;
+#pragma unroll 2
+  for (int col = 0; col < cols; ++col) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC * NC; ++j) acc = fmaf(sel[j], __ldg(g + tpos[j]), acc);
+    *op = acc;
+    g += gstride;
+    op += per_col;
+  }
+}
+
+int maxpool2d_bwd_nhwc(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH,
+                       int OW, int k, int s, int p, cudaStream_t st) {
+  if (Q * C == 0) return 0;
+  LPB_REQUIRE(Nb > 0 && k > 0 && s > 0 && p >= 0, "maxpool2d_bwd_nhwc: bad geometry");
+  LPB_REQUIRE(Q % Nb == 0, "maxpool2d_bwd_nhwc: Q must be a multiple of the argmax batch Nb");
+  const int nc = (k + s - 1) / s;
+  LPB_REQUIRE(nc <= 3, "maxpool2d_bwd_nhwc: kernel_size > 3 * stride is not supported");
+  const int64_t per_col = (int64_t)Nb * H * W * C;
+  const int64_t blocks = ceil_div(per_col, 256);
+  LPB_REQUIRE(blocks < (1LL << 31), "maxpool2d_bwd_nhwc: too many elements");
+  const int cols = (int)(Q / Nb);
+  if (nc <= 1) maxpool2d_bwd_nhwc_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(g, idx, out, cols, Nb, C, H, W, OH, OW, k, s, p);
+  else if (nc == 2) maxpool2d_bwd_nhwc_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(g, idx, out, cols, Nb, C, H, W, OH, OW, k, s, p);
+  else maxpool2d_bwd_nhwc_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(g, idx, out, cols, Nb, C, H, W, OH, OW, k, s, p);
+  LPB_CHECK_LAUNCH("maxpool2d_bwd_nhwc");
+  return 0;
 }
 
 int maxpool2d_bwd(const float* g, const int64_t* idx, float* out, int64_t Q, int Nb, int C, int H, int W, int OH, int OW,
                   int k, int s, int p, cudaStream_t st) {
-  const int64_t planes = Q * C;
-  if (planes == 0) return 0;
+  if (Q * C == 0) return 0;
   LPB_REQUIRE(Nb > 0 && k > 0 && s > 0 && p >= 0, "maxpool2d_bwd: bad geometry");
-  LPB_REQUIRE(planes < (1LL << 31), "maxpool2d_bwd: too many planes");
+  LPB_REQUIRE(Q % Nb == 0, "maxpool2d_bwd: Q must be a multiple of the argmax batch Nb");
+  LPB_REQUIRE((int64_t)Nb * C < (1LL << 31), "maxpool2d_bwd: too many planes");
   LPB_REQUIRE((int64_t)H * W <= 1024, "maxpool2d_bwd: plane larger than one thread block (H*W <= 1024)");
+  const int nc = (k + s - 1) / s;   // windows covering one pixel, per dimension
+  LPB_REQUIRE(nc <= 3, "maxpool2d_bwd: kernel_size > 3 * stride is not supported");
   dim3 block(W, H);
-  const unsigned blocks = (unsigned)ceil_div(planes, POOL_PLANES);
-  maxpool2d_bwd_kernel<<<blocks, block, 0, st>>>(g, idx, out, (int)planes, Nb, C, H, W, OH, OW, k, s, p);
+  const unsigned blocks = (unsigned)(Nb * C);
+  const int cols = (int)(Q / Nb);
+  if (nc <= 1) maxpool2d_bwd_kernel<1><<<blocks, block, 0, st>>>(g, idx, out, cols, Nb * C, H, W, OH, OW, k, s, p);
+  else if (nc == 2) maxpool2d_bwd_kernel<2><<<blocks, block, 0, st>>>(g, idx, out, cols, Nb * C, H, W, OH, OW, k, s, p);
+  else maxpool2d_bwd_kernel<3><<<blocks, block, 0, st>>>(g, idx, out, cols, Nb * C, H, W, OH, OW, k, s, p);
   LPB_CHECK_LAUNCH("maxpool2d_bwd");
   return 0;
 }

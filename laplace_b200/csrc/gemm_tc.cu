@@ -12,6 +12,8 @@
 //   * SYRK mode visits only tiles on/above the diagonal and mirrors them;
 //   * optional error-compensated mode (NPROD = 3): hi*hi + hi*lo + lo*hi with bf16 hi/lo splits,
 //     all three products accumulated in the same TMEM tile (relative product error ~2^-16).
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lpb {
@@ -223,6 +225,26 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int
 static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
                    int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
                    int fp16_operands, cudaStream_t st);
+int launch_gemm_tc_pair(bool mn, bool x3, const CUtensorMap& tA_hi, const CUtensorMap& tA_lo, const CUtensorMap& tB_hi,
+                        const CUtensorMap& tB_lo, int64_t M, int64_t N, float alpha, float* D, int64_t ldd, int symmetric,
+                        int total_kchunks, int kchunks_per_split, int splits, int store_mode, int fp16_operands,
+                        cudaStream_t st);
+
+// 256 x 256 CTA-pair tiles (gemm_tc2.cu) when both extents reach 256 and padding them to 256 wastes at most ~15 %
+// more area than padding to 128.  LPB_GEMM_PAIR=0 / 1 or lpb_set_gemm_tile_mode() forces the choice (tests, A/B timing).
+static int g_pair_mode = -2;   // -2: read LPB_GEMM_PAIR on first use; -1 auto; 0 never; 1 whenever M, N >= 256
+void set_gemm_pair_mode(int mode) { g_pair_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
+static bool use_pair_tiles(int64_t M, int64_t N) {
+  if (g_pair_mode == -2) {
+    const char* e = getenv("LPB_GEMM_PAIR");
+    g_pair_mode = e ? (atoi(e) ? 1 : 0) : -1;
+  }
+  if (M < 256 || N < 256) return false;
+  if (g_pair_mode >= 0) return g_pair_mode != 0;
+  const double a128 = (double)(ceil_div(M, 128) * 128) * (double)(ceil_div(N, 128) * 128);
+  const double a256 = (double)(ceil_div(M, 256) * 256) * (double)(ceil_div(N, 256) * 256);
+  return a256 <= 1.15 * a128;
+}
 
 int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
                  int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
@@ -245,8 +267,11 @@ static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, con
                   ((uintptr_t)B_lo % 16) == 0,
               "gemm_nt_bf16: operands must be 16-byte aligned");
   if (M == 0 || N == 0) return 0;
-  const int tiles_m = (int)ceil_div(M, tc::BM), tiles_n = (int)ceil_div(N, tc::BN);
-  const int64_t tiles = symmetric ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
+  const bool pair = use_pair_tiles(M, N);
+  const int tile_edge = pair ? 256 : tc::BM;
+  const int tiles_m = (int)ceil_div(M, tile_edge), tiles_n = (int)ceil_div(N, tile_edge);
+  // CTAs per split: one per 128 x 128 tile, or two per 256 x 256 pair tile
+  const int64_t tiles = (symmetric ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n) * (pair ? 2 : 1);
   const int total_kchunks = (int)ceil_div(K, tc::BK);
   const int sms = sm_count();
   // overwrite + enough tiles (or a short K): one split per tile with plain stores
@@ -282,6 +307,9 @@ static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, con
   const int num_stages = x3 ? 3 : 6;
   const size_t smem = (size_t)num_stages * stage_bytes + (2 * num_stages + 1) * sizeof(uint64_t) + 16 + 1024;
   LPB_REQUIRE(tiles <= 2147483647LL, "gemm_tc: too many tiles");
+  if (pair)
+    return launch_gemm_tc_pair(mn, x3, tA_hi, tA_lo, tB_hi, tB_lo, M, N, alpha, D, ldd, symmetric, total_kchunks,
+                               kchunks_per_split, (int)splits, store_mode ? 1 : 0, fp16_operands, st);
   dim3 grid((unsigned)tiles, (unsigned)splits);
 #define LPB_LAUNCH_TC(NP, MNV)                                                                                          \
   do {                                                                                                                  \

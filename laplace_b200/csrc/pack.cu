@@ -439,6 +439,62 @@ __global__ void __launch_bounds__(128) col2im_small_kernel(const float* __restri
   }
 }
 
+// col2im gather, channels-last form: Dc [(q,oh,ow), (kh,kw,ci)] (row stride ldd)  ->  grad_in [Q, H, W, C].
+// One thread per (q, h, w, 4 channels): the <= ceil(KH/SH) * ceil(KW/SW) taps that reach the pixel are read as float4
+// runs that are contiguous in ci, the store is contiguous in ci -- both sides coalesced, no shared memory.
+template <bool VEC>
+__global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float* __restrict__ Dc, int64_t ldd, ConvGeom g,
+                                                          float* __restrict__ out) {
+  constexpr int V = VEC ? 4 : 1;
+  const int cv = g.C / V;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)g.N * g.H * g.W * cv;
+  if (i >= total) return;
+  const int c = (int)(i % cv) * V;
+  int64_t pix = i / cv;
+  const int w = (int)(pix % g.W);
+  pix /= g.W;
+  const int h = (int)(pix % g.H);
+  const int64_t q = pix / g.H;
+  float acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = 0.f;
+  for (int kh = 0; kh < g.KH; ++kh) {
+    const int hn = h + g.PH - kh * g.DH;
+    if (hn < 0 || hn % g.SH) continue;
+    const int oh = hn / g.SH;
+    if (oh >= g.OH) continue;
+    for (int kw = 0; kw < g.KW; ++kw) {
+      const int wn = w + g.PW - kw * g.DW;
+      if (wn < 0 || wn % g.SW) continue;
+      const int ow = wn / g.SW;
+      if (ow >= g.OW) continue;
+      const float* src = Dc + ((q * g.OH + oh) * g.OW + ow) * ldd + (int64_t)(kh * g.KW + kw) * g.C + c;
+      if (VEC) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        acc[0] += t.x; acc[1 % V] += t.y; acc[2 % V] += t.z; acc[3 % V] += t.w;
+      } else {
+        acc[0] += __ldg(src);
+      }
+    }
+  }
+  float* dst = out + ((q * g.H + h) * g.W + w) * g.C + c;
+  if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+  else *dst = acc[0];
+}
+
+int col2im_nhwc(const float* Dc, int64_t ldd, const ConvGeom& g, float* out, cudaStream_t st) {
+  if ((int64_t)g.N * g.C * g.H * g.W == 0) return 0;
+  const bool vec = (g.C % 4 == 0) && (ldd % 4 == 0) && ((uintptr_t)Dc % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  const int64_t total = (int64_t)g.N * g.H * g.W * (vec ? g.C / 4 : g.C);
+  const int64_t blocks = ceil_div(total, 256);
+  LPB_REQUIRE(blocks < (1LL << 31), "col2im_nhwc: too many elements");
+  if (vec) col2im_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(Dc, ldd, g, out);
+  else col2im_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(Dc, ldd, g, out);
+  LPB_CHECK_LAUNCH("col2im_nhwc");
+  return 0;
+}
+
 int col2im(const float* Dc, int64_t ldd, const ConvGeom& g, float* out, cudaStream_t st) {
   const int64_t per_c = (int64_t)g.N * g.H * g.W;
   if (per_c == 0) return 0;

@@ -77,6 +77,11 @@ def device_info():
     return sm.value, maj.value, mnr.value
 
 
+def set_gemm_tile_mode(mode: int) -> None:
+    """-1 automatic, 0 128x128 single-CTA tiles only, 1 256x256 CTA-pair tiles whenever M, N >= 256."""
+    _lib.call("lpb_set_gemm_tile_mode", int(mode))
+
+
 # ------------------------------------------------------------------------------ pack
 def pack_rows(src: torch.Tensor, kind: int, out: Packed | None = None, k0: int = 0, scale: float = 1.0,
               square: bool = False, row_scale: torch.Tensor | None = None, nrep: int = 1, total_K: int | None = None) -> Packed:
@@ -300,6 +305,17 @@ def col2im(Dc: torch.Tensor, in_shape, mod) -> torch.Tensor:
     return out
 
 
+def col2im_nhwc(Dc: torch.Tensor, in_shape, mod) -> torch.Tensor:
+    """``Dc [Q*OH*OW, kh*kw*C_in]`` (tap-major columns) -> ``grad_in [Q, C_in, H, W]`` as a channels-last view."""
+    _check(Dc, name="Dc")
+    assert Dc.dim() == 2 and Dc.stride(1) == 1
+    Q, Cin, H, W = in_shape
+    out = torch.empty(Q, H, W, Cin, device=Dc.device, dtype=torch.float32)
+    _lib.call("lpb_col2im_nhwc", _ptr(Dc), Dc.stride(0), *_conv_args(in_shape, mod), _ptr(out), _stream())
+    _bump()
+    return out.permute(0, 3, 1, 2)
+
+
 def conv_nhwc(X: Packed, Q: int, H: int, W: int, Wt: Packed, N: int, KH: int, KW: int, base_h: int, base_w: int, sgn: int,
               out: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
     """Implicit-GEMM stride-1 convolution on NHWC bf16(hi/lo) rows ``X [(q,h,w), Kc]`` with tap-major weights
@@ -355,8 +371,18 @@ def relu_bwd(g: torch.Tensor, y: torch.Tensor, reps: int) -> torch.Tensor:
 
 
 def maxpool2d_bwd(g: torch.Tensor, idx: torch.Tensor, in_shape, k: int, s: int, p: int) -> torch.Tensor:
-    """``g [Q, C, OH, OW]``, ``idx [Nb, C, OH, OW]`` int64 argmax -> ``[Q, C, H, W]`` (all NCHW-contiguous)."""
+    """``g [Q, C, OH, OW]``, ``idx [Nb, C, OH, OW]`` int64 argmax -> ``[Q, C, H, W]``.  Channels-last ``g`` and ``idx``
+    stay channels-last (no layout copies); anything else goes through the NCHW kernel."""
     _check(g, name="g")
+    Q, C, OH, OW = g.shape
+    H, W = in_shape[-2:]
+    cl = torch.channels_last
+    if C > 1 and g.is_contiguous(memory_format=cl) and idx.is_contiguous(memory_format=cl) and not g.is_contiguous():
+        out = torch.empty(Q, H, W, C, device=g.device, dtype=torch.float32)
+        _lib.call("lpb_maxpool2d_bwd_nhwc", _ptr(g), _ptr(idx), _ptr(out), Q, idx.shape[0], C, H, W, OH, OW, k, s, p,
+                  _stream())
+        _bump()
+        return out.permute(0, 3, 1, 2)
     g = g.contiguous()
     idx = idx.contiguous()
     Q, C, OH, OW = g.shape

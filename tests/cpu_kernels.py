@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "col2im_nhwc", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -204,6 +204,15 @@ def col2im(Dc, in_shape, mod):
     OH, OW = K.conv_out_hw(in_shape, mod)
     cols = Dc[:, :Q * OH * OW].reshape(Dc.shape[0], Q, OH * OW).permute(1, 0, 2)
     return F.fold(cols, (H, W), mod.kernel_size, dilation=mod.dilation, padding=mod.padding, stride=mod.stride)
+
+
+def col2im_nhwc(Dc, in_shape, mod):
+    Q, C, H, W = in_shape
+    OH, OW = K.conv_out_hw(in_shape, mod)
+    kh, kw = mod.kernel_size
+    cols = Dc[:, :kh * kw * C].reshape(Q, OH * OW, kh * kw, C).permute(0, 3, 2, 1).reshape(Q, C * kh * kw, OH * OW)
+    out = F.fold(cols, (H, W), mod.kernel_size, dilation=mod.dilation, padding=mod.padding, stride=mod.stride)
+    return out.contiguous(memory_format=torch.channels_last)
 
 
 def conv_nhwc(X, Q, H, W, Wt, N, KH, KW, base_h, base_w, sgn, out, alpha=1.0):
@@ -249,4 +258,6 @@ def maxpool2d_bwd(g, idx, in_shape, k, s, p):
     out = torch.zeros(Q, C, H * W)
     ii = idx.reshape(Nb, C, OH * OW).repeat(Q // Nb, 1, 1)
     out.scatter_add_(2, ii, g.reshape(Q, C, OH * OW).float())
-    return out.reshape(Q, C, H, W)
+    out = out.reshape(Q, C, H, W)
+    # the native wrapper keeps channels-last gradients channels-last
+    return out.contiguous(memory_format=torch.channels_last) if not g.is_contiguous() else out

@@ -47,6 +47,11 @@ def test_engine_operand_kernels(geom):
     refc = ck.col2im(Dc, (9, cin, hw, hw), mod)
     outc = K.col2im(Dc.to(DEV), (9, cin, hw, hw), mod)
     assert rel_fro(outc.cpu(), refc) < 1e-6
+    # channels-last form: rows (q,t), tap-major columns (kh,kw,ci)
+    Dn = Dc.reshape(cin, k * k, 9, T).permute(2, 3, 1, 0).reshape(9 * T, k * k * cin).contiguous()
+    outn = K.col2im_nhwc(Dn.to(DEV), (9, cin, hw, hw), mod)
+    assert outn.shape == refc.shape and outn.permute(0, 2, 3, 1).is_contiguous()
+    assert rel_fro(outn.cpu(), refc) < 1e-6
 
 
 @pytest.mark.parametrize("geom", GEOMS)
@@ -64,6 +69,8 @@ def test_conv_forward_backward_vs_fp64(geom):
     gref = torch.nn.grad.conv2d_input((65, cin, hw, hw), mod.weight.double(), g.double(), s, p, d)
     gin = conv_engine.conv_backward_data(g, mod, (65, cin, hw, hw))
     assert gin.shape == gref.shape and rel_fro(gin, gref) < 2e-5
+    gin_cl = conv_engine.conv_backward_data(g.contiguous(memory_format=torch.channels_last), mod, (65, cin, hw, hw))
+    assert rel_fro(gin_cl, gref) < 2e-5
 
 
 def test_store_mode_gemm_nonsymmetric():

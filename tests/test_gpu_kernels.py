@@ -252,3 +252,51 @@ def test_maxpool_backward_kernel(geom):
     ref = torch.stack([torch.autograd.grad(out, x, g[i * 4:(i + 1) * 4], retain_graph=True)[0] for i in range(3)]).reshape(12, 6, hw, hw)
     got = K.maxpool2d_bwd(g, idx, x.shape, k, s, p)
     assert torch.allclose(got, ref, atol=1e-6)
+    # channels-last operands take the NHWC kernel and stay channels-last
+    cl = torch.channels_last
+    xc = x.detach().contiguous(memory_format=cl).requires_grad_(True)
+    outc, idxc = torch.nn.functional.max_pool2d(xc, k, s, p, return_indices=True)
+    assert torch.equal(idxc, idx)
+    gotc = K.maxpool2d_bwd(g.contiguous(memory_format=cl), idxc.contiguous(memory_format=cl), x.shape, k, s, p)
+    assert gotc.is_contiguous(memory_format=cl) and torch.allclose(gotc, ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("M,N,Kc", [(256, 256, 64), (256, 256, 4096), (513, 257, 2048), (300, 300, 40000), (1000, 1000, 512),
+                                    (1152, 1152, 3000), (640, 2000, 130)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 1e-5)])
+@pytest.mark.parametrize("rows", [False, True])
+def test_gemm_cta_pair_tiles(M, N, Kc, kind, tol, rows):
+    """256 x 256 CTA-pair tiles (tcgen05 cta_group::2), K-major and row (MN-major) operands, forced on for every
+    shape with M, N >= 256: same results as fp64 and as the single-CTA tiling, including ragged edges, split-K
+    accumulation, overwrite mode and the mirrored SYRK."""
+    torch.manual_seed(11)
+    A, B = torch.randn(M, Kc), torch.randn(N, Kc)
+    ref = A.double() @ B.double().t()
+    if rows:
+        pa, pb = K.pack_cast(A.t().contiguous().to(DEV), kind), K.pack_cast(B.t().contiguous().to(DEV), kind)
+        gemm = K.gemm_tn
+    else:
+        pa, pb = K.pack_rows(A.t().contiguous().to(DEV), kind), K.pack_rows(B.t().contiguous().to(DEV), kind)
+        gemm = K.gemm_nt
+    try:
+        K.set_gemm_tile_mode(1)
+        out = torch.zeros(M, N, device=DEV)
+        gemm(pa, pb, out, alpha=2.0, accumulate=True)
+        gemm(pa, pb, out, alpha=-1.0, accumulate=True)
+        assert rel_fro(out.cpu(), ref) < tol
+        out.fill_(7.0)
+        gemm(pa, pb, out, alpha=1.0, accumulate=False)
+        assert rel_fro(out.cpu(), ref) < tol
+        K.set_gemm_tile_mode(0)
+        single = torch.zeros(M, N, device=DEV)
+        gemm(pa, pb, single, alpha=1.0, accumulate=False)
+        assert rel_fro(out, single) < (1e-3 if kind == K.BF16 else 2e-5)
+        if M == N:
+            K.set_gemm_tile_mode(1)
+            sym = torch.zeros(M, M, device=DEV)
+            gemm(pa, pa, sym, alpha=1.0, accumulate=True, symmetric=True)
+            assert rel_fro(sym.cpu(), A.double() @ A.double().t()) < tol
+            assert rel_fro(sym, sym.t()) < 1e-5
+            assert (sym.diagonal() >= 0).all()
+    finally:
+        K.set_gemm_tile_mode(-1)
