@@ -38,8 +38,9 @@ int lpb_version(void);
 const char* lpb_last_error(void);
 /* sm count / compute capability of the current device */
 int lpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* Tile shape of lpb_gemm_nt_tc / lpb_gemm_tn_tc: -1 automatic (default), 0 always 128 x 128 single-CTA tiles,
- * 1 256 x 256 CTA-pair tiles (tcgen05 cta_group::2) whenever M, N >= 256.  Results agree to fp32 rounding. */
+/* Schedule of lpb_gemm_nt_tc / lpb_gemm_tn_tc: -1 automatic (default), 0 one 128 x 128 tile per CTA,
+ * 1 256 x 256 CTA-pair tiles (tcgen05 cta_group::2) whenever M, N >= 256, 2 persistent CTAs with double-buffered
+ * TMEM accumulators.  Results agree to fp32 rounding. */
 int lpb_set_gemm_tile_mode(int mode);
 
 /* ---- pack: layer inputs / output gradients -> K-major staging ----------------------------

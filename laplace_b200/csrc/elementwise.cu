@@ -124,44 +124,59 @@ __global__ void maxpool2d_bwd_kernel(const float* __restrict__ g, const int64_t*
 }
 
 // Channels-last form of the same reverse pass: g [Q, OH, OW, C], argmax map [Nb, OH, OW, C] (values h * W + w),
-// out [Q, H, W, C].  One thread per (n, h, w, c); consecutive threads walk the channels, so the argmax loads, the
-// gradient loads and the stores are all coalesced; window membership is evaluated once and reused by every column.
-template <int NC>
+// out [Q, H, W, C].  One thread per (n, h, w, V channels), V = 4 when C % 4 == 0: consecutive threads walk the
+// channels, so the argmax loads, the gradient loads (float4) and the stores (float4) are all coalesced; window
+// membership is evaluated once and reused by every column.  32-bit index arithmetic (64-bit runtime divisions made an
+// earlier version ALU-bound at 1.5 TB/s).
+template <int NC, int V>
 __global__ void __launch_bounds__(256) maxpool2d_bwd_nhwc_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx,
                                                                  float* __restrict__ out, int cols, int Nb, int C, int H,
                                                                  int W, int OH, int OW, int k, int s, int p) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per_col = (int64_t)Nb * H * W * C;
-  if (i >= per_col) return;
-  const int c = (int)(i % C);
-  int64_t pix = i / C;
-  const int w = (int)(pix % W);
-  pix /= W;
-  const int h = (int)(pix % H);
-  const int64_t n = pix / H;
+  const uint32_t cv = (uint32_t)C / V;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = (uint32_t)Nb * H * W * cv;
+  if (i >= total) return;
+  const uint32_t c = (i % cv) * V;
+  uint32_t pix = i / cv;
+  const int w = (int)(pix % (uint32_t)W);
+  pix /= (uint32_t)W;
+  const int h = (int)(pix % (uint32_t)H);
+  const uint32_t n = pix / (uint32_t)H;
   const int me = h * W + w;
   const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
   const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
-  int64_t tpos[NC * NC];
-  float sel[NC * NC];
+  uint32_t tpos[NC * NC];
+  float sel[NC * NC][V];
 #pragma unroll
   for (int a = 0; a < NC; ++a)
 #pragma unroll
     for (int b = 0; b < NC; ++b) {
       const int oh = oh_lo + a, ow = ow_lo + b;
       const bool in = oh <= oh_hi && ow <= ow_hi;
-      const int64_t t = in ? ((n * OH + oh) * OW + ow) * C + c : (n * OH * OW) * C + c;
+      const uint32_t t = ((n * OH + (in ? oh : 0)) * OW + (in ? ow : 0)) * C + c;   // < Nb*OH*OW*C <= total
       tpos[a * NC + b] = t;
-      sel[a * NC + b] = (in && (int)__ldg(idx + t) == me) ? 1.f : 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) sel[a * NC + b][v] = (in && (int)__ldg(idx + t + v) == me) ? 1.f : 0.f;
     }
-  const int64_t gstride = (int64_t)Nb * OH * OW * C;
-  float* op = out + i;
+  const int64_t gstride = (int64_t)Nb * OH * OW * C, per_col = (int64_t)Nb * H * W * C;
+  float* op = out + (int64_t)i * V;
 #pragma unroll 2
   for (int col = 0; col < cols; ++col) {
-    float acc = 0.f;
+    float acc[V];
 #pragma unroll
-    for (int j = 0; j < NC * NC; ++j) acc = fmaf(sel[j], __ldg(g + tpos[j]), acc);
-    *op = acc;
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC * NC; ++j) {
+      if (V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(g + tpos[j]));
+        acc[0] = fmaf(sel[j][0], t.x, acc[0]); acc[1 % V] = fmaf(sel[j][1 % V], t.y, acc[1 % V]);
+        acc[2 % V] = fmaf(sel[j][2 % V], t.z, acc[2 % V]); acc[3 % V] = fmaf(sel[j][3 % V], t.w, acc[3 % V]);
+      } else {
+        acc[0] = fmaf(sel[j][0], __ldg(g + tpos[j]), acc[0]);
+      }
+    }
+    if (V == 4) *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+    else *op = acc[0];
     g += gstride;
     op += per_col;
   }
@@ -174,13 +189,20 @@ int maxpool2d_bwd_nhwc(const float* g, const int64_t* idx, float* out, int64_t Q
   LPB_REQUIRE(Q % Nb == 0, "maxpool2d_bwd_nhwc: Q must be a multiple of the argmax batch Nb");
   const int nc = (k + s - 1) / s;
   LPB_REQUIRE(nc <= 3, "maxpool2d_bwd_nhwc: kernel_size > 3 * stride is not supported");
+  LPB_REQUIRE(OH <= H && OW <= W, "maxpool2d_bwd_nhwc: output larger than input");
+  const bool vec = (C % 4 == 0) && ((uintptr_t)g % 16 == 0) && ((uintptr_t)out % 16 == 0);
   const int64_t per_col = (int64_t)Nb * H * W * C;
-  const int64_t blocks = ceil_div(per_col, 256);
-  LPB_REQUIRE(blocks < (1LL << 31), "maxpool2d_bwd_nhwc: too many elements");
+  LPB_REQUIRE(per_col < (1LL << 31), "maxpool2d_bwd_nhwc: argmax batch too large for 32-bit indexing");
+  const int64_t blocks = ceil_div(vec ? per_col / 4 : per_col, 256);
   const int cols = (int)(Q / Nb);
-  if (nc <= 1) maxpool2d_bwd_nhwc_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(g, idx, out, cols, Nb, C, H, W, OH, OW, k, s, p);
-  else if (nc == 2) maxpool2d_bwd_nhwc_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(g, idx, out, cols, Nb, C, H, W, OH, OW, k, s, p);
-  else maxpool2d_bwd_nhwc_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(g, idx, out, cols, Nb, C, H, W, OH, OW, k, s, p);
+#define LPB_POOL(NCV, VV) \
+  maxpool2d_bwd_nhwc_kernel<NCV, VV><<<(unsigned)blocks, 256, 0, st>>>(g, idx, out, cols, Nb, C, H, W, OH, OW, k, s, p)
+  if (vec) {
+    if (nc <= 1) LPB_POOL(1, 4); else if (nc == 2) LPB_POOL(2, 4); else LPB_POOL(3, 4);
+  } else {
+    if (nc <= 1) LPB_POOL(1, 1); else if (nc == 2) LPB_POOL(2, 1); else LPB_POOL(3, 1);
+  }
+#undef LPB_POOL
   LPB_CHECK_LAUNCH("maxpool2d_bwd_nhwc");
   return 0;
 }

@@ -231,16 +231,30 @@ int launch_gemm_tc_pair(bool mn, bool x3, const CUtensorMap& tA_hi, const CUtens
                         cudaStream_t st);
 
 // 256 x 256 CTA-pair tiles (gemm_tc2.cu) when both extents reach 256 and padding them to 256 wastes at most ~15 %
-// more area than padding to 128.  LPB_GEMM_PAIR=0 / 1 or lpb_set_gemm_tile_mode() forces the choice (tests, A/B timing).
-static int g_pair_mode = -2;   // -2: read LPB_GEMM_PAIR on first use; -1 auto; 0 never; 1 whenever M, N >= 256
-void set_gemm_pair_mode(int mode) { g_pair_mode = mode < 0 ? -1 : (mode ? 1 : 0); }
-static bool use_pair_tiles(int64_t M, int64_t N) {
+// more area than padding to 128.  LPB_GEMM_MODE or lpb_set_gemm_tile_mode() forces the choice (tests, A/B timing).
+void persistent_schedule(int64_t tiles, int total_kchunks, int ctas, bool allow_single_store, int* kchunks_per_split,
+                         int* splits, bool* single);
+int launch_gemm_tc_persistent(bool mn, bool x3, const CUtensorMap& tA_hi, const CUtensorMap& tA_lo, const CUtensorMap& tB_hi,
+                              const CUtensorMap& tB_lo, int64_t M, int64_t N, float alpha, float* D, int64_t ldd,
+                              int symmetric, int tiles_m, int tiles_n, int64_t num_tiles, int total_kchunks,
+                              int kchunks_per_split, int splits, int store_mode, int fp16_operands, int ctas,
+                              cudaStream_t st);
+
+// -2: read LPB_GEMM_MODE on first use; -1 auto; 0 one 128x128 tile per CTA; 1 CTA-pair tiles whenever M, N >= 256;
+// 2 persistent CTAs with double-buffered TMEM (gemm_tc3.cu)
+static int g_pair_mode = -2;
+void set_gemm_pair_mode(int mode) { g_pair_mode = mode < 0 ? -1 : imin(mode, 2); }
+static int gemm_mode() {
   if (g_pair_mode == -2) {
-    const char* e = getenv("LPB_GEMM_PAIR");
-    g_pair_mode = e ? (atoi(e) ? 1 : 0) : -1;
+    const char* e = getenv("LPB_GEMM_MODE");
+    g_pair_mode = e ? (int)imin(imax(atoi(e), -1), 2) : -1;
   }
-  if (M < 256 || N < 256) return false;
-  if (g_pair_mode >= 0) return g_pair_mode != 0;
+  return g_pair_mode;
+}
+static bool use_pair_tiles(int64_t M, int64_t N) {
+  const int mode = gemm_mode();
+  if (M < 256 || N < 256 || mode == 2) return false;
+  if (mode >= 0) return mode == 1;
   const double a128 = (double)(ceil_div(M, 128) * 128) * (double)(ceil_div(N, 128) * 128);
   const double a256 = (double)(ceil_div(M, 256) * 256) * (double)(ceil_div(N, 256) * 256);
   return a256 <= 1.15 * a128;
@@ -274,6 +288,28 @@ static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, con
   const int64_t tiles = (symmetric ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n) * (pair ? 2 : 1);
   const int total_kchunks = (int)ceil_div(K, tc::BK);
   const int sms = sm_count();
+  if (gemm_mode() == 2 && K > 0) {
+    int kps = 0, nsplit = 1;
+    bool single = false;
+    persistent_schedule(tiles, total_kchunks, sms, !accumulate && !symmetric, &kps, &nsplit, &single);
+    const bool store = !accumulate && !symmetric && single;
+    if (!accumulate && !store &&
+        check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, N * sizeof(float), M, st), "gemm_tc memset"))
+      return 1;
+    const bool x3p = A_lo != nullptr;
+    CUtensorMap pA_hi, pA_lo, pB_hi, pB_lo;
+    auto mk = [&](CUtensorMap* m, const void* p, int64_t feat, int64_t ld) {
+      return mn ? make_tmap_rows(m, p, K, feat, ld) : make_tmap_2d(m, p, feat, K, ld);
+    };
+    if (mk(&pA_hi, A_hi, M, lda) || mk(&pB_hi, B_hi, N, ldb)) return 1;
+    if (x3p) {
+      if (mk(&pA_lo, A_lo, M, lda) || mk(&pB_lo, B_lo, N, ldb)) return 1;
+    } else {
+      pA_lo = pA_hi; pB_lo = pB_hi;
+    }
+    return launch_gemm_tc_persistent(mn, x3p, pA_hi, pA_lo, pB_hi, pB_lo, M, N, alpha, D, ldd, symmetric, tiles_m, tiles_n,
+                                     tiles, total_kchunks, kps, nsplit, store ? 1 : 0, fp16_operands, sms, st);
+  }
   // overwrite + enough tiles (or a short K): one split per tile with plain stores
   const bool store_mode = !accumulate && !symmetric && K > 0 && (tiles >= sms / 2 || total_kchunks <= 16) && total_kchunks <= 128;
   if (!accumulate && !store_mode) {

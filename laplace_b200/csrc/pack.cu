@@ -446,16 +446,17 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float* __restrict__ Dc, int64_t ldd, ConvGeom g,
                                                           float* __restrict__ out) {
   constexpr int V = VEC ? 4 : 1;
-  const int cv = g.C / V;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)g.N * g.H * g.W * cv;
+  // 32-bit index arithmetic (the host checks N*H*W*C < 2^31); only the final addresses are 64-bit
+  const uint32_t cv = (uint32_t)g.C / V;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t total = (uint32_t)g.N * g.H * g.W * cv;
   if (i >= total) return;
   const int c = (int)(i % cv) * V;
-  int64_t pix = i / cv;
-  const int w = (int)(pix % g.W);
-  pix /= g.W;
-  const int h = (int)(pix % g.H);
-  const int64_t q = pix / g.H;
+  uint32_t pix = i / cv;
+  const int w = (int)(pix % (uint32_t)g.W);
+  pix /= (uint32_t)g.W;
+  const int h = (int)(pix % (uint32_t)g.H);
+  const uint32_t q = pix / (uint32_t)g.H;
   float acc[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = 0.f;
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float* __restric
       if (wn < 0 || wn % g.SW) continue;
       const int ow = wn / g.SW;
       if (ow >= g.OW) continue;
-      const float* src = Dc + ((q * g.OH + oh) * g.OW + ow) * ldd + (int64_t)(kh * g.KW + kw) * g.C + c;
+      const float* src = Dc + (int64_t)((q * g.OH + oh) * g.OW + ow) * ldd + (kh * g.KW + kw) * g.C + c;
       if (VEC) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(src));
         acc[0] += t.x; acc[1 % V] += t.y; acc[2 % V] += t.z; acc[3 % V] += t.w;
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const float* __restric
       }
     }
   }
-  float* dst = out + ((q * g.H + h) * g.W + w) * g.C + c;
+  float* dst = out + (int64_t)i * V;   // i enumerates (q, h, w, c / V) in memory order
   if (VEC) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
   else *dst = acc[0];
 }
@@ -488,7 +489,8 @@ int col2im_nhwc(const float* Dc, int64_t ldd, const ConvGeom& g, float* out, cud
   const bool vec = (g.C % 4 == 0) && (ldd % 4 == 0) && ((uintptr_t)Dc % 16 == 0) && ((uintptr_t)out % 16 == 0);
   const int64_t total = (int64_t)g.N * g.H * g.W * (vec ? g.C / 4 : g.C);
   const int64_t blocks = ceil_div(total, 256);
-  LPB_REQUIRE(blocks < (1LL << 31), "col2im_nhwc: too many elements");
+  LPB_REQUIRE((int64_t)g.N * g.H * g.W * g.C < (1LL << 31) && (int64_t)g.N * g.OH * g.OW < (1LL << 31),
+              "col2im_nhwc: batch too large for 32-bit indexing");
   if (vec) col2im_nhwc_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(Dc, ldd, g, out);
   else col2im_nhwc_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(Dc, ldd, g, out);
   LPB_CHECK_LAUNCH("col2im_nhwc");

@@ -78,7 +78,7 @@ def device_info():
 
 
 def set_gemm_tile_mode(mode: int) -> None:
-    """-1 automatic, 0 128x128 single-CTA tiles only, 1 256x256 CTA-pair tiles whenever M, N >= 256."""
+    """-1 automatic, 0 one 128x128 tile per CTA, 1 256x256 CTA-pair tiles whenever M, N >= 256, 2 persistent CTAs."""
     _lib.call("lpb_set_gemm_tile_mode", int(mode))
 
 

@@ -262,13 +262,14 @@ def test_maxpool_backward_kernel(geom):
 
 
 @pytest.mark.parametrize("M,N,Kc", [(256, 256, 64), (256, 256, 4096), (513, 257, 2048), (300, 300, 40000), (1000, 1000, 512),
-                                    (1152, 1152, 3000), (640, 2000, 130)])
+                                    (1152, 1152, 3000), (640, 2000, 130), (64, 64, 300000)])
 @pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 1e-5)])
 @pytest.mark.parametrize("rows", [False, True])
-def test_gemm_cta_pair_tiles(M, N, Kc, kind, tol, rows):
-    """256 x 256 CTA-pair tiles (tcgen05 cta_group::2), K-major and row (MN-major) operands, forced on for every
-    shape with M, N >= 256: same results as fp64 and as the single-CTA tiling, including ragged edges, split-K
-    accumulation, overwrite mode and the mirrored SYRK."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gemm_cta_pair_tiles(M, N, Kc, kind, tol, rows, mode):
+    """Alternative schedules of the tensor-core contraction -- 256 x 256 CTA-pair tiles (tcgen05 cta_group::2) and
+    persistent CTAs with double-buffered TMEM -- on K-major and row (MN-major) operands: same results as fp64 and as
+    the one-tile-per-CTA kernel, including ragged edges, split-K accumulation, overwrite mode and the mirrored SYRK."""
     torch.manual_seed(11)
     A, B = torch.randn(M, Kc), torch.randn(N, Kc)
     ref = A.double() @ B.double().t()
@@ -279,7 +280,7 @@ def test_gemm_cta_pair_tiles(M, N, Kc, kind, tol, rows):
         pa, pb = K.pack_rows(A.t().contiguous().to(DEV), kind), K.pack_rows(B.t().contiguous().to(DEV), kind)
         gemm = K.gemm_nt
     try:
-        K.set_gemm_tile_mode(1)
+        K.set_gemm_tile_mode(mode)
         out = torch.zeros(M, N, device=DEV)
         gemm(pa, pb, out, alpha=2.0, accumulate=True)
         gemm(pa, pb, out, alpha=-1.0, accumulate=True)
@@ -292,7 +293,7 @@ def test_gemm_cta_pair_tiles(M, N, Kc, kind, tol, rows):
         gemm(pa, pb, single, alpha=1.0, accumulate=False)
         assert rel_fro(out, single) < (1e-3 if kind == K.BF16 else 2e-5)
         if M == N:
-            K.set_gemm_tile_mode(1)
+            K.set_gemm_tile_mode(mode)
             sym = torch.zeros(M, M, device=DEV)
             gemm(pa, pa, sym, alpha=1.0, accumulate=True, symmetric=True)
             assert rel_fro(sym.cpu(), A.double() @ A.double().t()) < tol
