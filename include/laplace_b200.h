@@ -117,6 +117,18 @@ int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W
                      const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
                      float* D, int64_t ldd, int fp16_operands, void* stream);
 
+/* ---- KFAC input factor of a stride-1 'same' convolution without im2col -----------------------------------------
+ * D[(t,ci),(t',cj)] (+)= alpha * sum_{n,h,w} x[n,h+kh-PH,w+kw-PW,ci] * x[n,h+kh'-PH,w+kw'-PW,cj]   (zero padding),
+ * t = kh*KW + kw (tap-major feature order, d = KH*KW*Ci), x given as 16-bit hi(/lo) NHWC rows [(n,h,w), Ci] (ldx).
+ * Replaces unfold + einsum("b t i, b t j -> i j") behind reference laplace/curvature/curvlinops.py:100 for those
+ * layers; the 9x larger patch matrix is never formed (shifted 4-D TMA boxes feed the tensor cores directly).
+ * Needs Ci % 64 == 0, H*W dividing 64 or (W | 64 and 64/W | H).  D is symmetric (both triangles written).      */
+int lpb_syrk_conv_patches_tc(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q, int H, int W, int Ci, int KH, int KW,
+                             int PH, int PW, float alpha, int accumulate, float* D, int64_t ldd, int fp16_operands,
+                             void* stream);
+/* out[(ci*KK+t), (cj*KK+t')] += T[(t*Ci+ci), (t'*Ci+cj)]: tap-major factor -> parameter order (ci,kh,kw), KK <= 9 */
+int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int KK, float* out, int64_t ldo, void* stream);
+
 /* ---- reverse-pass element-wise maps of the convolution engine (columns folded into the batch) -----------------
  * out[i] = g[i] * scale[(i / inner) % C]                 frozen BatchNorm as per-channel affine map (backward)   */
 int lpb_scale_channels(const float* g, const float* scale, float* out, int64_t n, int C, int64_t inner, void* stream);

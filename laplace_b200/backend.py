@@ -344,14 +344,24 @@ class _B200Mixin:
             if L.has_w:
                 Bf, Af = kron.kfacs[idx]
                 Prows = rows.get("P")
-                if Prows is None and L.is_conv and stash is not None and len(stash) > 0:
+                Xs = rows.get("X")
+                a_done = False
+                if (Xs is not None and Xs[1] == M
+                        and K.conv_patches_ok(Xs[0].K, Xs[2], Xs[3], *L.mod.kernel_size)):
+                    # implicit-path convolution: the A factor straight from the NHWC input rows the forward packed
+                    X, _, Hh, Ww = Xs
+                    K.syrk_conv_patches(X, M, Hh, Ww, L.mod, Af, alpha=sq / (N * Hh * Ww))
+                    a_done = True
+                elif Prows is None and L.is_conv and stash is not None and len(stash) > 0:
                     # implicit-path convolution: build the patch rows once (row-major pack is ~2x cheaper than the
                     # transposing K-major one) and contract them with the MN-major SYRK
                     af = a.float() if a.dtype != torch.float32 else a
                     Prows = K.pack_conv_rows(af, L.mod, K.BF16X3)
                 if Prows is not None and Prows.rows % M != 0:
                     Prows = None
-                if Prows is not None:
+                if a_done:
+                    pass
+                elif Prows is not None:
                     T = Prows.rows // M
                     K.gemm_tn(Prows, Prows, Af, alpha=sq / (N * T), accumulate=True, symmetric=True)
                 else:

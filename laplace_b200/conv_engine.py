@@ -97,6 +97,9 @@ def _implicit(x: torch.Tensor, mod: nn.Conv2d, which: str, n_out: int, sgn: int,
     kh, kw = mod.kernel_size
     if X is None:
         X = nhwc_rows(x, KIND_FWD if sgn > 0 else KIND)
+    if sgn > 0:
+        # forward: the packed NHWC input rows double as the operand of the implicit A-factor SYRK (no im2col at all)
+        STASH.setdefault(id(mod), {})["X"] = (X, N, H, W)
     Wt = _CACHE.get(mod, which)
     out = torch.empty(N * H * W, n_out, device=x.device, dtype=torch.float32)
     ph, pw = mod.padding

@@ -60,6 +60,9 @@ int ll_sigma_gather(const float*, int, int, int, float*, cudaStream_t);
 int eigh_jacobi(const float*, int, int, float*, float*, int, cudaStream_t);
 
 void set_gemm_pair_mode(int mode);
+int syrk_conv_patches(const void*, const void*, int64_t, int64_t, int, int, int, int, int, int, int, float, int, float*, int64_t,
+                      int, cudaStream_t);
+int taps_to_param_accumulate(const float*, int64_t, int, int, float*, int64_t, cudaStream_t);
 int col2im_nhwc(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
 int maxpool2d_bwd_nhwc(const float*, const int64_t*, float*, int64_t, int, int, int, int, int, int, int, int, int, cudaStream_t);
 }  // namespace lpb
@@ -160,6 +163,18 @@ int lpb_col2im(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH,
   if (make_geom(g, Q, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW)) return 1;
   LPB_REQUIRE(ldd >= (int64_t)Q * g.OH * g.OW, "lpb_col2im: ldd too small");
   return lpb::col2im(Dc, ldd, g, grad_in, ST(stream));
+}
+
+int lpb_syrk_conv_patches_tc(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q, int H, int W, int Ci, int KH, int KW,
+                             int PH, int PW, float alpha, int accumulate, float* D, int64_t ldd, int fp16_operands,
+                             void* stream) {
+  return lpb::syrk_conv_patches(X_hi, X_lo, ldx, Q, H, W, Ci, KH, KW, PH, PW, alpha, accumulate, D, ldd, fp16_operands,
+                                ST(stream));
+}
+
+int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int KK, float* out, int64_t ldo, void* stream) {
+  LPB_REQUIRE(ldt >= (int64_t)Ci * KK && ldo >= (int64_t)Ci * KK, "lpb_taps_to_param_accumulate: leading dimension too small");
+  return lpb::taps_to_param_accumulate(T, ldt, Ci, KK, out, ldo, ST(stream));
 }
 
 int lpb_col2im_nhwc(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,

@@ -230,15 +230,16 @@ int launch_gemm_tc_pair(bool mn, bool x3, const CUtensorMap& tA_hi, const CUtens
                         int total_kchunks, int kchunks_per_split, int splits, int store_mode, int fp16_operands,
                         cudaStream_t st);
 
-// 256 x 256 CTA-pair tiles (gemm_tc2.cu) when both extents reach 256 and padding them to 256 wastes at most ~15 %
-// more area than padding to 128.  LPB_GEMM_MODE or lpb_set_gemm_tile_mode() forces the choice (tests, A/B timing).
+// Schedules: persistent CTAs with double-buffered TMEM (gemm_tc3.cu) by default -- measured 10-40 % faster than one
+// tile per CTA on every factor shape of the benchmark; 128 x 128 one-tile CTAs (this file) and 256 x 256 CTA-pair
+// tiles (gemm_tc2.cu) stay selectable through LPB_GEMM_MODE / lpb_set_gemm_tile_mode() for tests and A/B timing.
 void persistent_schedule(int64_t tiles, int total_kchunks, int ctas, bool allow_single_store, int* kchunks_per_split,
                          int* splits, bool* single);
 int launch_gemm_tc_persistent(bool mn, bool x3, const CUtensorMap& tA_hi, const CUtensorMap& tA_lo, const CUtensorMap& tB_hi,
                               const CUtensorMap& tB_lo, int64_t M, int64_t N, float alpha, float* D, int64_t ldd,
                               int symmetric, int tiles_m, int tiles_n, int64_t num_tiles, int total_kchunks,
                               int kchunks_per_split, int splits, int store_mode, int fp16_operands, int ctas,
-                              cudaStream_t st);
+                              cudaStream_t st, const tc::PatchGeom* patches);
 
 // -2: read LPB_GEMM_MODE on first use; -1 auto; 0 one 128x128 tile per CTA; 1 CTA-pair tiles whenever M, N >= 256;
 // 2 persistent CTAs with double-buffered TMEM (gemm_tc3.cu)
@@ -251,14 +252,7 @@ static int gemm_mode() {
   }
   return g_pair_mode;
 }
-static bool use_pair_tiles(int64_t M, int64_t N) {
-  const int mode = gemm_mode();
-  if (M < 256 || N < 256 || mode == 2) return false;
-  if (mode >= 0) return mode == 1;
-  const double a128 = (double)(ceil_div(M, 128) * 128) * (double)(ceil_div(N, 128) * 128);
-  const double a256 = (double)(ceil_div(M, 256) * 256) * (double)(ceil_div(N, 256) * 256);
-  return a256 <= 1.15 * a128;
-}
+static bool use_pair_tiles(int64_t M, int64_t N) { return gemm_mode() == 1 && M >= 256 && N >= 256; }
 
 int gemm_nt_bf16(const void* A_hi, const void* A_lo, int64_t lda, const void* B_hi, const void* B_lo, int64_t ldb,
                  int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
@@ -288,7 +282,7 @@ static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, con
   const int64_t tiles = (symmetric ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n) * (pair ? 2 : 1);
   const int total_kchunks = (int)ceil_div(K, tc::BK);
   const int sms = sm_count();
-  if (gemm_mode() == 2 && K > 0) {
+  if ((gemm_mode() == 2 || gemm_mode() == -1) && K > 0) {
     int kps = 0, nsplit = 1;
     bool single = false;
     persistent_schedule(tiles, total_kchunks, sms, !accumulate && !symmetric, &kps, &nsplit, &single);
@@ -308,7 +302,7 @@ static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, con
       pA_lo = pA_hi; pB_lo = pB_hi;
     }
     return launch_gemm_tc_persistent(mn, x3p, pA_hi, pA_lo, pB_hi, pB_lo, M, N, alpha, D, ldd, symmetric, tiles_m, tiles_n,
-                                     tiles, total_kchunks, kps, nsplit, store ? 1 : 0, fp16_operands, sms, st);
+                                     tiles, total_kchunks, kps, nsplit, store ? 1 : 0, fp16_operands, sms, st, nullptr);
   }
   // overwrite + enough tiles (or a short K): one split per tile with plain stores
   const bool store_mode = !accumulate && !symmetric && K > 0 && (tiles >= sms / 2 || total_kchunks <= 16) && total_kchunks <= 128;

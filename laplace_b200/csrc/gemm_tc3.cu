@@ -1,7 +1,7 @@
 // Persistent variant of the factor contraction (gemm_tc.cu):  D[M,N] (fp32) += alpha * A * B^T
 //
 // One CTA per SM walks a static list of work items (output tile x K-range).  Within an item the K-range is cut into
-// groups of <= 32 k-chunks (K = 2048: the TMEM accumulator truncates, longer chains show a measurable bias); groups
+// groups of <= 16 k-chunks (K = 1024: the TMEM accumulator truncates, longer chains show a measurable bias); groups
 // alternate between two TMEM accumulators, the epilogue warps drain one while the tensor pipe fills the other and sum
 // the group results in registers (round-to-nearest fp32).  An item therefore ends with ONE set of reductions into D
 // however long its K-range is.  Compared with the one-tile-per-CTA kernel this
@@ -15,7 +15,8 @@ namespace lpb {
 
 namespace tc {
 
-constexpr int GROUP_CHUNKS = 32;      // k-chunks accumulated in one TMEM tile
+constexpr int GROUP_CHUNKS = 16;      // k-chunks (K = 1024) chained in one TMEM tile: the accumulator truncates, the
+                                      // bias grows ~3.5e-7 per chunk on same-sign sums; group sums are added in fp32 RN
 constexpr int TMEM_COLS_P = 256;      // two 128-column accumulators
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -44,13 +45,15 @@ __device__ __forceinline__ ItemGeom decode_item(int item, int num_tiles, int sym
   return g;
 }
 
-template <int NPROD, bool MN>
+// LOADER 0: K-major 2-D operands; 1: row (MN-major) 2-D operands; 2: implicit convolution patches (MN-major, 4-D)
+template <int NPROD, int LOADER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                           const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, int M,
                           int N, float alpha, float* __restrict__ D, int64_t ldd, int symmetric, int tiles_m, int tiles_n,
                           int num_tiles, int num_items, int total_kchunks, int kchunks_per_split, int num_stages,
-                          int store_mode, int fp16_operands) {
+                          int store_mode, int fp16_operands, PatchGeom pg) {
+  constexpr bool MN = LOADER != 0;
   constexpr int TILES_PER_STAGE = NPROD == 3 ? 4 : 2;
   constexpr int STAGE_BYTES = TILES_PER_STAGE * TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -89,7 +92,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], it.diag ? STAGE_BYTES / 2 : STAGE_BYTES);
           auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, int tile) {
-            if (MN) {
+            if (LOADER == 2) {
+              int n0, h0;
+              if (pg.chunks_per_img > 0) { n0 = kc / pg.chunks_per_img; h0 = (kc - n0 * pg.chunks_per_img) * pg.rows_per_chunk; }
+              else { n0 = kc * pg.imgs_per_chunk; h0 = 0; }
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const int fb = tile * 2 + b;
+                const int tap = fb / pg.blocks_per_tap;
+                const int kh = tap / pg.KW, kw = tap - kh * pg.KW;
+                // feature blocks past the last tap read channel coordinate Ci: entirely out of bounds = zeros
+                const int ci0 = tap < pg.num_taps ? (fb - tap * pg.blocks_per_tap) * 64 : pg.Ci;
+                tma_load_4d(map, &full_bar[stage], dst + b * (TILE_BYTES / 2), ci0, kw - pg.PW, h0 + kh - pg.PH, n0);
+              }
+            } else if (MN) {
               tma_load_2d(map, &full_bar[stage], dst, tile * BM, kc * BK);
               tma_load_2d(map, &full_bar[stage], dst + TILE_BYTES / 2, tile * BM + 64, kc * BK);
             } else {
@@ -228,6 +244,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
 }  // namespace tc
 
 // Split-K choice for the persistent schedule: minimise  waves x (chunks per item + epilogue)  over the number of splits.
+int launch_gemm_tc_persistent(bool mn, bool x3, const CUtensorMap& tA_hi, const CUtensorMap& tA_lo, const CUtensorMap& tB_hi,
+                              const CUtensorMap& tB_lo, int64_t M, int64_t N, float alpha, float* D, int64_t ldd,
+                              int symmetric, int tiles_m, int tiles_n, int64_t num_tiles, int total_kchunks,
+                              int kchunks_per_split, int splits, int store_mode, int fp16_operands, int ctas,
+                              cudaStream_t st, const tc::PatchGeom* patches);
+
 void persistent_schedule(int64_t tiles, int total_kchunks, int ctas, bool allow_single_store, int* kchunks_per_split,
                          int* splits, bool* single) {
   const double EPI = 3.0;   // one item's output pass, in k-chunk equivalents (mostly hidden behind the next item)
@@ -253,13 +275,15 @@ int launch_gemm_tc_persistent(bool mn, bool x3, const CUtensorMap& tA_hi, const 
                               const CUtensorMap& tB_lo, int64_t M, int64_t N, float alpha, float* D, int64_t ldd,
                               int symmetric, int tiles_m, int tiles_n, int64_t num_tiles, int total_kchunks,
                               int kchunks_per_split, int splits, int store_mode, int fp16_operands, int ctas,
-                              cudaStream_t st) {
+                              cudaStream_t st, const tc::PatchGeom* patches) {
   const int64_t items = num_tiles * splits;
   LPB_REQUIRE(items <= 2147483647LL, "gemm_tc_persistent: too many work items");
   const int stage_bytes = (x3 ? 4 : 2) * tc::TILE_BYTES;
   const int num_stages = x3 ? 3 : 6;
   const size_t smem = (size_t)num_stages * stage_bytes + (2 * num_stages + 4) * sizeof(uint64_t) + 16 + 1024;
   const unsigned grid = (unsigned)imin(items, ctas);
+  tc::PatchGeom pg = {};
+  if (patches) pg = *patches;
 #define LPB_LAUNCH_P(NP, MNV)                                                                                            \
   do {                                                                                                                   \
     static bool attr_done = false;                                                                                       \
@@ -272,14 +296,114 @@ int launch_gemm_tc_persistent(bool mn, bool x3, const CUtensorMap& tA_hi, const 
     }                                                                                                                    \
     tc::gemm_tc_persistent_kernel<NP, MNV><<<grid, tc::NUM_THREADS, smem, st>>>(                                         \
         tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd, symmetric, tiles_m, tiles_n, (int)num_tiles,          \
-        (int)items, total_kchunks, kchunks_per_split, num_stages, store_mode, fp16_operands);                            \
+        (int)items, total_kchunks, kchunks_per_split, num_stages, store_mode, fp16_operands, pg);                        \
   } while (0)
-  if (x3 && mn) LPB_LAUNCH_P(3, true);
-  else if (x3) LPB_LAUNCH_P(3, false);
-  else if (mn) LPB_LAUNCH_P(1, true);
-  else LPB_LAUNCH_P(1, false);
+  if (patches) {
+    if (x3) LPB_LAUNCH_P(3, 2);
+    else LPB_LAUNCH_P(1, 2);
+  } else if (x3 && mn) LPB_LAUNCH_P(3, 1);
+  else if (x3) LPB_LAUNCH_P(3, 0);
+  else if (mn) LPB_LAUNCH_P(1, 1);
+  else LPB_LAUNCH_P(1, 0);
 #undef LPB_LAUNCH_P
   LPB_CHECK_LAUNCH("gemm_tc_persistent");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// KFAC input factor of a stride-1 "same" convolution straight from the NHWC activation rows:
+//     D[(t,ci),(t',cj)] (+)= alpha * sum_{n,h,w} x[n, h+kh-PH, w+kw-PW, ci] * x[n, h+kh'-PH, w+kw'-PW, cj]
+// (tap-major feature order; taps_to_param_accumulate() below folds it into the parameter order (ci,kh,kw)).
+// The patch matrix [(n,h,w), KH*KW*Ci] -- 9x the activation for 3x3 kernels -- is never written or read.
+static int make_tmap_patches(CUtensorMap* map, const void* ptr, int64_t Q, int H, int W, int64_t Ci, int64_t ld, int box_h,
+                             int box_n) {
+  PFN_encodeTiled enc = get_tensormap_encoder();
+  LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)Ci, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Q};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(patches) failed (%d) Q=%lld H=%d W=%d Ci=%lld ld=%lld", (int)r,
+              (long long)Q, H, W, (long long)Ci, (long long)ld);
+  return 0;
+}
+
+int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q, int H, int W, int Ci, int KH, int KW, int PH,
+                      int PW, float alpha, int accumulate, float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
+  LPB_REQUIRE(Q > 0 && H > 0 && W > 0 && Ci > 0 && KH > 0 && KW > 0, "syrk_conv_patches: bad extents");
+  LPB_REQUIRE(Ci % 64 == 0, "syrk_conv_patches: C_in must be a multiple of 64 (got %d)", Ci);
+  LPB_REQUIRE(2 * PH == KH - 1 && 2 * PW == KW - 1, "syrk_conv_patches: stride-1 'same' convolutions only");
+  LPB_REQUIRE((ldx % 8) == 0 && ldx >= Ci && ((uintptr_t)X_hi % 16) == 0 && ((uintptr_t)X_lo % 16) == 0,
+              "syrk_conv_patches: operand rows must be 16-byte aligned");
+  const int HW = H * W;
+  tc::PatchGeom pg = {};
+  pg.KW = KW; pg.PH = PH; pg.PW = PW; pg.Ci = Ci; pg.num_taps = KH * KW; pg.blocks_per_tap = Ci / 64;
+  int box_h, box_n;
+  if (HW >= 64) {
+    LPB_REQUIRE(64 % W == 0 && H % (64 / W) == 0, "syrk_conv_patches: %dx%d images do not tile 64-row chunks", H, W);
+    pg.rows_per_chunk = 64 / W; pg.chunks_per_img = HW / 64; pg.imgs_per_chunk = 0;
+    box_h = pg.rows_per_chunk; box_n = 1;
+  } else {
+    LPB_REQUIRE(64 % HW == 0, "syrk_conv_patches: %dx%d images do not tile 64-row chunks", H, W);
+    pg.rows_per_chunk = H; pg.chunks_per_img = 0; pg.imgs_per_chunk = 64 / HW;
+    box_h = H; box_n = pg.imgs_per_chunk;
+  }
+  const int64_t d = (int64_t)KH * KW * Ci;
+  LPB_REQUIRE(ldd >= d, "syrk_conv_patches: ldd too small");
+  const int64_t kchunks64 = HW >= 64 ? Q * pg.chunks_per_img : ceil_div(Q, (int64_t)pg.imgs_per_chunk);
+  LPB_REQUIRE(kchunks64 < (1LL << 31), "syrk_conv_patches: too many sample rows");
+  const int total_kchunks = (int)kchunks64;
+  const bool x3 = X_lo != nullptr;
+  CUtensorMap tX_hi, tX_lo;
+  if (make_tmap_patches(&tX_hi, X_hi, Q, H, W, Ci, ldx, box_h, box_n)) return 1;
+  if (x3) {
+    if (make_tmap_patches(&tX_lo, X_lo, Q, H, W, Ci, ldx, box_h, box_n)) return 1;
+  } else {
+    tX_lo = tX_hi;
+  }
+  const int tiles_m = (int)ceil_div(d, tc::BM);
+  const int64_t tiles = (int64_t)tiles_m * (tiles_m + 1) / 2;
+  const int sms = sm_count();
+  int kps = 0, nsplit = 1;
+  bool single = false;
+  persistent_schedule(tiles, total_kchunks, sms, false, &kps, &nsplit, &single);
+  if (!accumulate && check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, d * sizeof(float), d, st), "syrk_conv_patches memset"))
+    return 1;
+  return launch_gemm_tc_persistent(true, x3, tX_hi, tX_lo, tX_hi, tX_lo, d, d, alpha, D, ldd, 1, tiles_m, tiles_m, tiles,
+                                   total_kchunks, kps, nsplit, 0, fp16_operands, sms, st, &pg);
+}
+
+// out[(ci*KK + t), (cj*KK + t')] += T[(t*Ci + ci), (t'*Ci + cj)]   (KK = KH*KW <= 9).  One CTA per (ci, 32 cj's):
+// the KK x KK x 32 block is read in 128-byte runs, staged in shared memory and written as KK runs of 32*KK floats.
+__global__ void __launch_bounds__(256) taps_to_param_kernel(const float* __restrict__ T, int64_t ldt, int Ci, int KK,
+                                                            float* __restrict__ out, int64_t ldo) {
+  __shared__ float s[9 * 9 * 32];
+  const int ci = blockIdx.y, cj0 = blockIdx.x * 32;
+  const int ncj = min(32, Ci - cj0);
+  for (int e = threadIdx.x; e < KK * KK * 32; e += blockDim.x) {
+    const int cjl = e & 31, tt = e >> 5;          // tt = t * KK + t'
+    const int t = tt / KK, t2 = tt - t * KK;
+    if (cjl < ncj) s[e] = T[(int64_t)(t * Ci + ci) * ldt + t2 * Ci + cj0 + cjl];
+  }
+  __syncthreads();
+  const int run = ncj * KK;
+  for (int e = threadIdx.x; e < KK * run; e += blockDim.x) {
+    const int t = e / run, r = e - t * run;
+    const int cjl = r / KK, t2 = r - cjl * KK;
+    float* dst = out + (int64_t)(ci * KK + t) * ldo + (int64_t)cj0 * KK + r;
+    *dst += s[(t * KK + t2) * 32 + cjl];
+  }
+}
+
+int taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int KK, float* out, int64_t ldo, cudaStream_t st) {
+  LPB_REQUIRE(KK >= 1 && KK <= 9, "taps_to_param_accumulate: kernel window larger than 9 taps");
+  LPB_REQUIRE(Ci > 0 && Ci <= 65535, "taps_to_param_accumulate: bad channel count");
+  dim3 grid((unsigned)ceil_div(Ci, 32), (unsigned)Ci);
+  taps_to_param_kernel<<<grid, 256, 0, st>>>(T, ldt, Ci, KK, out, ldo);
+  LPB_CHECK_LAUNCH("taps_to_param_accumulate");
   return 0;
 }
 

@@ -14,6 +14,12 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;                  // warp0 TMA, warp1 MMA/TMEM, warps2-5 epilogue
 constexpr int TMEM_COLS = 128;
 
+// Implicit convolution-patch operand of the persistent contraction (gemm_tc3.cu): feature f = tap * Ci + ci of sample
+// row (n,h,w) is x[n, h + kh - PH, w + kw - PW, ci] (zero outside the image), fetched as a shifted 4-D TMA box.
+struct PatchGeom {
+  int KW, PH, PW, Ci, num_taps, blocks_per_tap, chunks_per_img, rows_per_chunk, imgs_per_chunk;
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

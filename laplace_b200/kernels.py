@@ -344,6 +344,31 @@ def gemm_tn(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumul
     return out
 
 
+def conv_patches_ok(Ci: int, H: int, W: int, kh: int, kw: int) -> bool:
+    """Shapes ``syrk_conv_patches`` accepts (64-channel feature blocks, images tiling 64-row chunks, <= 9 taps)."""
+    if Ci % 64 or kh * kw > 9:
+        return False
+    hw = H * W
+    return (64 % hw == 0) if hw < 64 else (64 % W == 0 and H % (64 // W) == 0)
+
+
+def syrk_conv_patches(X: Packed, Q: int, H: int, W: int, mod, out: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """``out[d_in, d_in] += alpha * P^T P`` for the im2col patch matrix ``P [(n,h,w), C_in*kh*kw]`` of a stride-1 'same'
+    convolution, computed from the NHWC rows ``X [(n,h,w), C_in]`` without forming ``P``: implicit (shifted 4-D TMA)
+    SYRK into a tap-major scratch factor, then a permuting accumulate into the parameter order ``(ci,kh,kw)``."""
+    _check(out, name="out")
+    kh, kw = mod.kernel_size
+    Ci = X.K
+    d = Ci * kh * kw
+    assert out.shape == (d, d) and X.rows == Q * H * W and X.kind in (BF16, BF16X3, F16X3)
+    T = torch.empty(d, d, device=out.device, dtype=torch.float32)
+    _lib.call("lpb_syrk_conv_patches_tc", _ptr(X.hi), _ptr(X.lo), X.ldk, Q, H, W, Ci, kh, kw, mod.padding[0], mod.padding[1],
+              alpha, 0, _ptr(T), T.stride(0), 1 if X.kind == F16X3 else 0, _stream())
+    _lib.call("lpb_taps_to_param_accumulate", _ptr(T), T.stride(0), Ci, kh * kw, _ptr(out), out.stride(0), _stream())
+    _bump(2)
+    return out
+
+
 # ------------------------------------------------------------------------------ reverse-pass element-wise maps
 def scale_channels(g: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """``g [Q, C, H, W]`` (NCHW- or channels_last-dense) times a per-channel ``scale [C]``; same layout out."""

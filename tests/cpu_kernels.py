@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "col2im_nhwc", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "col2im_nhwc", "syrk_conv_patches", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -204,6 +204,14 @@ def col2im(Dc, in_shape, mod):
     OH, OW = K.conv_out_hw(in_shape, mod)
     cols = Dc[:, :Q * OH * OW].reshape(Dc.shape[0], Q, OH * OW).permute(1, 0, 2)
     return F.fold(cols, (H, W), mod.kernel_size, dilation=mod.dilation, padding=mod.padding, stride=mod.stride)
+
+
+def syrk_conv_patches(X, Q, H, W, mod, out, alpha=1.0):
+    Ci = X.K
+    x = X.hi[:, :Ci].reshape(Q, H, W, Ci).permute(0, 3, 1, 2).float()
+    P = F.unfold(x, mod.kernel_size, padding=mod.padding).transpose(1, 2).reshape(Q * H * W, -1)
+    out += alpha * (P.t() @ P)
+    return out
 
 
 def col2im_nhwc(Dc, in_shape, mod):

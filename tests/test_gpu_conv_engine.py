@@ -101,3 +101,48 @@ def test_layer_gradients_match_fp64_autograd(name, kw):
     assert rel_fro(f, f64) < 1e-5
     worst = max(rel_fro(a, b) for a, b in zip(grads, g64))
     assert worst < 5e-5, worst
+
+
+@pytest.mark.parametrize("geom", [(64, 8, 8, 3, 70), (128, 4, 4, 3, 130), (64, 2, 2, 3, 33), (256, 1, 1, 3, 200), (64, 16, 16, 3, 5),
+                                  (64, 8, 8, 1, 40), (128, 16, 8, 3, 9), (64, 32, 32, 3, 3)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16X3, 3e-5), (K.F16X3, 1e-5), (K.BF16, 6e-3)])
+def test_syrk_conv_patches_vs_unfold(geom, kind, tol):
+    """im2col-free A factor (shifted 4-D TMA boxes feeding the MN-major SYRK) == fp64 unfold + P^T P, in the parameter
+    order (ci, kh, kw), accumulating into the existing factor; ragged image counts included."""
+    Ci, H, W, k, Q = geom
+    torch.manual_seed(3)
+    mod = torch.nn.Conv2d(Ci, 8, k, 1, k // 2)
+    x = torch.randn(Q, Ci, H, W)
+    P = F.unfold(x.double(), k, padding=k // 2).transpose(1, 2).reshape(Q * H * W, -1)
+    ref = P.t() @ P
+    assert K.conv_patches_ok(Ci, H, W, k, k)
+    X = conv_engine.nhwc_rows(x.to(DEV).contiguous(memory_format=torch.channels_last), kind)
+    base = torch.randn(ref.shape[0], ref.shape[0])
+    out = base.to(DEV)
+    K.syrk_conv_patches(X, Q, H, W, mod, out, alpha=0.5)
+    assert rel_fro(out.cpu().double() - base.double(), 0.5 * ref) < tol
+    assert rel_fro(out - base.to(DEV), (out - base.to(DEV)).t()) < 1e-5
+
+
+def test_implicit_patch_factor_model_parity():
+    """A 64-channel convolution stack: KFAC-GGN factors through the im2col-free path == oracle (<= 1e-4)."""
+    from laplace_b200 import B200GGN
+    from oracle import curvature_oracle as co
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 3, 1, 1), torch.nn.ReLU(), torch.nn.Conv2d(64, 64, 3, 1, 1, bias=False),
+                                torch.nn.ReLU(), torch.nn.Conv2d(64, 128, 1), torch.nn.ReLU(),
+                                torch.nn.Conv2d(128, 64, 3, 1, 1), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
+                                torch.nn.Linear(64, 5)).eval()
+    X, y = torch.randn(12, 3, 8, 8), torch.randint(5, (12,))
+    calls = []
+    orig = K.syrk_conv_patches
+    K.syrk_conv_patches = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        _, kron = B200GGN(model.to(DEV), "classification").kron(X.to(DEV), y.to(DEV), N=36)
+    finally:
+        K.syrk_conv_patches = orig
+    assert len(calls) == 3
+    _, kf = co.kfac_factors(model.cpu().double(), "classification", X.double(), y, N=36)
+    worst = max(rel_fro(H.cpu(), Ho) for F_, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F_, Fo))
+    assert worst < 1e-4, worst

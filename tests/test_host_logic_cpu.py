@@ -173,3 +173,24 @@ def test_mapping_inputs_and_dtype_propagation(golden, cpu_kernels):
     be = B200GGN(m64, "regression")
     assert be.jacobians(X64)[0].dtype == torch.float64 and be.full(X64, y64)[1].dtype == torch.float64
     assert be.diag(X64, y64)[1].dtype == torch.float64 and be.kron(X64, y64, N=10)[1].kfacs[0][0].dtype == torch.float64
+
+
+def test_implicit_patch_factor_path(cpu_kernels, monkeypatch):
+    """64-channel stride-1 convolutions take the im2col-free A-factor path (K.syrk_conv_patches on the forward's NHWC
+    rows): same factors as the oracle, in parameter order."""
+    from laplace_b200 import conv_engine, kernels as K
+
+    calls = []
+    orig = K.syrk_conv_patches
+    monkeypatch.setattr(K, "syrk_conv_patches", lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
+    monkeypatch.setattr(conv_engine, "ELEMENTWISE_MIN_BATCH", 0)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 3, 1, 1), torch.nn.ReLU(), torch.nn.Conv2d(64, 64, 3, 1, 1, bias=False),
+                                torch.nn.ReLU(), torch.nn.Conv2d(64, 16, 1), torch.nn.AdaptiveAvgPool2d(1),
+                                torch.nn.Flatten(), torch.nn.Linear(16, 5)).eval()
+    X, y = torch.randn(6, 3, 8, 8), torch.randint(5, (6,))
+    _, kron = B200GGN(model, "classification").kron(X, y, N=18)
+    assert len(calls) == 2          # the 3x3 64->64 and the 1x1 64->16 convolution
+    _, kf = co.kfac_factors(model, "classification", X, y, N=18)
+    worst = max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo))
+    assert worst < 1e-5, worst
