@@ -357,6 +357,9 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
         "gemm_nt": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[1].rows * a[0].K, a[0].kind != K.F32),
         "gemm_tn": lambda r, a, kw: ("flops", 2.0 * a[0].K * a[1].K * a[0].rows, True),
         "conv_nhwc": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[5] * a[0].K * a[6] * a[7], True),
+        # implicit patch SYRK: dense 2 * d^2 * rows convention, d = C_in * kh * kw
+        "syrk_conv_patches": lambda r, a, kw: ("flops", 2.0 * float(a[5].shape[0]) ** 2 * a[0].rows, True),
+        "col2im_nhwc": lambda r, a, kw: ("bytes", 4.0 * (a[0].shape[0] * a[0].shape[1] + r.numel()), False),
         "pack_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
         "pack_conv": lambda r, a, kw: ("bytes", bytes_packed(r[0]), False),
         "pack_nchw": lambda r, a, kw: ("bytes", bytes_packed(r), False),
@@ -391,9 +394,10 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
     d = fam[dom]
     tensor = d["kind"] == "flops"
     peak = (pk["bf16_sustained"] or 1400.0) if tensor else (pk["hbm"] or 6650.0)
-    names = {"gemm_nt": "tc::gemm_nt_tc_kernel<.,false> (tcgen05 GEMM-NT/SYRK, K-major operands: KFAC factor contractions + explicit-engine GEMMs)",
-             "gemm_tn": "tc::gemm_nt_tc_kernel<.,true> (tcgen05 SYRK on row-major operands, MN-major descriptors: KFAC factor contractions)",
-             "conv_nhwc": "tc::conv_nhwc_tc_kernel (tcgen05 implicit-GEMM convolution, forward + backward-data)"}
+    names = {"gemm_nt": "tc::gemm_tc_persistent_kernel<.,0> (tcgen05 GEMM-NT/SYRK, K-major operands: KFAC factor contractions + explicit-engine GEMMs)",
+             "gemm_tn": "tc::gemm_tc_persistent_kernel<.,1> (tcgen05 SYRK on row-major operands, MN-major descriptors: KFAC factor contractions)",
+             "syrk_conv_patches": "tc::gemm_tc_persistent_kernel<.,2> (tcgen05 SYRK on implicit convolution patches, shifted 4-D TMA boxes: KFAC input factors)",
+             "conv_nhwc": "tc::conv_nhwc_tc_persistent_kernel (tcgen05 implicit-GEMM convolution, forward + backward-data)"}
     return {"bound": "tensor" if tensor else "hbm", "kernel": names.get(dom, "lpb::" + dom + "_kernel"),
             "achieved": d["achieved"], "peak": peak, "unit": d["unit"], "frac": d["achieved"] / peak, "traffic": None,
             "peak_source": pk["source"] + (", bf16 sustained" if tensor else ", copy bandwidth"),

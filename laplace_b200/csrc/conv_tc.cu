@@ -11,6 +11,8 @@
 // channels, loops over taps x channel chunks through the same full/empty mbarrier ring as the GEMM kernel,
 // accumulates in TMEM and stores the fp32 tile once.  bf16 hi/lo operands, three products per tile
 // (NPROD = 3) give fp32-level accuracy.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lpb {
@@ -131,6 +133,171 @@ conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_con
   }
 }
 
+// Persistent form of the same convolution: one CTA per SM walks the (row tile, channel tile) list; taps x channel
+// chunks of a tile are cut into groups of <= 16 k-chunks that alternate between two TMEM accumulators, the epilogue
+// warps sum the groups in registers and store the tile while the tensor pipe already works on the next one.  Hides the
+// per-tile prologue (barrier init, TMEM allocation, first TMA round trip) and epilogue that made the one-tile-per-CTA
+// kernel spend ~1/3 of its time outside the MMA loop on 64-channel layers (9 k-chunks per tile).
+constexpr int CONV_GROUP = 16;
+
+template <int NPROD>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                               int64_t Mrows, int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile, int KH,
+                               int KW, int base_h, int base_w, int sgn, int kchunks, int num_stages, int fp16_operands, int bn,
+                               int tiles_n, int num_items) {
+  const int B_BYTES = bn * BK * 2;
+  const int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (TILE_BYTES + B_BYTES);
+  const int OFF_B_HI = TILE_BYTES, OFF_A_LO = TILE_BYTES + B_BYTES, OFF_B_LO = 2 * TILE_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + num_stages;
+  uint64_t* tfull_bar = empty_bar + num_stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int total = KH * KW * kchunks;
+  const int ngroups = (total + CONV_GROUP - 1) / CONV_GROUP;
+  const int glen = (total + ngroups - 1) / ngroups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tm = item / tiles_n, tn = item - tm * tiles_n;
+        const int q0 = tm * q_per_tile;
+        for (int it = 0; it < total; ++it) {
+          const int tap = it / kchunks, kc = it - tap * kchunks;
+          const int kh = tap / KW, kw = tap - kh * KW;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int ch = base_h + sgn * kh, cw = base_w + sgn * kw;
+          tma_load_4d(&tmX_hi, &full_bar[stage], st, kc * BK, cw, ch, q0);
+          tma_load_2d(&tmW_hi, &full_bar[stage], st + OFF_B_HI, kc * BK, tap * N + tn * bn);
+          if (NPROD == 3) {
+            tma_load_4d(&tmX_lo, &full_bar[stage], st + OFF_A_LO, kc * BK, cw, ch, q0);
+            tma_load_2d(&tmW_lo, &full_bar[stage], st + OFF_B_LO, kc * BK, tap * N + tn * bn);
+          }
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, bn, fp16_operands);
+      int stage = 0; uint32_t phase = 0; uint32_t grp = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        for (int g0 = 0; g0 < total; g0 += glen, ++grp) {
+          const uint32_t buf = grp & 1;
+          mbar_wait(&tempty_bar[buf], ((grp >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tacc = tmem_base + buf * 128;
+          uint32_t acc = 0;
+          const int gend = min(total, g0 + glen);
+          for (int it = g0; it < gend; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sbase = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint64_t a_hi = make_smem_desc(sbase), b_hi = make_smem_desc(sbase + OFF_B_HI);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+              umma_f16(tacc, a_hi + koff, b_hi + koff, idesc, acc);
+              acc = 1;
+              if (NPROD == 3) {
+                const uint64_t a_lo = make_smem_desc(sbase + OFF_A_LO), b_lo = make_smem_desc(sbase + OFF_B_LO);
+                umma_f16(tacc, a_hi + koff, b_lo + koff, idesc, 1);
+                umma_f16(tacc, a_lo + koff, b_hi + koff, idesc, 1);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[buf]);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const bool vec_ok = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0);
+    uint32_t grp = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tm = item / tiles_n, tn = item - tm * tiles_n;
+      float accv[128];
+      for (int g0 = 0; g0 < total; g0 += glen, ++grp) {
+        const uint32_t buf = grp & 1;
+        mbar_wait(&tfull_bar[buf], (grp >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + buf * 128 + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          if (chunk * 32 < bn) {   // uniform
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)(chunk * 32), v);
+            if (g0 == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) accv[chunk * 32 + j] = v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) accv[chunk * 32 + j] += v[j];
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[buf])) : "memory");
+        }
+      }
+      const int64_t row = (int64_t)tm * BM + q * 32 + lane;
+      if (row < Mrows) {
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          const int col0 = tn * bn + chunk * 32;
+          if (chunk * 32 < bn && col0 < N) {
+            float* drow = D + row * ldd + col0;
+            const float* v = accv + chunk * 32;
+            if (vec_ok && col0 + 32 <= N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(drow + j) = make_float4(alpha * v[j], alpha * v[j + 1], alpha * v[j + 2], alpha * v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) drow[j] = alpha * v[j];
+            }
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
 }  // namespace tc
 
 static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int64_t Q, int H, int W, int64_t Kc, int64_t ld, int q_per_tile) {
@@ -188,6 +355,41 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
                    "conv_nhwc_bf16 attr"))
       return 1;
     attr1 = true;
+  }
+  static int conv_mode = -1;
+  if (conv_mode < 0) {
+    const char* e = getenv("LPB_CONV_MODE");   // 0: one tile per CTA (A/B timing); default: persistent CTAs
+    conv_mode = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  if (conv_mode == 1) {
+    const int64_t items = tiles_m * tiles_n;
+    LPB_REQUIRE(items <= 2147483647LL, "conv_nhwc_bf16: too many tiles");
+    const int pstages = (int)imin(8, (196 * 1024) / stage_bytes);
+    const size_t psmem = (size_t)pstages * stage_bytes + (2 * pstages + 4) * sizeof(uint64_t) + 16 + 1024;
+    static bool pattr1 = false, pattr3 = false;
+    if (x3 && !pattr3) {
+      if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024), "conv_nhwc_bf16 attr"))
+        return 1;
+      pattr3 = true;
+    }
+    if (!x3 && !pattr1) {
+      if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024), "conv_nhwc_bf16 attr"))
+        return 1;
+      pattr1 = true;
+    }
+    const unsigned pgrid = (unsigned)imin(items, sm_count());
+    if (x3)
+      tc::conv_nhwc_tc_persistent_kernel<3><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
+          tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, KH, KW, base_h, base_w, sgn, kchunks, pstages,
+          fp16_operands, bn, tiles_n, (int)items);
+    else
+      tc::conv_nhwc_tc_persistent_kernel<1><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
+          tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, KH, KW, base_h, base_w, sgn, kchunks, pstages,
+          fp16_operands, bn, tiles_n, (int)items);
+    LPB_CHECK_LAUNCH("conv_nhwc_bf16 (persistent)");
+    return 0;
   }
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
   if (x3)
