@@ -366,6 +366,7 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
         "pack_conv_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
         "pack_nchw_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
         "pack_cast": lambda r, a, kw: ("bytes", bytes_packed(r), False),
+        "pack_cast_fused": lambda r, a, kw: ("bytes", bytes_packed(r) + (4.0 * a[3].numel() if len(a) > 3 and a[3] is not None else 0.0), False),
         "scale_channels": lambda r, a, kw: ("bytes", 8.0 * r.numel(), False),
         "relu_bwd": lambda r, a, kw: ("bytes", 8.0 * r.numel() + 4.0 * a[1].numel(), False),
         "maxpool2d_bwd": lambda r, a, kw: ("bytes", 4.0 * (r.numel() + a[0].numel()) + 8.0 * a[1].numel(), False),

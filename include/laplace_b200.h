@@ -83,6 +83,11 @@ int lpb_pack_nchw_rows(const float* g, int64_t Q, int Cc, int HW, void* dst_hi, 
 /* src [rows, cols] fp32 (ld_src) -> same layout in out_kind (row stride ld)                               */
 int lpb_pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst_hi, void* dst_lo, int out_kind,
                   int64_t ld, void* stream);
+/* pack_cast with the element-wise maps that precede a convolution's reverse pass fused in:
+ * dst[r, c] = split(src[r, c] * scale[c] * (y[r % rows_y, c] > 0)); scale / y may be NULL.  Replaces the vmapped
+ * threshold_backward + native_batch_norm_backward (eval) of the reference's reverse pass plus the operand cast.   */
+int lpb_pack_cast_fused(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* scale, const float* y,
+                        int64_t rows_y, int64_t ld_y, void* dst_hi, void* dst_lo, int out_kind, int64_t ld, void* stream);
 /* col2im gather: Dc [(ci,kh,kw), ldd] with columns (q,oh,ow) -> grad_in [Q, C, H, W] (overwrites)        */
 int lpb_col2im(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,
                int DH, int DW, float* grad_in, void* stream);

@@ -70,13 +70,16 @@ class _B200Mixin:
     """Shared machinery of the GGN and EF flavours."""
 
     def _b200_init(self, precision: str = "auto", batched_backward: bool = True, model_tf32: bool = False,
-                   conv_engine: bool = True):
+                   conv_engine: bool = True, fuse_elementwise: bool = True):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
         self.batched_backward = batched_backward
         self.model_tf32 = model_tf32
         self.conv_engine = conv_engine and not model_tf32
+        # KFAC path only: reverse pass of conv -> frozen BN -> ReLU chains as one node per convolution (conv_engine.py)
+        self.fuse_elementwise = fuse_elementwise
+        self._fused = False
         self._layers: list[_Layer] | None = None
         self._unsupported: list[str] = []
         self._hooks = []
@@ -138,16 +141,17 @@ class _B200Mixin:
             raise RuntimeError("the B200 curvature backend runs on CUDA only (model/input on %s); there is no "
                                "CPU fallback" % t.device)
 
-    def _forward(self, x):
+    def _forward(self, x, fuse: bool = False):
         self._plan()
         self._acts, self._outs = {}, {}
+        self._fused = bool(fuse and self.conv_engine)
         if self.conv_engine:
             from . import conv_engine
 
             conv_engine.STASH.clear()
         self._capturing = True
         try:
-            with torch.enable_grad(), self._model_numerics(), self._conv_patch():
+            with torch.enable_grad(), self._model_numerics(), self._conv_patch(self._fused):
                 f = self.model(x)
         finally:
             self._capturing = False
@@ -159,7 +163,7 @@ class _B200Mixin:
             torch._assert_async(torch.isfinite(f).all())
         return f
 
-    def _conv_patch(self):
+    def _conv_patch(self, fuse: bool = False):
         """fp32-accurate convolution passes on the tensor cores (laplace_b200/conv_engine.py) instead of cuDNN's
         fp32 fallback kernels; ``conv_engine=False`` keeps the model's own convolution implementation."""
         import contextlib
@@ -168,7 +172,7 @@ class _B200Mixin:
             return contextlib.nullcontext()
         from .conv_engine import patched_convs
 
-        return patched_convs(self.model)
+        return patched_convs(self.model, fuse=fuse)
 
     def _model_numerics(self):
         """The network's own forward/reverse passes run in true fp32 unless ``model_tf32=True``: PyTorch's default
@@ -187,31 +191,57 @@ class _B200Mixin:
         """Gradients of ``sum_n <cols[j, n], f[n]>`` w.r.t. every captured layer output, for all ``j`` at once.
         Returns one fp32 tensor ``[ncols, M, ...]`` per planned layer."""
         outs = [self._outs[L.name] for L in self._layers]
+        n_layers = len(outs)
+        bump = lambda: None
+        if self.conv_engine:
+            from . import conv_engine
+
+            def bump():
+                conv_engine.PASS_ID[0] += 1
+
+            if self._fused:
+                # fused chains hang off the layer INPUT and weight, not off the captured layer output: ask for the
+                # weights of fused layers too so that their reverse node runs (and packs its gradient rows) even when
+                # nothing upstream needs an input gradient (first layer).  The weight "gradient" itself is None.
+                outs = outs + [L.mod.weight for L in self._layers
+                               if conv_engine.STASH.get(id(L.mod), {}).get("fused") and L.mod.weight.requires_grad]
         cols = cols.to(f.dtype)
         grads = None
         if self.batched_backward and cols.shape[0] > 1:
             try:
                 if self.conv_engine:
                     # functorch vmap over autograd.grad: custom Functions fold the column dim into the batch
-                    def one(col):
-                        return torch.autograd.grad(f, outs, grad_outputs=col, retain_graph=True, allow_unused=True)
+                    missing = []
 
-                    grads = torch.func.vmap(one)(cols)
+                    def one(col):
+                        gs = torch.autograd.grad(f, outs, grad_outputs=col, retain_graph=True, allow_unused=True)
+                        missing[:] = [g is None for g in gs]
+                        return tuple(col.new_zeros(()) if g is None else g for g in gs)
+
+                    bump()
+                    grads = list(torch.func.vmap(one)(cols))
+                    grads = [None if miss else g for g, miss in zip(grads, missing)]
                 else:
                     grads = torch.autograd.grad(f, outs, grad_outputs=cols, is_grads_batched=True, retain_graph=True,
                                                 allow_unused=True)
                 self.last_backward_mode = "batched"
             except (RuntimeError, NotImplementedError) as e:
+                if self.conv_engine and isinstance(e, conv_engine.FusionConflict):
+                    raise
                 grads = None  # an op without a batching rule: fall back to one reverse pass per column
                 self.last_backward_mode = f"loop ({type(e).__name__}: {str(e)[:120]})"
         if grads is None:
             per = []
             for j in range(cols.shape[0]):
+                bump()
                 per.append(torch.autograd.grad(f, outs, grad_outputs=cols[j], retain_graph=j + 1 < cols.shape[0],
                                                allow_unused=True))
             grads = [None if per[0][i] is None else torch.stack([p[i] for p in per]) for i in range(len(outs))]
         res = []
-        for L, g, o in zip(self._layers, grads, outs):
+        for L, g, o in zip(self._layers, grads[:n_layers], outs[:n_layers]):
+            if g is None and self._fused:
+                res.append(None)   # fused chain: the gradient exists only as packed rows in conv_engine.STASH
+                continue
             if g is None:
                 g = torch.zeros((cols.shape[0],) + tuple(o.shape), device=o.device, dtype=torch.float32)
             res.append(g.detach().float())   # layout fixed lazily by the consumers (no copy when unused)
@@ -295,14 +325,33 @@ class _B200Mixin:
             raise ValueError(f"kfac_approx must be 'expand' or 'reduce', got {kfac_approx!r}")
         self._require_supported("kron()")
         reduce = kfac_approx == "reduce"
-        f = self._forward(x)
+        fuse = (self.conv_engine and self.fuse_elementwise and not reduce and self.precision in ("auto", "bf16x3")
+                and self.batched_backward)
+        f = self._forward(x, fuse=fuse)
         fd = f.detach()
         M = fd.shape[0]
         y = y.to(fd.device)
         loss = self.factor * self.lossfunc(fd, y)
         cols = cols_fn(fd, y)
         acts = self._acts
-        grads = self._backward(f, cols)
+        try:
+            grads = self._backward(f, cols)
+        except RuntimeError as e:
+            from . import conv_engine as _ce
+
+            if not (self._fused and isinstance(e, _ce.FusionConflict)):
+                raise
+            # a fused intermediate has a second consumer in this model: keep the chains unfused from now on
+            self.fuse_elementwise = False
+            f = self._forward(x, fuse=False)
+            acts = self._acts
+            grads = self._backward(f, cols)
+        if self._fused and not (cols.shape[0] == 1 or getattr(self, "last_backward_mode", "") == "batched"):
+            # the column-batched reverse pass was not available: the fused chains keep gradients only as packed rows
+            # of ONE pass, so redo the passes unfused (one reverse pass per column, gradients as tensors)
+            f = self._forward(x, fuse=False)
+            acts = self._acts
+            grads = self._backward(f, cols)
         self._acts = {}
         dims = []
         for L in self._layers:
@@ -321,10 +370,13 @@ class _B200Mixin:
             stash = conv_engine.STASH   # row-major operands the engine already packed for this batch
         for L, g in zip(self._layers, grads):
             a = acts[L.name]
-            ncols = g.shape[0]
+            ncols = cols.shape[0]
             rows = stash.get(id(L.mod), {})
             Grows = rows.get("G")
-            if Grows is not None and Grows.rows != g.numel() // L.d_out:
+            if g is None:
+                if Grows is None:
+                    raise RuntimeError(f"{L.name}: fused reverse chain left no gradient rows (internal error)")
+            elif Grows is not None and Grows.rows != g.numel() // L.d_out:
                 Grows = None
             if Grows is None and L.is_conv and stash is not None and len(stash) > 0 and g.dim() == 5:
                 # a convolution whose reverse node never ran (the first layer: nothing upstream needs its input
@@ -563,15 +615,17 @@ class B200GGN(_B200Mixin, GGNInterface):
 
     Parameters beyond the reference's: ``precision`` in {"auto", "fp32", "bf16", "bf16x3"} selects the
     operand format of the tensor-core contractions (fp32 accumulation always); ``batched_backward=False``
-    falls back to one reverse pass per column for models with ops that lack a vmap rule.
+    falls back to one reverse pass per column for models with ops that lack a vmap rule; ``fuse_elementwise=False``
+    keeps ``conv -> frozen BatchNorm -> ReLU`` chains as separate reverse-pass kernels in ``kron()`` (required only if a
+    convolution output feeds a BatchNorm/ReLU *and* another operation, which the backend detects and reports).
     """
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
                  dict_key_y="labels", stochastic=False, num_samples=1, precision="auto", batched_backward=True,
-                 model_tf32=False, conv_engine=True):
+                 model_tf32=False, conv_engine=True, fuse_elementwise=True):
         GGNInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y,
                               stochastic, num_samples)
-        self._b200_init(precision, batched_backward, model_tf32, conv_engine)
+        self._b200_init(precision, batched_backward, model_tf32, conv_engine, fuse_elementwise)
 
     def _ggn_cols(self, f, y=None):
         return self._mc_cols(f, self.num_samples) if self.stochastic else self._hessian_sqrt_cols(f)
@@ -665,9 +719,10 @@ class B200EF(_B200Mixin, EFInterface):
     """Empirical Fisher on B200 (drop-in for ``CurvlinopsEF``, curvature/curvlinops.py:171-180)."""
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
-                 dict_key_y="labels", precision="auto", batched_backward=True, model_tf32=False, conv_engine=True):
+                 dict_key_y="labels", precision="auto", batched_backward=True, model_tf32=False, conv_engine=True,
+                 fuse_elementwise=True):
         EFInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y)
-        self._b200_init(precision, batched_backward, model_tf32, conv_engine)
+        self._b200_init(precision, batched_backward, model_tf32, conv_engine, fuse_elementwise)
 
     def kron(self, x, y, N, **kwargs: Any):
         """``CurvlinopsInterface.kron`` with ``FisherType.EMPIRICAL`` (curvature/curvlinops.py:174-176)."""

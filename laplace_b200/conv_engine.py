@@ -73,6 +73,14 @@ _CACHE = _WeightCache()
 #   "P": patch rows [(n,t), d_in] of explicit-path forwards, "G": output-gradient rows [(col,n,t), C_out].
 # The KFAC factor SYRKs consume them directly through the MN-major GEMM (no second, transposing pack).
 STASH: dict = {}
+# Reverse-pass counter (bumped by the backend before every autograd.grad call): a layer whose gradient rows are packed
+# twice within one pass has two consumers in the graph, which the fused chains cannot represent.
+PASS_ID = [0]
+
+
+class FusionConflict(RuntimeError):
+    """A fused conv -> BatchNorm -> ReLU chain whose intermediate is also consumed elsewhere (e.g. a pre-activation
+    residual that adds the raw convolution output).  The backend catches it and repeats the batch unfused."""
 
 
 def implicit_ok(mod: nn.Conv2d, H: int, W: int) -> bool:
@@ -92,19 +100,23 @@ def nhwc_rows(x: torch.Tensor, kind: int) -> K.Packed:
     return K.pack_nchw_rows(x.contiguous().reshape(N, C, H * W), kind)
 
 
+def _implicit_rows(X: K.Packed, N: int, H: int, W: int, mod: nn.Conv2d, which: str, n_out: int, sgn: int) -> torch.Tensor:
+    kh, kw = mod.kernel_size
+    Wt = _CACHE.get(mod, which)
+    out = torch.empty(N * H * W, n_out, device=X.hi.device, dtype=torch.float32)
+    ph, pw = mod.padding
+    K.conv_nhwc(X, N, H, W, Wt, n_out, kh, kw, -sgn * ph, -sgn * pw, sgn, out, alpha=getattr(Wt, "inv_scale", 1.0))
+    return out.view(N, H, W, n_out).permute(0, 3, 1, 2)     # channels_last view, no copy
+
+
 def _implicit(x: torch.Tensor, mod: nn.Conv2d, which: str, n_out: int, sgn: int, X: K.Packed | None = None) -> torch.Tensor:
     N, _, H, W = x.shape
-    kh, kw = mod.kernel_size
     if X is None:
         X = nhwc_rows(x, KIND_FWD if sgn > 0 else KIND)
     if sgn > 0:
         # forward: the packed NHWC input rows double as the operand of the implicit A-factor SYRK (no im2col at all)
         STASH.setdefault(id(mod), {})["X"] = (X, N, H, W)
-    Wt = _CACHE.get(mod, which)
-    out = torch.empty(N * H * W, n_out, device=x.device, dtype=torch.float32)
-    ph, pw = mod.padding
-    K.conv_nhwc(X, N, H, W, Wt, n_out, kh, kw, -sgn * ph, -sgn * pw, sgn, out, alpha=getattr(Wt, "inv_scale", 1.0))
-    return out.view(N, H, W, n_out).permute(0, 3, 1, 2)     # channels_last view, no copy
+    return _implicit_rows(X, N, H, W, mod, which, n_out, sgn)
 
 
 def conv_forward(x: torch.Tensor, mod: nn.Conv2d) -> torch.Tensor:
@@ -126,20 +138,55 @@ def conv_forward(x: torch.Tensor, mod: nn.Conv2d) -> torch.Tensor:
     return out
 
 
-def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape, need_dx: bool = True):
-    """Packs the output-gradient rows (stashed for the B-factor SYRK) and, if ``need_dx``, returns the input gradient."""
-    Q, Co = g.shape[0], g.shape[1]
-    T = g.shape[2] * g.shape[3]
-    G = nhwc_rows(g, KIND)                                   # [(q,t), Co]
-    STASH.setdefault(id(mod), {})["G"] = G
+def _backward_from_rows(G: K.Packed, Q: int, T: int, mod: nn.Conv2d, in_shape, need_dx: bool):
+    """Input gradient from the packed output-gradient rows ``G [(q,t), Co]`` (stashed for the B-factor SYRK)."""
+    st = STASH.setdefault(id(mod), {})
+    if st.get("G_pass") == PASS_ID[0]:
+        raise FusionConflict("convolution engine: the output of a fused convolution is consumed by more than one "
+                             "operation (two reverse passes reached the same layer); use fuse_elementwise=False")
+    st["G"], st["G_pass"] = G, PASS_ID[0]
     if not need_dx:
         return None
     if implicit_ok(mod, in_shape[2], in_shape[3]):
-        return _implicit(g, mod, "bwd_taps", mod.in_channels, -1, X=G)
+        return _implicit_rows(G, Q, in_shape[2], in_shape[3], mod, "bwd_taps", mod.in_channels, -1)
     Wt = _CACHE.get(mod, "bwd_taps")                         # [(kh,kw,ci), Co]
-    Dc = torch.empty(Q * T, Wt.rows, device=g.device, dtype=torch.float32)
+    Dc = torch.empty(Q * T, Wt.rows, device=G.hi.device, dtype=torch.float32)
     K.gemm_nt(G, Wt, Dc, 1.0, accumulate=False)              # [(q,t), (kh,kw,ci)]
     return K.col2im_nhwc(Dc, (Q,) + tuple(in_shape[1:]), mod)   # channels-last view: every gradient stays NHWC
+
+
+def conv_backward_data(g: torch.Tensor, mod: nn.Conv2d, in_shape, need_dx: bool = True):
+    """Packs the output-gradient rows (stashed for the B-factor SYRK) and, if ``need_dx``, returns the input gradient."""
+    if STASH.get(id(mod), {}).get("fused"):
+        raise FusionConflict("convolution engine: the output of a fused convolution is also consumed outside the fused "
+                             "BatchNorm/ReLU chain; use fuse_elementwise=False")
+    Q = g.shape[0]
+    T = g.shape[2] * g.shape[3]
+    G = nhwc_rows(g, KIND)                                   # [(q,t), Co]
+    return _backward_from_rows(G, Q, T, mod, in_shape, need_dx)
+
+
+def _is_nhwc(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.stride(1) == 1 and t.permute(0, 2, 3, 1).is_contiguous()
+
+
+def conv_backward_fused(g: torch.Tensor, mod: nn.Conv2d, in_shape, need_dx: bool, scale, y, reps: int):
+    """Reverse pass of ``relu?(affine?(conv(x)))`` w.r.t. the convolution: the ReLU mask (``y > 0``, shared by the
+    ``reps`` folded columns), the frozen-BN scale and the 16-bit hi/lo operand split happen in ONE pass over the
+    gradient (``pack_cast_fused``); the result is both the B-factor operand and the A operand of the backward-data
+    convolution.  The fp32 gradients between the three modules are never materialised."""
+    Q, Co = g.shape[0], g.shape[1]
+    T = g.shape[2] * g.shape[3]
+    if _is_nhwc(g) and (y is None or _is_nhwc(y)):
+        y2 = None if y is None else y.permute(0, 2, 3, 1).reshape(-1, Co)
+        G = K.pack_cast_fused(g.permute(0, 2, 3, 1).reshape(Q * T, Co), KIND, scale, y2)
+    else:   # unusual layouts: the separate kernels
+        if y is not None:
+            g = _ReluBwd.apply(g, y, reps)
+        if scale is not None:
+            g = K.scale_channels(g, scale)
+        G = nhwc_rows(g, KIND)
+    return _backward_from_rows(G, Q, T, mod, in_shape, need_dx)
 
 
 class _ConvBwdData(torch.autograd.Function):
@@ -243,6 +290,82 @@ class _Linear(torch.autograd.Function):
     def backward(ctx, g):
         gx = _LinearBwdData.apply(g, ctx.mod, bool(ctx.needs_input_grad[0]))
         return (gx if ctx.needs_input_grad[0] else None), None, None
+
+
+class _ConvFusedBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(g, mod, in_shape, need_dx, scale, y, reps):
+        out = conv_backward_fused(g if g.dtype == torch.float32 else g.float(), mod, in_shape, need_dx, scale, y, reps)
+        return out if out is not None else g.new_empty(0)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, *grads):  # pragma: no cover
+        raise NotImplementedError("double backward through the convolution engine is not supported")
+
+    @staticmethod
+    def vmap(info, in_dims, g, mod, in_shape, need_dx, scale, y, reps):
+        g = g.movedim(in_dims[0], 0)
+        nb, B = g.shape[0], g.shape[1]
+        out = _ConvFusedBwd.apply(g.reshape(nb * B, *g.shape[2:]), mod, (nb * B,) + tuple(in_shape[1:]), need_dx, scale, y,
+                                  nb * reps)
+        if out.numel() == 0:
+            return out, None
+        return out.view(nb, B, *out.shape[1:]), 0
+
+
+class _ConvAffine(torch.autograd.Function):
+    """``affine(conv(x))`` given the convolution output ``t1`` (already computed by ``_Conv``): forward is the affine map
+    alone, the reverse pass runs scale + operand split + backward-data convolution as one fused chain."""
+
+    @staticmethod
+    def forward(x, weight, mod, t1, scale, shift):
+        return t1 * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        x, weight, mod, t1, scale, shift = inputs
+        ctx.mod, ctx.in_shape = mod, tuple(x.shape)
+        ctx.save_for_backward(scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        need = bool(ctx.needs_input_grad[0])
+        gx = _ConvFusedBwd.apply(g, ctx.mod, ctx.in_shape, need, ctx.saved_tensors[0], None, 1)
+        return (gx if need else None), None, None, None, None, None
+
+
+class _ConvAffineRelu(torch.autograd.Function):
+    """``relu(affine?(conv(x)))`` given the pre-activation ``t2``; ``scale`` is ``None`` without a BatchNorm."""
+
+    @staticmethod
+    def forward(x, weight, mod, t2, scale):
+        return torch.relu(t2)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        x, weight, mod, t2, scale = inputs
+        ctx.mod, ctx.in_shape, ctx.has_scale = mod, tuple(x.shape), scale is not None
+        if scale is not None:
+            ctx.save_for_backward(output, scale)
+        else:
+            ctx.save_for_backward(output)
+
+    @staticmethod
+    def backward(ctx, g):
+        need = bool(ctx.needs_input_grad[0])
+        y = ctx.saved_tensors[0]
+        scale = ctx.saved_tensors[1] if ctx.has_scale else None
+        gx = _ConvFusedBwd.apply(g, ctx.mod, ctx.in_shape, need, scale, y, 1)
+        return (gx if need else None), None, None, None, None
+
+
+def _tag(t: torch.Tensor, info: tuple) -> torch.Tensor:
+    t._lpb_tag = info
+    return t
 
 
 def supported(mod: nn.Module) -> bool:
@@ -428,7 +551,11 @@ class patched_convs:
     ``native_batch_norm_backward``, whose vmap rule folds the column dimension into channels with two physical
     copies of the C-times-batched gradient (19 % of a step in profiles/r01_launches_conv_engine_implicit.md)."""
 
-    def __init__(self, model: nn.Module):
+    def __init__(self, model: nn.Module, fuse: bool = False):
+        # fuse: chain conv -> frozen BN -> ReLU (each optional after the conv) into one reverse-pass node per
+        # convolution (``_ConvAffine`` / ``_ConvAffineRelu``).  The per-layer output gradients are then not available
+        # as tensors -- only as the packed rows in ``STASH`` -- so only the KFAC path of the backend asks for it.
+        self.fuse = fuse
         self.mods = [m for m in model.modules() if supported(m)]
         self.bns = [m for m in model.modules() if _frozen_eval_bn(m)]
         self.linears = [m for m in model.modules() if type(m) is nn.Linear and m.in_features >= 16 and m.out_features >= 16]
@@ -440,7 +567,10 @@ class patched_convs:
             def fwd(x, m=m):
                 if x.dtype != torch.float32 or not x.is_cuda and not _ALLOW_CPU:
                     return nn.Conv2d.forward(m, x)
-                return _Conv.apply(x, m.weight, m)
+                out = _Conv.apply(x, m.weight, m)
+                if self.fuse and x.shape[0] >= ELEMENTWISE_MIN_BATCH:
+                    _tag(out, ("conv", m, x))
+                return out
             m.forward = fwd
         def usable(x):
             return x.dtype == torch.float32 and (x.is_cuda or _ALLOW_CPU)
@@ -452,6 +582,12 @@ class patched_convs:
                 scale, shift = _bn_affine(m)
                 if x.shape[0] < ELEMENTWISE_MIN_BATCH:
                     return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+                tag = getattr(x, "_lpb_tag", None)
+                if self.fuse and tag is not None and tag[0] == "conv":
+                    _, cm, xin = tag
+                    STASH.setdefault(id(cm), {})["fused"] = True
+                    out = _ConvAffine.apply(xin, cm.weight, cm, x.detach(), scale, shift)
+                    return _tag(out, ("conv_affine", cm, xin, scale))
                 return _Affine.apply(x, scale, shift)
             m.forward = bn_fwd
         for m in self.linears:
@@ -460,7 +596,14 @@ class patched_convs:
             m.forward = lin_fwd
         for m in self.relus:
             def relu_fwd(x, m=m):
-                return _Relu.apply(x) if (usable(x) and x.shape[0] >= ELEMENTWISE_MIN_BATCH) else nn.ReLU.forward(m, x)
+                if not (usable(x) and x.shape[0] >= ELEMENTWISE_MIN_BATCH):
+                    return nn.ReLU.forward(m, x)
+                tag = getattr(x, "_lpb_tag", None)
+                if self.fuse and tag is not None and x.dim() == 4:
+                    cm, xin = tag[1], tag[2]
+                    STASH.setdefault(id(cm), {})["fused"] = True
+                    return _ConvAffineRelu.apply(xin, cm.weight, cm, x.detach(), tag[3] if tag[0] == "conv_affine" else None)
+                return _Relu.apply(x)
             m.forward = relu_fwd
         for m, geom in self.pools:
             def pool_fwd(x, m=m, geom=geom):

@@ -63,6 +63,8 @@ void set_gemm_pair_mode(int mode);
 int syrk_conv_patches(const void*, const void*, int64_t, int64_t, int, int, int, int, int, int, int, float, int, float*, int64_t,
                       int, cudaStream_t);
 int taps_to_param_accumulate(const float*, int64_t, int, int, float*, int64_t, cudaStream_t);
+int pack_cast_fused(const float*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, void*, void*, int,
+                    int64_t, cudaStream_t);
 int col2im_nhwc(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
 int maxpool2d_bwd_nhwc(const float*, const int64_t*, float*, int64_t, int, int, int, int, int, int, int, int, int, cudaStream_t);
 }  // namespace lpb
@@ -175,6 +177,12 @@ int lpb_syrk_conv_patches_tc(const void* X_hi, const void* X_lo, int64_t ldx, in
 int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int KK, float* out, int64_t ldo, void* stream) {
   LPB_REQUIRE(ldt >= (int64_t)Ci * KK && ldo >= (int64_t)Ci * KK, "lpb_taps_to_param_accumulate: leading dimension too small");
   return lpb::taps_to_param_accumulate(T, ldt, Ci, KK, out, ldo, ST(stream));
+}
+
+int lpb_pack_cast_fused(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* scale, const float* y,
+                        int64_t rows_y, int64_t ld_y, void* dst_hi, void* dst_lo, int out_kind, int64_t ld, void* stream) {
+  LPB_REQUIRE(ld_src >= cols && ld >= cols, "lpb_pack_cast_fused: leading dimension too small");
+  return lpb::pack_cast_fused(src, rows, cols, ld_src, scale, y, rows_y, ld_y, dst_hi, dst_lo, out_kind, ld, ST(stream));
 }
 
 int lpb_col2im_nhwc(const float* Dc, int64_t ldd, int Q, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW,

@@ -385,6 +385,92 @@ __global__ void __launch_bounds__(256) pack_cast_vec8_kernel(const float* __rest
   }
 }
 
+// pack_cast with the two element-wise maps that precede a convolution's reverse pass fused in:
+//     dst[r, c] = split( src[r, c] * scale[c] * (y[r % rows_y, c] > 0) )
+// scale (frozen BatchNorm as a per-channel affine map) and y (forward output of the ReLU, shared by the rows_y-periodic
+// curvature columns) are optional.  One pass over the gradient instead of three (relu_bwd, scale_channels, pack_cast),
+// and the fp32 intermediates are never written.
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(256) pack_cast_fused_kernel(const float* __restrict__ src, int64_t rows, int64_t colsv,
+                                                               int64_t ld_src, const float* __restrict__ scale,
+                                                               const float* __restrict__ y, int64_t rows_y, int64_t ld_y,
+                                                               void* hi, void* lo, int64_t ld) {
+  constexpr int V = VEC ? 8 : 1;
+  const int64_t total = rows * colsv;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / colsv, c = (e - r * colsv) * V;
+    float v[V];
+    if (VEC) {
+      const float4 a = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+      const float4 b = *reinterpret_cast<const float4*>(src + r * ld_src + c + 4);
+      v[0] = a.x; v[1 % V] = a.y; v[2 % V] = a.z; v[3 % V] = a.w; v[4 % V] = b.x; v[5 % V] = b.y; v[6 % V] = b.z; v[7 % V] = b.w;
+    } else {
+      v[0] = src[r * ld_src + c];
+    }
+    if (scale) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[i] *= __ldg(scale + c + i);
+    }
+    if (y) {
+      const float* yp = y + (r % rows_y) * ld_y + c;
+      if (VEC) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(yp));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(yp + 4));
+        const float m[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[i] = m[i] > 0.f ? v[i] : 0.f;
+      } else {
+        v[0] = __ldg(yp) > 0.f ? v[0] : 0.f;
+      }
+    }
+    if (VEC) {
+      alignas(16) unsigned short h[8], l[8];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        if constexpr (KIND == OUT_F16_HILO) {
+          const __half hh = __float2half_rn(v[i]);
+          h[i] = __half_as_ushort(hh);
+          l[i] = __half_as_ushort(__float2half_rn(v[i] - __half2float(hh)));
+        } else {
+          const __nv_bfloat16 hh = __float2bfloat16_rn(v[i]);
+          h[i] = __bfloat16_as_ushort(hh);
+          l[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v[i] - __bfloat162float(hh)));
+        }
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(hi) + r * ld + c) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(lo) + r * ld + c) = *reinterpret_cast<const uint4*>(l);
+    } else {
+      store_packed<KIND>(hi, lo, r * ld + c, v[0]);
+    }
+  }
+}
+
+int pack_cast_fused(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* scale, const float* y,
+                    int64_t rows_y, int64_t ld_y, void* hi, void* lo, int kind, int64_t ld, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return 0;
+  LPB_REQUIRE(kind < OUT_BF16_HILO || lo != nullptr, "pack_cast_fused: hi+lo output needs a lo buffer");
+  LPB_REQUIRE(y == nullptr || (rows_y > 0 && rows % rows_y == 0 && ld_y >= cols),
+              "pack_cast_fused: mask rows must divide the gradient rows");
+  if (y == nullptr) rows_y = 1;
+  const bool vec = (kind == OUT_BF16_HILO || kind == OUT_F16_HILO) && cols % 8 == 0 && ld_src % 4 == 0 && ld % 8 == 0 &&
+                   ((uintptr_t)src % 16) == 0 && ((uintptr_t)hi % 16) == 0 && ((uintptr_t)lo % 16) == 0 &&
+                   (y == nullptr || (ld_y % 4 == 0 && ((uintptr_t)y % 16) == 0));
+  if (vec) {
+    const int64_t total = rows * (cols / 8);
+    const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
+    if (kind == OUT_F16_HILO)
+      pack_cast_fused_kernel<OUT_F16_HILO, true><<<blocks, 256, 0, st>>>(src, rows, cols / 8, ld_src, scale, y, rows_y, ld_y, hi, lo, ld);
+    else
+      pack_cast_fused_kernel<OUT_BF16_HILO, true><<<blocks, 256, 0, st>>>(src, rows, cols / 8, ld_src, scale, y, rows_y, ld_y, hi, lo, ld);
+  } else {
+    const int blocks = (int)imin(ceil_div(rows * cols, 256), (int64_t)sm_count() * 32);
+    DISPATCH_KIND(kind, (pack_cast_fused_kernel<KIND, false><<<blocks, 256, 0, st>>>(src, rows, cols, ld_src, scale, y, rows_y,
+                                                                                   ld_y, hi, lo, ld)));
+  }
+  LPB_CHECK_LAUNCH("pack_cast_fused");
+  return 0;
+}
+
 int pack_cast(const float* src, int64_t rows, int64_t cols, int64_t ld_src, void* hi, void* lo, int kind, int64_t ld,
               cudaStream_t st) {
   if (rows == 0 || cols == 0) return 0;

@@ -295,6 +295,29 @@ def pack_cast(src: torch.Tensor, kind: int) -> Packed:
     return out
 
 
+def pack_cast_fused(src: torch.Tensor, kind: int, scale: torch.Tensor | None = None, y: torch.Tensor | None = None) -> Packed:
+    """``pack_cast(src * scale[None, :] * (y > 0))`` in one pass: ``src [rows, cols]`` fp32, ``scale [cols]`` (frozen
+    BatchNorm as an affine map), ``y [rows_y, cols]`` (ReLU output, ``rows % rows_y == 0``: shared by the folded
+    curvature columns).  Either may be ``None``."""
+    _check(src, name="src")
+    assert src.dim() == 2 and src.stride(1) == 1
+    rows, cols = src.shape
+    rows_y = ld_y = 0
+    if y is not None:
+        _check(y, name="y")
+        assert y.dim() == 2 and y.stride(1) == 1 and y.shape[1] == cols and rows % y.shape[0] == 0
+        rows_y, ld_y = y.shape[0], y.stride(0)
+    if scale is not None:
+        _check(scale, name="scale")
+        scale = scale.contiguous()
+        assert scale.numel() == cols
+    out = alloc_rows(rows, cols, kind, src.device)
+    _lib.call("lpb_pack_cast_fused", _ptr(src), rows, cols, src.stride(0), _ptr(scale), _ptr(y), rows_y, ld_y, _ptr(out.hi),
+              _ptr(out.lo), out.kind, out.ldk, _stream())
+    _bump()
+    return out
+
+
 def col2im(Dc: torch.Tensor, in_shape, mod) -> torch.Tensor:
     """``Dc [C_in*kh*kw, Q*OH*OW]`` -> ``grad_in [Q, C_in, H, W]``."""
     _check(Dc, name="Dc")

@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "col2im_nhwc", "syrk_conv_patches", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -197,6 +197,15 @@ def pack_cast(src, kind):
     out = _alloc(src.shape[0], src.shape[1], kind, src.device)
     out.hi[:, :src.shape[1]] = src.float()
     return out
+
+
+def pack_cast_fused(src, kind, scale=None, y=None):
+    v = src.float()
+    if scale is not None:
+        v = v * scale.view(1, -1)
+    if y is not None:
+        v = (v.reshape(-1, y.shape[0], y.shape[1]) * (y > 0)).reshape(v.shape)
+    return pack_cast(v, kind)
 
 
 def col2im(Dc, in_shape, mod):

@@ -301,3 +301,22 @@ def test_gemm_cta_pair_tiles(M, N, Kc, kind, tol, rows, mode):
             assert (sym.diagonal() >= 0).all()
     finally:
         K.set_gemm_tile_mode(-1)
+
+
+@pytest.mark.parametrize("shape", [(640, 64), (96, 24), (130, 7), (4096, 512)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16X3, 2e-5), (K.F16X3, 5e-7), (K.BF16, 4e-3), (K.F32, 0.0)])
+def test_pack_cast_fused(shape, kind, tol):
+    """ReLU mask (shared by the folded columns) x BatchNorm scale x operand split in one pass == the three separate maps."""
+    rows, cols = shape
+    torch.manual_seed(12)
+    reps = 5 if rows % 5 == 0 else 2
+    g = torch.randn(rows, cols, device=DEV)
+    y = torch.randn(rows // reps, cols, device=DEV).clamp_min(0)
+    scale = torch.rand(cols, device=DEV) + 0.5
+    ref = (g.view(reps, rows // reps, cols) * (y > 0)).view(rows, cols) * scale
+    for sc, yy, want in ((scale, y, ref), (None, y, (g.view(reps, -1, cols) * (y > 0)).view(rows, cols)), (scale, None, g * scale),
+                         (None, None, g)):
+        p = K.pack_cast_fused(g, kind, sc, yy)
+        got = p.hi[:, :cols].float() + (p.lo[:, :cols].float() if p.lo is not None else 0)
+        err = float((got - want).norm() / want.norm())
+        assert err <= tol, (err, sc is None, yy is None)

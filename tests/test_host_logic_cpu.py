@@ -140,6 +140,10 @@ def test_convolution_engine_paths_on_model_zoo(cpu_kernels, monkeypatch, name, k
     be = B200GGN(model, "classification")
     _, kron = be.kron(X, y, N=4)
     assert be.last_backward_mode == "batched"
+    # conv -> frozen BN -> ReLU chains run as one fused reverse node; the reduced WideResNet adds the raw stem output
+    # to a residual (a second consumer of a fused intermediate): detected, repeated unfused, and remembered
+    assert be.fuse_elementwise == (name != "wrn28_10")
+    assert be._fused == (name != "wrn28_10")
     _, kf = co.kfac_factors(model, "classification", X, y, N=4)
     worst = max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo))
     assert worst < 1e-5, worst
