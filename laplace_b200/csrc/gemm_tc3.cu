@@ -255,14 +255,22 @@ void persistent_schedule(int64_t tiles, int total_kchunks, int ctas, bool allow_
   const double EPI = 3.0;   // one item's output pass, in k-chunk equivalents (mostly hidden behind the next item)
   double best = 1e300, cost1 = 1e300;
   int best_s = 1;
-  const int max_s = (int)imin(total_kchunks, 16384);
-  for (int s = 1; s <= max_s; ++s) {
-    const int kps = (int)ceil_div(total_kchunks, s);
-    if ((int)ceil_div(total_kchunks, kps) != s) continue;
+  auto consider = [&](int64_t s64) {
+    if (s64 < 1 || s64 > total_kchunks) return;
+    const int kps = (int)ceil_div(total_kchunks, s64);
+    const int s = (int)ceil_div(total_kchunks, kps);   // the split count this chunk size really produces
     const double waves = (double)ceil_div(tiles * s, (int64_t)ctas);
     const double cost = waves * (kps + EPI);
     if (s == 1) cost1 = cost;
-    if (cost < best * 0.999) { best = cost; best_s = s; }
+    if (cost < best * 0.999 || (cost < best * 1.001 && s < best_s)) { best = cost; best_s = s; }
+  };
+  // only split counts that fill w waves exactly (or nearly) can be optimal: s = floor(w * ctas / tiles), w = 1, 2, ...
+  consider(1);
+  for (int w = 1; w <= 64; ++w) {
+    const int64_t s = (int64_t)w * ctas / tiles;
+    consider(s);
+    consider(s + 1);
+    if (s >= total_kchunks) break;
   }
   // overwrite semantics: plain stores (no memset, no atomics) if a single split is nearly as good
   if (allow_single_store && cost1 <= 1.15 * best) best_s = 1;
