@@ -124,15 +124,17 @@ int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W
 
 /* ---- KFAC input factor of a stride-1 'same' convolution without im2col -----------------------------------------
  * D[(t,ci),(t',cj)] (+)= alpha * sum_{n,h,w} x[n,h+kh-PH,w+kw-PW,ci] * x[n,h+kh'-PH,w+kw'-PW,cj]   (zero padding),
- * t = kh*KW + kw (tap-major feature order, d = KH*KW*Ci), x given as 16-bit hi(/lo) NHWC rows [(n,h,w), Ci] (ldx).
+ * t = kh*KW + kw, feature (t,ci) at index t*Ci_pad + ci with Ci_pad = Ci rounded up to 64 (D is [KH*KW*Ci_pad]^2, padded
+ * rows / columns exactly zero); x given as 16-bit hi(/lo) NHWC rows [(n,h,w), Ci] (ldx).
  * Replaces unfold + einsum("b t i, b t j -> i j") behind reference laplace/curvature/curvlinops.py:100 for those
  * layers; the 9x larger patch matrix is never formed (shifted 4-D TMA boxes feed the tensor cores directly).
- * Needs Ci % 64 == 0, H*W dividing 64 or (W | 64 and 64/W | H).  D is symmetric (both triangles written).      */
+ * Needs H*W dividing 64 or (W | 64 and 64/W | H).  D is symmetric (both triangles written).                      */
 int lpb_syrk_conv_patches_tc(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q, int H, int W, int Ci, int KH, int KW,
                              int PH, int PW, float alpha, int accumulate, float* D, int64_t ldd, int fp16_operands,
                              void* stream);
-/* out[(ci*KK+t), (cj*KK+t')] += T[(t*Ci+ci), (t'*Ci+cj)]: tap-major factor -> parameter order (ci,kh,kw), KK <= 9 */
-int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int KK, float* out, int64_t ldo, void* stream);
+/* out[(ci*KK+t), (cj*KK+t')] += T[(t*Ci_pad+ci), (t'*Ci_pad+cj)]: tap-major factor -> parameter order (ci,kh,kw), KK <= 9 */
+int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
+                                 void* stream);
 
 /* ---- reverse-pass element-wise maps of the convolution engine (columns folded into the batch) -----------------
  * out[i] = g[i] * scale[(i / inner) % C]                 frozen BatchNorm as per-channel affine map (backward)   */

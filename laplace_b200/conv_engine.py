@@ -84,12 +84,17 @@ class FusionConflict(RuntimeError):
 
 
 def implicit_ok(mod: nn.Conv2d, H: int, W: int) -> bool:
-    """Stride-1 'same' convolutions whose images tile a 128-row MMA block: no im2col / col2im at all."""
+    """Stride-1 'same' convolutions whose images tile 128-row MMA blocks -- whole images (``H*W`` divides 128) or
+    ``128 / W`` image rows of a larger image: no im2col / col2im at all."""
     kh, kw = mod.kernel_size
     if not USE_IMPLICIT:
         return False
-    return (tuple(mod.stride) == (1, 1) and tuple(mod.dilation) == (1, 1) and 2 * mod.padding[0] == kh - 1
-            and 2 * mod.padding[1] == kw - 1 and H * W <= 128 and 128 % (H * W) == 0)
+    if not (tuple(mod.stride) == (1, 1) and tuple(mod.dilation) == (1, 1) and 2 * mod.padding[0] == kh - 1
+            and 2 * mod.padding[1] == kw - 1):
+        return False
+    if H * W <= 128:
+        return 128 % (H * W) == 0
+    return W <= 128 and 128 % W == 0 and H % (128 // W) == 0
 
 
 def nhwc_rows(x: torch.Tensor, kind: int) -> K.Packed:
@@ -517,6 +522,11 @@ def _frozen_eval_bn(m: nn.Module) -> bool:
 # The custom element-wise Functions trade ~0.15 ms of host time per call (functorch dispatch of a Python
 # autograd.Function) for 2-4x less device time on the folded C x B gradients: worth it once a step is device-bound.
 ELEMENTWISE_MIN_BATCH = 1024
+ELEMENTWISE_MIN_NUMEL = 1 << 23   # ... or a single activation of >= 8 M elements (wide layers at small batch)
+
+
+def _device_bound(x: torch.Tensor) -> bool:
+    return x.shape[0] >= ELEMENTWISE_MIN_BATCH or x.numel() >= ELEMENTWISE_MIN_NUMEL
 
 _BN_CACHE: dict = {}
 
@@ -568,7 +578,7 @@ class patched_convs:
                 if x.dtype != torch.float32 or not x.is_cuda and not _ALLOW_CPU:
                     return nn.Conv2d.forward(m, x)
                 out = _Conv.apply(x, m.weight, m)
-                if self.fuse and x.shape[0] >= ELEMENTWISE_MIN_BATCH:
+                if self.fuse and _device_bound(x):
                     _tag(out, ("conv", m, x))
                 return out
             m.forward = fwd
@@ -580,7 +590,7 @@ class patched_convs:
                 if x.dim() != 4 or not usable(x):
                     return nn.BatchNorm2d.forward(m, x)
                 scale, shift = _bn_affine(m)
-                if x.shape[0] < ELEMENTWISE_MIN_BATCH:
+                if not _device_bound(x):
                     return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
                 tag = getattr(x, "_lpb_tag", None)
                 if self.fuse and tag is not None and tag[0] == "conv":
@@ -596,7 +606,7 @@ class patched_convs:
             m.forward = lin_fwd
         for m in self.relus:
             def relu_fwd(x, m=m):
-                if not (usable(x) and x.shape[0] >= ELEMENTWISE_MIN_BATCH):
+                if not (usable(x) and _device_bound(x)):
                     return nn.ReLU.forward(m, x)
                 tag = getattr(x, "_lpb_tag", None)
                 if self.fuse and tag is not None and x.dim() == 4:
@@ -607,7 +617,7 @@ class patched_convs:
             m.forward = relu_fwd
         for m, geom in self.pools:
             def pool_fwd(x, m=m, geom=geom):
-                if x.dim() != 4 or not usable(x) or x.shape[0] < ELEMENTWISE_MIN_BATCH or x.shape[2] * x.shape[3] > 1024:
+                if x.dim() != 4 or not usable(x) or not _device_bound(x) or x.shape[2] * x.shape[3] > 1024:
                     return nn.MaxPool2d.forward(m, x)
                 return _MaxPool.apply(x, *geom)[0]
             m.forward = pool_fwd

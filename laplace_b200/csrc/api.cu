@@ -62,7 +62,7 @@ int eigh_jacobi(const float*, int, int, float*, float*, int, cudaStream_t);
 void set_gemm_pair_mode(int mode);
 int syrk_conv_patches(const void*, const void*, int64_t, int64_t, int, int, int, int, int, int, int, float, int, float*, int64_t,
                       int, cudaStream_t);
-int taps_to_param_accumulate(const float*, int64_t, int, int, float*, int64_t, cudaStream_t);
+int taps_to_param_accumulate(const float*, int64_t, int, int, int, float*, int64_t, cudaStream_t);
 int pack_cast_fused(const float*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, void*, void*, int,
                     int64_t, cudaStream_t);
 int col2im_nhwc(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
@@ -174,9 +174,10 @@ int lpb_syrk_conv_patches_tc(const void* X_hi, const void* X_lo, int64_t ldx, in
                                 ST(stream));
 }
 
-int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int KK, float* out, int64_t ldo, void* stream) {
-  LPB_REQUIRE(ldt >= (int64_t)Ci * KK && ldo >= (int64_t)Ci * KK, "lpb_taps_to_param_accumulate: leading dimension too small");
-  return lpb::taps_to_param_accumulate(T, ldt, Ci, KK, out, ldo, ST(stream));
+int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
+                                 void* stream) {
+  LPB_REQUIRE(ldt >= (int64_t)Ci_pad * KK && ldo >= (int64_t)Ci * KK, "lpb_taps_to_param_accumulate: leading dimension too small");
+  return lpb::taps_to_param_accumulate(T, ldt, Ci, Ci_pad, KK, out, ldo, ST(stream));
 }
 
 int lpb_pack_cast_fused(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* scale, const float* y,

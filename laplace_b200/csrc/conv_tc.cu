@@ -146,7 +146,7 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
                                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                                int64_t Mrows, int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile, int KH,
                                int KW, int base_h, int base_w, int sgn, int kchunks, int num_stages, int fp16_operands, int bn,
-                               int tiles_n, int num_items) {
+                               int tiles_n, int num_items, int tiles_per_img, int rows_per_tile) {
   const int B_BYTES = bn * BK * 2;
   const int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (TILE_BYTES + B_BYTES);
   const int OFF_B_HI = TILE_BYTES, OFF_A_LO = TILE_BYTES + B_BYTES, OFF_B_LO = 2 * TILE_BYTES + B_BYTES;
@@ -183,14 +183,16 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const int tm = item / tiles_n, tn = item - tm * tiles_n;
-        const int q0 = tm * q_per_tile;
+        // small images: a tile is q_per_tile whole images; large images: rows_per_tile image rows of one image
+        int q0 = tm * q_per_tile, h0 = 0;
+        if (tiles_per_img > 0) { q0 = tm / tiles_per_img; h0 = (tm - q0 * tiles_per_img) * rows_per_tile; }
         for (int it = 0; it < total; ++it) {
           const int tap = it / kchunks, kc = it - tap * kchunks;
           const int kh = tap / KW, kw = tap - kh * KW;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int ch = base_h + sgn * kh, cw = base_w + sgn * kw;
+          const int ch = h0 + base_h + sgn * kh, cw = base_w + sgn * kw;
           tma_load_4d(&tmX_hi, &full_bar[stage], st, kc * BK, cw, ch, q0);
           tma_load_2d(&tmW_hi, &full_bar[stage], st + OFF_B_HI, kc * BK, tap * N + tn * bn);
           if (NPROD == 3) {
@@ -300,12 +302,13 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
 
 }  // namespace tc
 
-static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int64_t Q, int H, int W, int64_t Kc, int64_t ld, int q_per_tile) {
+static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int64_t Q, int H, int W, int64_t Kc, int64_t ld, int q_per_tile,
+                          int box_h = 0) {
   PFN_encodeTiled enc = get_tensormap_encoder();
   LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)Kc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Q};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)W, (cuuint32_t)H, (cuuint32_t)q_per_tile};
+  cuuint32_t box[4] = {(cuuint32_t)tc::BK, (cuuint32_t)W, (cuuint32_t)(box_h > 0 ? box_h : H), (cuuint32_t)q_per_tile};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -319,24 +322,27 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
                    const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
                    float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
   LPB_REQUIRE(Q > 0 && H > 0 && W > 0 && Kc > 0 && N > 0 && KH > 0 && KW > 0, "conv_nhwc_bf16: bad extents");
-  LPB_REQUIRE(H * W <= 128 && 128 % (H * W) == 0, "conv_nhwc_bf16: H*W must divide 128 (got %dx%d)", H, W);
+  const bool big = H * W > 128;   // tiles of 128 / W image rows instead of whole images
+  LPB_REQUIRE(big ? (128 % W == 0 && H % (128 / W) == 0) : (128 % (H * W) == 0),
+              "conv_nhwc_bf16: %dx%d images do not tile 128-row blocks", H, W);
   LPB_REQUIRE((ldx % 8) == 0 && (ldw % 8) == 0 && ldx >= Kc && ldw >= Kc, "conv_nhwc_bf16: bad leading dimensions");
   LPB_REQUIRE((X_lo == nullptr) == (W_lo == nullptr), "conv_nhwc_bf16: lo operands must both be given or both NULL");
   LPB_REQUIRE(ldd >= N, "conv_nhwc_bf16: ldd too small");
   const bool x3 = X_lo != nullptr;
-  const int q_per_tile = 128 / (H * W);
+  const int q_per_tile = big ? 1 : 128 / (H * W);
+  const int rows_per_tile = big ? 128 / W : H, tiles_per_img = big ? H / rows_per_tile : 0;
   CUtensorMap tX_hi, tX_lo, tW_hi, tW_lo;
   const int bn = N <= 64 ? 64 : 128;
-  if (make_tmap_nhwc(&tX_hi, X_hi, Q, H, W, Kc, ldx, q_per_tile)) return 1;
+  if (make_tmap_nhwc(&tX_hi, X_hi, Q, H, W, Kc, ldx, q_per_tile, rows_per_tile)) return 1;
   if (make_tmap_2d(&tW_hi, W_hi, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
   if (x3) {
-    if (make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile)) return 1;
+    if (make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile, rows_per_tile)) return 1;
     if (make_tmap_2d(&tW_lo, W_lo, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
   } else {
     tX_lo = tX_hi; tW_lo = tW_hi;
   }
   const int64_t Mrows = Q * H * W;
-  const int64_t tiles_m = ceil_div(Q, q_per_tile);
+  const int64_t tiles_m = big ? Q * tiles_per_img : ceil_div(Q, q_per_tile);
   const int tiles_n = (int)ceil_div(N, bn);
   LPB_REQUIRE(tiles_m <= 2147483647LL && tiles_n <= 65535, "conv_nhwc_bf16: too many tiles");
   const int kchunks = (int)ceil_div(Kc, tc::BK);
@@ -383,14 +389,15 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
     if (x3)
       tc::conv_nhwc_tc_persistent_kernel<3><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
           tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, KH, KW, base_h, base_w, sgn, kchunks, pstages,
-          fp16_operands, bn, tiles_n, (int)items);
+          fp16_operands, bn, tiles_n, (int)items, tiles_per_img, rows_per_tile);
     else
       tc::conv_nhwc_tc_persistent_kernel<1><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
           tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, KH, KW, base_h, base_w, sgn, kchunks, pstages,
-          fp16_operands, bn, tiles_n, (int)items);
+          fp16_operands, bn, tiles_n, (int)items, tiles_per_img, rows_per_tile);
     LPB_CHECK_LAUNCH("conv_nhwc_bf16 (persistent)");
     return 0;
   }
+  LPB_REQUIRE(!big, "conv_nhwc_bf16: images larger than 128 pixels need the persistent kernel (LPB_CONV_MODE unset)");
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
   if (x3)
     tc::conv_nhwc_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,

@@ -342,13 +342,15 @@ static int make_tmap_patches(CUtensorMap* map, const void* ptr, int64_t Q, int H
 int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q, int H, int W, int Ci, int KH, int KW, int PH,
                       int PW, float alpha, int accumulate, float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
   LPB_REQUIRE(Q > 0 && H > 0 && W > 0 && Ci > 0 && KH > 0 && KW > 0, "syrk_conv_patches: bad extents");
-  LPB_REQUIRE(Ci % 64 == 0, "syrk_conv_patches: C_in must be a multiple of 64 (got %d)", Ci);
   LPB_REQUIRE(2 * PH == KH - 1 && 2 * PW == KW - 1, "syrk_conv_patches: stride-1 'same' convolutions only");
   LPB_REQUIRE((ldx % 8) == 0 && ldx >= Ci && ((uintptr_t)X_hi % 16) == 0 && ((uintptr_t)X_lo % 16) == 0,
               "syrk_conv_patches: operand rows must be 16-byte aligned");
   const int HW = H * W;
   tc::PatchGeom pg = {};
-  pg.KW = KW; pg.PH = PH; pg.PW = PW; pg.Ci = Ci; pg.num_taps = KH * KW; pg.blocks_per_tap = Ci / 64;
+  // channel counts that are not a multiple of 64 are padded per tap: feature (t, ci) sits at t * Ci_pad + ci, the
+  // TMA unit zero-fills channel coordinates >= Ci, so the padded rows / columns of D come out exactly zero
+  const int Ci_pad = (int)ceil_div(Ci, 64) * 64;
+  pg.KW = KW; pg.PH = PH; pg.PW = PW; pg.Ci = Ci; pg.num_taps = KH * KW; pg.blocks_per_tap = Ci_pad / 64;
   int box_h, box_n;
   if (HW >= 64) {
     LPB_REQUIRE(64 % W == 0 && H % (64 / W) == 0, "syrk_conv_patches: %dx%d images do not tile 64-row chunks", H, W);
@@ -359,8 +361,8 @@ int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q
     pg.rows_per_chunk = H; pg.chunks_per_img = 0; pg.imgs_per_chunk = 64 / HW;
     box_h = H; box_n = pg.imgs_per_chunk;
   }
-  const int64_t d = (int64_t)KH * KW * Ci;
-  LPB_REQUIRE(ldd >= d, "syrk_conv_patches: ldd too small");
+  const int64_t d = (int64_t)KH * KW * Ci_pad;
+  LPB_REQUIRE(ldd >= d, "syrk_conv_patches: ldd too small (D is [KH*KW*Ci_pad]^2, Ci_pad = C_in rounded up to 64)");
   const int64_t kchunks64 = HW >= 64 ? Q * pg.chunks_per_img : ceil_div(Q, (int64_t)pg.imgs_per_chunk);
   LPB_REQUIRE(kchunks64 < (1LL << 31), "syrk_conv_patches: too many sample rows");
   const int total_kchunks = (int)kchunks64;
@@ -384,9 +386,10 @@ int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q
                                    total_kchunks, kps, nsplit, 0, fp16_operands, sms, st, &pg);
 }
 
-// out[(ci*KK + t), (cj*KK + t')] += T[(t*Ci + ci), (t'*Ci + cj)]   (KK = KH*KW <= 9).  One CTA per (ci, 32 cj's):
-// the KK x KK x 32 block is read in 128-byte runs, staged in shared memory and written as KK runs of 32*KK floats.
-__global__ void __launch_bounds__(256) taps_to_param_kernel(const float* __restrict__ T, int64_t ldt, int Ci, int KK,
+// out[(ci*KK + t), (cj*KK + t')] += T[(t*Cp + ci), (t'*Cp + cj)]   (KK = KH*KW <= 9, Cp = padded channel stride of T).
+// One CTA per (ci, 32 cj's): the KK x KK x 32 block is read in 128-byte runs, staged in shared memory and written as
+// KK runs of 32*KK floats.
+__global__ void __launch_bounds__(256) taps_to_param_kernel(const float* __restrict__ T, int64_t ldt, int Ci, int Cp, int KK,
                                                             float* __restrict__ out, int64_t ldo) {
   __shared__ float s[9 * 9 * 32];
   const int ci = blockIdx.y, cj0 = blockIdx.x * 32;
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(256) taps_to_param_kernel(const float* __restr
   for (int e = threadIdx.x; e < KK * KK * 32; e += blockDim.x) {
     const int cjl = e & 31, tt = e >> 5;          // tt = t * KK + t'
     const int t = tt / KK, t2 = tt - t * KK;
-    if (cjl < ncj) s[e] = T[(int64_t)(t * Ci + ci) * ldt + t2 * Ci + cj0 + cjl];
+    if (cjl < ncj) s[e] = T[(int64_t)(t * Cp + ci) * ldt + t2 * Cp + cj0 + cjl];
   }
   __syncthreads();
   const int run = ncj * KK;
@@ -406,11 +409,13 @@ __global__ void __launch_bounds__(256) taps_to_param_kernel(const float* __restr
   }
 }
 
-int taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int KK, float* out, int64_t ldo, cudaStream_t st) {
+int taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
+                             cudaStream_t st) {
+  LPB_REQUIRE(Ci_pad >= Ci, "taps_to_param_accumulate: padded channel stride smaller than the channel count");
   LPB_REQUIRE(KK >= 1 && KK <= 9, "taps_to_param_accumulate: kernel window larger than 9 taps");
   LPB_REQUIRE(Ci > 0 && Ci <= 65535, "taps_to_param_accumulate: bad channel count");
   dim3 grid((unsigned)ceil_div(Ci, 32), (unsigned)Ci);
-  taps_to_param_kernel<<<grid, 256, 0, st>>>(T, ldt, Ci, KK, out, ldo);
+  taps_to_param_kernel<<<grid, 256, 0, st>>>(T, ldt, Ci, Ci_pad, KK, out, ldo);
   LPB_CHECK_LAUNCH("taps_to_param_accumulate");
   return 0;
 }

@@ -368,8 +368,9 @@ def gemm_tn(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumul
 
 
 def conv_patches_ok(Ci: int, H: int, W: int, kh: int, kw: int) -> bool:
-    """Shapes ``syrk_conv_patches`` accepts (64-channel feature blocks, images tiling 64-row chunks, <= 9 taps)."""
-    if Ci % 64 or kh * kw > 9:
+    """Shapes ``syrk_conv_patches`` accepts (images tiling 64-row chunks, <= 9 taps) and pays off on (channel padding
+    to 64 per tap wastes at most ~1/3 of the tensor work)."""
+    if kh * kw > 9 or Ci < 48 or (-(-Ci // 64) * 64) > 1.34 * Ci:
         return False
     hw = H * W
     return (64 % hw == 0) if hw < 64 else (64 % W == 0 and H % (64 // W) == 0)
@@ -383,11 +384,13 @@ def syrk_conv_patches(X: Packed, Q: int, H: int, W: int, mod, out: torch.Tensor,
     kh, kw = mod.kernel_size
     Ci = X.K
     d = Ci * kh * kw
+    Ci_pad = -(-Ci // 64) * 64
+    dp = Ci_pad * kh * kw
     assert out.shape == (d, d) and X.rows == Q * H * W and X.kind in (BF16, BF16X3, F16X3)
-    T = torch.empty(d, d, device=out.device, dtype=torch.float32)
+    T = torch.empty(dp, dp, device=out.device, dtype=torch.float32)
     _lib.call("lpb_syrk_conv_patches_tc", _ptr(X.hi), _ptr(X.lo), X.ldk, Q, H, W, Ci, kh, kw, mod.padding[0], mod.padding[1],
               alpha, 0, _ptr(T), T.stride(0), 1 if X.kind == F16X3 else 0, _stream())
-    _lib.call("lpb_taps_to_param_accumulate", _ptr(T), T.stride(0), Ci, kh * kw, _ptr(out), out.stride(0), _stream())
+    _lib.call("lpb_taps_to_param_accumulate", _ptr(T), T.stride(0), Ci, Ci_pad, kh * kw, _ptr(out), out.stride(0), _stream())
     _bump(2)
     return out
 

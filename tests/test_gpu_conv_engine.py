@@ -13,12 +13,15 @@ DEV = "cuda"
 GEOMS = [(3, 64, 7, 2, 3, 1, 32), (64, 64, 3, 1, 1, 1, 8), (64, 128, 3, 2, 1, 1, 8), (64, 128, 1, 2, 0, 1, 8), (256, 512, 3, 2, 1, 1, 2),
          (512, 512, 3, 1, 1, 1, 1), (5, 7, 3, 1, 2, 2, 9), (4, 6, 2, 2, 0, 1, 5),
          # implicit-GEMM eligible (stride 1, same padding, H*W | 128), incl. ragged channel counts
-         (128, 128, 3, 1, 1, 1, 4), (256, 256, 3, 1, 1, 1, 2), (24, 40, 5, 1, 2, 1, 4), (16, 200, 1, 1, 0, 1, 8), (72, 8, 3, 1, 1, 1, 8)]
+         (128, 128, 3, 1, 1, 1, 4), (256, 256, 3, 1, 1, 1, 2), (24, 40, 5, 1, 2, 1, 4), (16, 200, 1, 1, 0, 1, 8), (72, 8, 3, 1, 1, 1, 8),
+         # implicit GEMM on images larger than one 128-row tile (tiles of 128 / W image rows)
+         (16, 32, 3, 1, 1, 1, 32), (64, 64, 3, 1, 1, 1, 16), (3, 16, 3, 1, 1, 1, 32), (8, 24, 5, 1, 2, 1, 64)]
 
 
 def test_implicit_path_selected():
     m = torch.nn.Conv2d(64, 64, 3, 1, 1)
-    assert conv_engine.implicit_ok(m, 8, 8) and conv_engine.implicit_ok(m, 1, 1) and not conv_engine.implicit_ok(m, 16, 16)
+    assert conv_engine.implicit_ok(m, 8, 8) and conv_engine.implicit_ok(m, 1, 1) and conv_engine.implicit_ok(m, 16, 16)
+    assert conv_engine.implicit_ok(m, 32, 32) and not conv_engine.implicit_ok(m, 12, 12) and not conv_engine.implicit_ok(m, 6, 48)
     assert not conv_engine.implicit_ok(torch.nn.Conv2d(64, 64, 3, 2, 1), 8, 8)
 
 
@@ -105,7 +108,9 @@ def test_layer_gradients_match_fp64_autograd(name, kw):
 
 
 @pytest.mark.parametrize("geom", [(64, 8, 8, 3, 70), (128, 4, 4, 3, 130), (64, 2, 2, 3, 33), (256, 1, 1, 3, 200), (64, 16, 16, 3, 5),
-                                  (64, 8, 8, 1, 40), (128, 16, 8, 3, 9), (64, 32, 32, 3, 3)])
+                                  (64, 8, 8, 1, 40), (128, 16, 8, 3, 9), (64, 32, 32, 3, 3),
+                                  # channel counts padded to 64 per tap (zero-filled by the TMA unit)
+                                  (160, 8, 8, 3, 20), (96, 4, 4, 3, 50), (48, 8, 8, 1, 10)])
 @pytest.mark.parametrize("kind,tol", [(K.BF16X3, 3e-5), (K.F16X3, 1e-5), (K.BF16, 6e-3)])
 def test_syrk_conv_patches_vs_unfold(geom, kind, tol):
     """im2col-free A factor (shifted 4-D TMA boxes feeding the MN-major SYRK) == fp64 unfold + P^T P, in the parameter

@@ -126,7 +126,8 @@ def test_structured_predictive_matches_dense(golden, cpu_kernels):
         assert torch.allclose(fv.double(), ref, rtol=1e-3, atol=1e-6)
 
 
-@pytest.mark.parametrize("name,kw", [("resnet18", {"width": 8}), ("wrn28_10", {"depth": 10, "widen": 1}),
+@pytest.mark.parametrize("name,kw", [("resnet18", {"width": 8}), ("resnet18", {"width": 8, "cifar_stem": True}),
+                                     ("wrn28_10", {"depth": 10, "widen": 1}),
                                      ("vit_b16", {"image": 32, "patch": 8, "dim": 32, "depth": 2, "heads": 4, "mlp_dim": 64})])
 def test_convolution_engine_paths_on_model_zoo(cpu_kernels, monkeypatch, name, kw):
     """Full engine (implicit/explicit convolutions, Linear layers, frozen-BN affine, ReLU and MaxPool custom reverse
