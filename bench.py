@@ -290,6 +290,7 @@ def run_ours(args):
         extras["decompose_ms_once_per_fit"] = (time.perf_counter() - t0) * 1e3
         # BASELINE config: one fit() over N = 50 000 samples = N / value seconds of per-batch work + one decompose
         extras["fit_50k_samples_per_sec_incl_decompose"] = N_total / (N_total / value + extras["decompose_ms_once_per_fit"] / 1e3)
+        extras["jtj_syrk_kernel"] = measure_syrk_probe(K, dev)
         if args.predictive:
             extras.update(measure_predictive(model, dev, B200Laplace, B200GGN, args))
 
@@ -406,6 +407,38 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
                     "products per algorithmic MAC, so the tensor pipe does 3x the counted work" if tensor and args.precision == "bf16x3" else "",
             "launches_per_step": d["launches_per_step"], "ms_per_step_in_kernel": d["ms_per_step"],
             "families": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in fam.items()}}
+
+
+def measure_syrk_probe(K, dev):
+    """The J^T J contraction kernel alone (tensor-pipe fraction of the factor SYRK): d = 4608
+    (ResNet-18 layer-4 input factor), 65 536 sample rows, row-major operands, timed with CUDA events after warm-up.
+    `tensor_tflops` counts issued products (3 per MAC in the bf16x3 mode), `algorithmic_tflops` one per MAC of the
+    upper triangle."""
+    torch.manual_seed(7)
+    d, rows = 4608, 65536
+    X = torch.randn(rows, d, device=dev)
+    out = {}
+    pk = peaks()
+    peak = pk["bf16_sustained"] or 1400.0
+    for kind, name, nprod in ((K.BF16X3, "bf16x3", 3), (K.BF16, "bf16", 1)):
+        P = K.pack_cast(X, kind)
+        H = torch.zeros(d, d, device=dev)
+        for _ in range(2):
+            K.gemm_tn(P, P, H, 1.0, True, symmetric=True)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(5):
+            K.gemm_tn(P, P, H, 1.0, True, symmetric=True)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 5
+        alg = (d * (d + 128) / 2) * 2.0 * rows / (ms / 1e3) / 1e12     # tiles on/above the diagonal
+        out[name] = {"ms": round(ms, 3), "algorithmic_tflops": round(alg, 1), "tensor_tflops": round(alg * nprod, 1),
+                     "tensor_frac_of_peak": round(alg * nprod / peak, 3)}
+        del P, H
+    out["shape"] = f"SYRK d={d}, K={rows} sample rows (working set 1.2 GB > L2), peak {peak:.0f} TFLOP/s ({pk['source']})"
+    return out
 
 
 def measure_predictive(model, dev, B200Laplace, B200GGN, args):

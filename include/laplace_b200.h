@@ -132,6 +132,18 @@ int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W
 int lpb_syrk_conv_patches_tc(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q, int H, int W, int Ci, int KH, int KW,
                              int PH, int PW, float alpha, int accumulate, float* D, int64_t ldd, int fp16_operands,
                              void* stream);
+/* Diagonal GGN / EF of a stride-1 'same' convolution weight, per-sample weight gradients squared and summed on the
+ * tensor cores (replaces einsum("bcp,bcp->p") / ("bp,bp->p") on materialised per-sample gradients,
+ * reference laplace/curvature/curvature.py:429-431, 504):
+ *   D[co, t*Ci_pad + ci] (+)= alpha * sum_{q < Qtot} ( sum_{h,w} G[(q,h,w), co] * x[q % Nimg, h+kh-PH, w+kw-PW, ci] )^2
+ * G: 16-bit hi(/lo) output-gradient rows [(q,h,w), Co] of all folded curvature columns, x: NHWC rows [(n,h,w), Ci] in
+ * the same format (bf16).  Needs H*W >= 64 with W | 64 and 64/W | H.  lpb_taps_to_param_rect folds the tap-major,
+ * channel-padded columns into the parameter order (ci,kh,kw).                                                       */
+int lpb_diag_conv_sq_tc(const void* G_hi, const void* G_lo, int64_t ldg, const void* X_hi, const void* X_lo, int64_t ldx,
+                        int64_t Qtot, int64_t Nimg, int H, int W, int Ci, int Co, int KH, int KW, int PH, int PW, float alpha,
+                        int accumulate, float* D, int64_t ldd, void* stream);
+int lpb_taps_to_param_rect(const float* Dt, int64_t ldt, int Co, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
+                           void* stream);
 /* out[(ci*KK+t), (cj*KK+t')] += T[(t*Ci_pad+ci), (t'*Ci_pad+cj)]: tap-major factor -> parameter order (ci,kh,kw), KK <= 9 */
 int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
                                  void* stream);

@@ -280,6 +280,28 @@ class _B200Mixin:
         p = torch.softmax(f, dim=-1)
         return (p - torch.nn.functional.one_hot(y, f.shape[-1]).to(f.dtype)).unsqueeze(0)
 
+    def _diag_conv_tc(self, L, a, g, M, ncols, out, scale) -> bool:
+        """Diagonal of a stride-1 convolution weight on the tensor cores (``K.diag_conv_sq``): per-sample weight
+        gradients formed in TMEM from the engine's gradient rows and the NHWC input rows, squared and summed --
+        instead of the fp32 SIMT contraction over a 9x-inflated im2col.  Returns False when the layer does not qualify."""
+        if not (self.conv_engine and L.is_conv and self.precision in ("auto", "bf16x3") and a.dim() == 4 and g.dim() == 5):
+            return False
+        from . import conv_engine
+
+        mod = L.mod
+        H, W = a.shape[2], a.shape[3]
+        if not (conv_engine.implicit_ok(mod, H, W) and tuple(g.shape[3:]) == (H, W)
+                and K.diag_conv_ok(mod.in_channels, H, W, *mod.kernel_size)):
+            return False
+        G = conv_engine.STASH.get(id(mod), {}).get("G")
+        if (G is None or G.rows != ncols * M * H * W or G.kind != K.BF16X3
+                or not (ncols == 1 or getattr(self, "last_backward_mode", "") == "batched")):
+            g4 = g.reshape(ncols * M, *g.shape[2:])
+            G = conv_engine.nhwc_rows(g4 if g4.dtype == torch.float32 else g4.float(), K.BF16X3)
+        X = conv_engine.nhwc_rows(a, K.BF16X3)
+        K.diag_conv_sq(G, X, M, H, W, mod, out, alpha=scale)
+        return True
+
     # ------------------------------------------------------------------ precision policy
     def _kind(self, d: int, k: int) -> int:
         """Operand format of one contraction with output dim ``d`` and reduction length ``k``."""
@@ -703,6 +725,8 @@ class B200GGN(_B200Mixin, GGNInterface):
                     g2 = K.pack_rows((g * g).sum(0).contiguous(), K.F32)
                     a2 = K.pack_rows(a.contiguous(), K.F32, square=True)
                     K.gemm_nt(g2, a2, out, alpha=scale, accumulate=True)
+                elif self._diag_conv_tc(L, a, g, M, ncols, out, scale):
+                    pass
                 else:
                     A, T = self._pack_act(L, a, K.F32)
                     G = self._pack_grad(L, g, K.F32)

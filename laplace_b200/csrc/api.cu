@@ -63,6 +63,9 @@ void set_gemm_pair_mode(int mode);
 int syrk_conv_patches(const void*, const void*, int64_t, int64_t, int, int, int, int, int, int, int, float, int, float*, int64_t,
                       int, cudaStream_t);
 int taps_to_param_accumulate(const float*, int64_t, int, int, int, float*, int64_t, cudaStream_t);
+int diag_conv_sq(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, int, int,
+                 int, int, int, float, int, float*, int64_t, cudaStream_t);
+int taps_to_param_rect(const float*, int64_t, int, int, int, int, float*, int64_t, cudaStream_t);
 int pack_cast_fused(const float*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, void*, void*, int,
                     int64_t, cudaStream_t);
 int col2im_nhwc(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
@@ -178,6 +181,19 @@ int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad
                                  void* stream) {
   LPB_REQUIRE(ldt >= (int64_t)Ci_pad * KK && ldo >= (int64_t)Ci * KK, "lpb_taps_to_param_accumulate: leading dimension too small");
   return lpb::taps_to_param_accumulate(T, ldt, Ci, Ci_pad, KK, out, ldo, ST(stream));
+}
+
+int lpb_diag_conv_sq_tc(const void* G_hi, const void* G_lo, int64_t ldg, const void* X_hi, const void* X_lo, int64_t ldx,
+                        int64_t Qtot, int64_t Nimg, int H, int W, int Ci, int Co, int KH, int KW, int PH, int PW, float alpha,
+                        int accumulate, float* D, int64_t ldd, void* stream) {
+  return lpb::diag_conv_sq(G_hi, G_lo, ldg, X_hi, X_lo, ldx, Qtot, Nimg, H, W, Ci, Co, KH, KW, PH, PW, alpha, accumulate, D, ldd,
+                           ST(stream));
+}
+
+int lpb_taps_to_param_rect(const float* Dt, int64_t ldt, int Co, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
+                           void* stream) {
+  LPB_REQUIRE(Ci_pad >= Ci && ldt >= (int64_t)Ci_pad * KK && ldo >= (int64_t)Ci * KK, "lpb_taps_to_param_rect: bad extents");
+  return lpb::taps_to_param_rect(Dt, ldt, Co, Ci, Ci_pad, KK, out, ldo, ST(stream));
 }
 
 int lpb_pack_cast_fused(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* scale, const float* y,

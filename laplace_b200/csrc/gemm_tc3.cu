@@ -45,7 +45,10 @@ __device__ __forceinline__ ItemGeom decode_item(int item, int num_tiles, int sym
   return g;
 }
 
-// LOADER 0: K-major 2-D operands; 1: row (MN-major) 2-D operands; 2: implicit convolution patches (MN-major, 4-D)
+// LOADER 0: K-major 2-D operands; 1: row (MN-major) 2-D operands; 2: implicit convolution patches (MN-major, 4-D);
+// 3: A = row operand (output-gradient rows), B = implicit patches of the same samples, and every sample's product is
+//    SQUARED before it is accumulated:  D[i,j] += alpha * sum_q ( sum_t A[(q,t), i] * patch[(q mod n_images, t), j] )^2
+//    -- the diagonal GGN / EF of a convolution weight (per-sample weight gradients, never materialised).
 template <int NPROD, int LOADER>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -91,11 +94,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], it.diag ? STAGE_BYTES / 2 : STAGE_BYTES);
-          auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, int tile) {
-            if (LOADER == 2) {
+          auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, int tile, bool is_b) {
+            if (LOADER == 2 || (LOADER == 3 && is_b)) {
               int n0, h0;
               if (pg.chunks_per_img > 0) { n0 = kc / pg.chunks_per_img; h0 = (kc - n0 * pg.chunks_per_img) * pg.rows_per_chunk; }
               else { n0 = kc * pg.imgs_per_chunk; h0 = 0; }
+              if (LOADER == 3 && pg.n_images > 0) n0 %= pg.n_images;
 #pragma unroll
               for (int b = 0; b < 2; ++b) {
                 const int fb = tile * 2 + b;
@@ -112,11 +116,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
               tma_load_2d(map, &full_bar[stage], dst, kc * BK, tile * BM);
             }
           };
-          load_tile(&tmA_hi, st, it.tm);
-          if (!it.diag) load_tile(&tmB_hi, st + TILE_BYTES, it.tn);
+          load_tile(&tmA_hi, st, it.tm, false);
+          if (!it.diag) load_tile(&tmB_hi, st + TILE_BYTES, it.tn, true);
           if (NPROD == 3) {
-            load_tile(&tmA_lo, st + 2 * TILE_BYTES, it.tm);
-            if (!it.diag) load_tile(&tmB_lo, st + 3 * TILE_BYTES, it.tn);
+            load_tile(&tmA_lo, st + 2 * TILE_BYTES, it.tm, false);
+            if (!it.diag) load_tile(&tmB_lo, st + 3 * TILE_BYTES, it.tn, true);
           }
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
@@ -132,7 +136,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
         const ItemGeom it = decode_item(item, num_tiles, symmetric, tiles_m, tiles_n, total_kchunks, kchunks_per_split);
         const int n = it.kc_end - it.kc_begin;
         const int ngroups = (n + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
-        const int glen = (n + ngroups - 1) / ngroups;
+        const int glen = (LOADER == 3) ? pg.group_chunks : (n + ngroups - 1) / ngroups;
         for (int g0 = 0; g0 < n; g0 += glen, ++grp) {
           const uint32_t buf = grp & 1;
           mbar_wait(&tempty_bar[buf], ((grp >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
@@ -173,7 +177,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
       const ItemGeom it = decode_item(item, num_tiles, symmetric, tiles_m, tiles_n, total_kchunks, kchunks_per_split);
       const int n = it.kc_end - it.kc_begin;
       const int ngroups = (n + GROUP_CHUNKS - 1) / GROUP_CHUNKS;
-      const int glen = (n + ngroups - 1) / ngroups;
+      const int glen = (LOADER == 3) ? pg.group_chunks : (n + ngroups - 1) / ngroups;
       float accv[BN];
       for (int g0 = 0; g0 < n; g0 += glen, ++grp) {
         const uint32_t buf = grp & 1;
@@ -184,7 +188,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
         for (int chunk = 0; chunk < BN / 32; ++chunk) {
           float v[32];
           tmem_ld32(taddr + (uint32_t)(chunk * 32), v);
-          if (g0 == 0) {
+          if (LOADER == 3) {   // one group = one sample: square, then sum over samples
+            if (g0 == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) accv[chunk * 32 + j] = v[j] * v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) accv[chunk * 32 + j] = fmaf(v[j], v[j], accv[chunk * 32 + j]);
+            }
+          } else if (g0 == 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) accv[chunk * 32 + j] = v[j];
           } else {
@@ -306,7 +318,10 @@ int launch_gemm_tc_persistent(bool mn, bool x3, const CUtensorMap& tA_hi, const 
         tA_hi, tA_lo, tB_hi, tB_lo, (int)M, (int)N, alpha, D, ldd, symmetric, tiles_m, tiles_n, (int)num_tiles,          \
         (int)items, total_kchunks, kchunks_per_split, num_stages, store_mode, fp16_operands, pg);                        \
   } while (0)
-  if (patches) {
+  if (patches && patches->group_chunks > 0) {
+    if (x3) LPB_LAUNCH_P(3, 3);
+    else LPB_LAUNCH_P(1, 3);
+  } else if (patches) {
     if (x3) LPB_LAUNCH_P(3, 2);
     else LPB_LAUNCH_P(1, 2);
   } else if (x3 && mn) LPB_LAUNCH_P(3, 1);
@@ -323,6 +338,22 @@ int launch_gemm_tc_persistent(bool mn, bool x3, const CUtensorMap& tA_hi, const 
 //     D[(t,ci),(t',cj)] (+)= alpha * sum_{n,h,w} x[n, h+kh-PH, w+kw-PW, ci] * x[n, h+kh'-PH, w+kw'-PW, cj]
 // (tap-major feature order; taps_to_param_accumulate() below folds it into the parameter order (ci,kh,kw)).
 // The patch matrix [(n,h,w), KH*KW*Ci] -- 9x the activation for 3x3 kernels -- is never written or read.
+// row-major [rows, cols] 16-bit matrix, boxes of 64 columns x 64 rows (the MN-major operand tiles of gemm_tc.cu)
+static int make_tmap_rows_ext(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  PFN_encodeTiled enc = get_tensormap_encoder();
+  LPB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LPB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rows) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+  return 0;
+}
+
 static int make_tmap_patches(CUtensorMap* map, const void* ptr, int64_t Q, int H, int W, int64_t Ci, int64_t ld, int box_h,
                              int box_n) {
   PFN_encodeTiled enc = get_tensormap_encoder();
@@ -384,6 +415,75 @@ int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q
     return 1;
   return launch_gemm_tc_persistent(true, x3, tX_hi, tX_lo, tX_hi, tX_lo, d, d, alpha, D, ldd, 1, tiles_m, tiles_m, tiles,
                                    total_kchunks, kps, nsplit, 0, fp16_operands, sms, st, &pg);
+}
+
+// Diagonal GGN / EF of a stride-1 'same' convolution weight on the tensor cores:
+//     D[co, (t,ci)] (+)= alpha * sum_{q=(col,n)} ( sum_{h,w} G[(q,h,w), co] * x[n, h+kh-PH, w+kw-PW, ci] )^2
+// G: output-gradient rows of all folded columns (bf16 hi/lo), x: NHWC activation rows of the Nimg images (same
+// format).  One TMEM accumulation per sample (H*W/64 k-chunks), squared by the epilogue and summed over the CTA's
+// samples in registers; tap-major columns with Ci padded to 64 (taps_to_param_rect() folds them into (ci,kh,kw)).
+int diag_conv_sq(const void* G_hi, const void* G_lo, int64_t ldg, const void* X_hi, const void* X_lo, int64_t ldx, int64_t Qtot,
+                 int64_t Nimg, int H, int W, int Ci, int Co, int KH, int KW, int PH, int PW, float alpha, int accumulate,
+                 float* D, int64_t ldd, cudaStream_t st) {
+  LPB_REQUIRE(Qtot > 0 && Nimg > 0 && Qtot % Nimg == 0, "diag_conv_sq: sample rows must be a multiple of the image count");
+  LPB_REQUIRE(2 * PH == KH - 1 && 2 * PW == KW - 1, "diag_conv_sq: stride-1 'same' convolutions only");
+  const int HW = H * W;
+  LPB_REQUIRE(HW >= 64 && 64 % W == 0 && H % (64 / W) == 0, "diag_conv_sq: %dx%d images do not tile 64-row chunks", H, W);
+  LPB_REQUIRE((ldx % 8) == 0 && ldx >= Ci && (ldg % 8) == 0 && ldg >= Co, "diag_conv_sq: bad leading dimensions");
+  LPB_REQUIRE((G_lo == nullptr) == (X_lo == nullptr), "diag_conv_sq: lo operands must both be given or both NULL");
+  const int Ci_pad = (int)ceil_div(Ci, 64) * 64;
+  tc::PatchGeom pg = {};
+  pg.KW = KW; pg.PH = PH; pg.PW = PW; pg.Ci = Ci; pg.num_taps = KH * KW; pg.blocks_per_tap = Ci_pad / 64;
+  pg.rows_per_chunk = 64 / W; pg.chunks_per_img = HW / 64; pg.imgs_per_chunk = 0;
+  pg.n_images = (int)Nimg; pg.group_chunks = pg.chunks_per_img;
+  LPB_REQUIRE(pg.group_chunks <= 64, "diag_conv_sq: images larger than 4096 pixels are not supported");
+  const int64_t Ncols = (int64_t)KH * KW * Ci_pad;
+  LPB_REQUIRE(ldd >= Ncols, "diag_conv_sq: ldd too small");
+  const int64_t kchunks64 = Qtot * pg.chunks_per_img;
+  LPB_REQUIRE(kchunks64 < (1LL << 31) && Nimg < (1LL << 31), "diag_conv_sq: too many sample rows");
+  const bool x3 = G_lo != nullptr;
+  CUtensorMap tG_hi, tG_lo, tX_hi, tX_lo;
+  if (make_tmap_rows_ext(&tG_hi, G_hi, Qtot * HW, Co, ldg)) return 1;
+  if (make_tmap_patches(&tX_hi, X_hi, Nimg, H, W, Ci, ldx, pg.rows_per_chunk, 1)) return 1;
+  if (x3) {
+    if (make_tmap_rows_ext(&tG_lo, G_lo, Qtot * HW, Co, ldg)) return 1;
+    if (make_tmap_patches(&tX_lo, X_lo, Nimg, H, W, Ci, ldx, pg.rows_per_chunk, 1)) return 1;
+  } else {
+    tG_lo = tG_hi; tX_lo = tX_hi;
+  }
+  const int tiles_m = (int)ceil_div(Co, tc::BM), tiles_n = (int)ceil_div(Ncols, tc::BN);
+  const int64_t tiles = (int64_t)tiles_m * tiles_n;
+  const int sms = sm_count();
+  // split over samples (a sample's chunks stay together): schedule in units of one sample
+  int qps = 0, nsplit = 1;
+  bool single = false;
+  persistent_schedule(tiles, (int)imin(Qtot, 2147483647LL), sms, false, &qps, &nsplit, &single);
+  if (!accumulate && check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, Ncols * sizeof(float), Co, st), "diag_conv_sq memset"))
+    return 1;
+  return launch_gemm_tc_persistent(true, x3, tG_hi, tG_lo, tX_hi, tX_lo, Co, Ncols, alpha, D, ldd, 0, tiles_m, tiles_n, tiles,
+                                   (int)kchunks64, qps * pg.chunks_per_img, nsplit, 0, 0, sms, st, &pg);
+}
+
+// out[co, ci*KK + t] += Dt[co, t*Cp + ci]
+__global__ void __launch_bounds__(256) taps_to_param_rect_kernel(const float* __restrict__ Dt, int64_t ldt, int Co, int Ci, int Cp,
+                                                                 int KK, float* __restrict__ out, int64_t ldo) {
+  const int64_t total = (int64_t)Co * Ci * KK;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t co = e / (Ci * KK);
+    const int r = (int)(e - co * Ci * KK);
+    const int ci = r / KK, t = r - ci * KK;
+    out[co * ldo + r] += Dt[co * ldt + (int64_t)t * Cp + ci];
+  }
+}
+
+int taps_to_param_rect(const float* Dt, int64_t ldt, int Co, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
+                       cudaStream_t st) {
+  const int64_t total = (int64_t)Co * Ci * KK;
+  if (total == 0) return 0;
+  const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 16);
+  taps_to_param_rect_kernel<<<blocks, 256, 0, st>>>(Dt, ldt, Co, Ci, Ci_pad, KK, out, ldo);
+  LPB_CHECK_LAUNCH("taps_to_param_rect");
+  return 0;
 }
 
 // out[(ci*KK + t), (cj*KK + t')] += T[(t*Cp + ci), (t'*Cp + cj)]   (KK = KH*KW <= 9, Cp = padded channel stride of T).

@@ -395,6 +395,30 @@ def syrk_conv_patches(X: Packed, Q: int, H: int, W: int, mod, out: torch.Tensor,
     return out
 
 
+def diag_conv_ok(Ci: int, H: int, W: int, kh: int, kw: int) -> bool:
+    """Shapes ``diag_conv_sq`` accepts: one TMEM accumulation per sample needs whole 64-pixel chunks per image."""
+    hw = H * W
+    return hw >= 64 and 64 % W == 0 and H % (64 // W) == 0 and hw <= 4096 and Ci >= 16
+
+
+def diag_conv_sq(G: Packed, X: Packed, Nimg: int, H: int, W: int, mod, out: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """``out[co, (ci,kh,kw)] += alpha * sum_q (per-sample weight gradient)^2`` of a stride-1 'same' convolution on the
+    tensor cores: ``G [(q,h,w), C_out]`` gradient rows of all folded columns (``q = col * Nimg + n``), ``X [(n,h,w), C_in]``
+    NHWC input rows, both bf16 hi/lo.  Per-sample gradients are formed in TMEM, squared by the epilogue, never stored."""
+    _check(out, name="out")
+    kh, kw = mod.kernel_size
+    Ci, Co = X.K, G.K
+    Ci_pad = -(-Ci // 64) * 64
+    assert out.shape == (Co, Ci * kh * kw) and X.rows == Nimg * H * W and G.rows % X.rows == 0 and G.kind == X.kind
+    assert G.kind in (BF16, BF16X3)
+    Dt = torch.empty(Co, kh * kw * Ci_pad, device=out.device, dtype=torch.float32)
+    _lib.call("lpb_diag_conv_sq_tc", _ptr(G.hi), _ptr(G.lo), G.ldk, _ptr(X.hi), _ptr(X.lo), X.ldk, G.rows // (H * W), Nimg, H, W,
+              Ci, Co, kh, kw, mod.padding[0], mod.padding[1], alpha, 0, _ptr(Dt), Dt.stride(0), _stream())
+    _lib.call("lpb_taps_to_param_rect", _ptr(Dt), Dt.stride(0), Co, Ci, Ci_pad, kh * kw, _ptr(out), out.stride(0), _stream())
+    _bump(2)
+    return out
+
+
 # ------------------------------------------------------------------------------ reverse-pass element-wise maps
 def scale_channels(g: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """``g [Q, C, H, W]`` (NCHW- or channels_last-dense) times a per-channel ``scale [C]``; same layout out."""

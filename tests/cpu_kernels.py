@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "diag_conv_sq", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -220,6 +220,16 @@ def syrk_conv_patches(X, Q, H, W, mod, out, alpha=1.0):
     x = X.hi[:, :Ci].reshape(Q, H, W, Ci).permute(0, 3, 1, 2).float()
     P = F.unfold(x, mod.kernel_size, padding=mod.padding).transpose(1, 2).reshape(Q * H * W, -1)
     out += alpha * (P.t() @ P)
+    return out
+
+
+def diag_conv_sq(G, X, Nimg, H, W, mod, out, alpha=1.0):
+    Ci, Co = X.K, G.K
+    x = X.hi[:, :Ci].reshape(Nimg, H, W, Ci).permute(0, 3, 1, 2).float()
+    P = F.unfold(x, mod.kernel_size, padding=mod.padding).transpose(1, 2)          # [Nimg, T, Ci*KK]
+    g = G.hi[:, :Co].reshape(-1, Nimg, H * W, Co).float()                          # [cols, Nimg, T, Co]
+    per = torch.einsum("cnto,ntp->cnop", g, P)
+    out += alpha * (per * per).sum((0, 1))
     return out
 
 

@@ -152,3 +152,53 @@ def test_implicit_patch_factor_model_parity():
     _, kf = co.kfac_factors(model.cpu().double(), "classification", X.double(), y, N=36)
     worst = max(rel_fro(H.cpu(), Ho) for F_, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F_, Fo))
     assert worst < 1e-4, worst
+
+
+@pytest.mark.parametrize("geom", [(64, 32, 8, 8, 3, 6, 2), (160, 40, 8, 8, 3, 5, 1), (16, 130, 16, 16, 3, 3, 3), (24, 8, 32, 32, 1, 2, 2),
+                                  (64, 64, 16, 8, 3, 4, 10)])
+@pytest.mark.parametrize("kind,tol", [(K.BF16X3, 5e-5), (K.BF16, 2e-2)])
+def test_diag_conv_sq_vs_per_sample_gradients(geom, kind, tol):
+    """Tensor-core diagonal of a convolution weight: sum over (column, sample) of the squared per-sample weight
+    gradient == fp64 einsum on unfolded patches, in the parameter order (co, ci, kh, kw)."""
+    Ci, Co, H, W, k, Nimg, ncols = geom
+    torch.manual_seed(4)
+    mod = torch.nn.Conv2d(Ci, Co, k, 1, k // 2)
+    x = torch.randn(Nimg, Ci, H, W)
+    g = torch.randn(ncols * Nimg, Co, H, W)
+    P = F.unfold(x.double(), k, padding=k // 2).transpose(1, 2)                          # [Nimg, T, Ci*k*k]
+    per = torch.einsum("cnto,ntp->cnop", g.double().reshape(ncols, Nimg, Co, H * W).transpose(2, 3), P)
+    ref = (per * per).sum((0, 1))
+    assert K.diag_conv_ok(Ci, H, W, k, k)
+    cl = torch.channels_last
+    X = conv_engine.nhwc_rows(x.to(DEV).contiguous(memory_format=cl), kind)
+    G = conv_engine.nhwc_rows(g.to(DEV).contiguous(memory_format=cl), kind)
+    base = torch.rand(Co, Ci * k * k)
+    out = base.to(DEV)
+    K.diag_conv_sq(G, X, Nimg, H, W, mod, out, alpha=0.25)
+    assert rel_fro(out.cpu().double() - base.double(), 0.25 * ref) < tol
+
+
+def test_diag_tensor_core_model_parity():
+    """diag GGN / diag EF of a convolution stack through the tensor-core diagonal == oracle (rel-fro <= 1e-4)."""
+    from laplace_b200 import B200EF
+    from oracle import curvature_oracle as co
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 32, 3, 1, 1), torch.nn.ReLU(), torch.nn.Conv2d(32, 48, 3, 1, 1, bias=False),
+                                torch.nn.ReLU(), torch.nn.Conv2d(48, 16, 1), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
+                                torch.nn.Linear(16, 5)).eval()
+    X, y = torch.randn(7, 3, 8, 8), torch.randint(5, (7,))
+    calls = []
+    orig = K.diag_conv_sq
+    K.diag_conv_sq = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        _, d = B200GGN(model.to(DEV), "classification").diag(X.to(DEV), y.to(DEV))
+        _, de = B200EF(model, "classification").diag(X.to(DEV), y.to(DEV))
+    finally:
+        K.diag_conv_sq = orig
+    assert len(calls) == 4
+    m64 = model.cpu().double()
+    Js, f = co.jacobians(m64, X.double())
+    _, dref = co.ggn_diag(Js, f, y, "classification")
+    _, deref = co.ef_diag(Js, f, y, "classification")
+    assert rel_fro(d.cpu(), dref) < 1e-4 and rel_fro(de.cpu(), deref) < 1e-4

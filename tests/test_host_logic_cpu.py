@@ -199,3 +199,29 @@ def test_implicit_patch_factor_path(cpu_kernels, monkeypatch):
     _, kf = co.kfac_factors(model, "classification", X, y, N=18)
     worst = max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo))
     assert worst < 1e-5, worst
+
+
+def test_diag_tensor_core_conv_path(cpu_kernels):
+    """Stride-1 convolutions on >= 64-pixel images take the tensor-core diagonal (K.diag_conv_sq): diag GGN and diag EF
+    equal the oracle's, in parameter order."""
+    from laplace_b200 import kernels as K
+
+    calls = []
+    orig = K.diag_conv_sq
+    K.diag_conv_sq = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, 1, 1), torch.nn.ReLU(), torch.nn.Conv2d(16, 24, 3, 1, 1, bias=False),
+                                    torch.nn.ReLU(), torch.nn.Conv2d(24, 8, 1), torch.nn.AdaptiveAvgPool2d(1),
+                                    torch.nn.Flatten(), torch.nn.Linear(8, 5)).eval()
+        X, y = torch.randn(6, 3, 8, 8), torch.randint(5, (6,))
+        _, d = B200GGN(model, "classification").diag(X, y)
+        assert len(calls) == 2      # the 16->24 3x3 and 24->8 1x1 convolutions (the 3-channel stem stays on the SIMT path)
+        Js, f = co.jacobians(model, X)
+        _, dref = co.ggn_diag(Js, f, y, "classification")
+        assert rel_fro(d, dref) < 1e-5
+        _, de = B200EF(model, "classification").diag(X, y)
+        _, deref = co.ef_diag(Js, f, y, "classification")
+        assert rel_fro(de, deref) < 1e-5
+    finally:
+        K.diag_conv_sq = orig
