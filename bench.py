@@ -360,6 +360,7 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
         "conv_nhwc": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[5] * a[0].K * a[6] * a[7], True),
         # implicit patch SYRK: dense 2 * d^2 * rows convention, d = C_in * kh * kw
         "syrk_conv_patches": lambda r, a, kw: ("flops", 2.0 * float(a[5].shape[0]) ** 2 * a[0].rows, True),
+        "conv_bwd_strided": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[0].K * a[4].rows, True),
         "col2im_nhwc": lambda r, a, kw: ("bytes", 4.0 * (a[0].shape[0] * a[0].shape[1] + r.numel()), False),
         "pack_rows": lambda r, a, kw: ("bytes", bytes_packed(r), False),
         "pack_conv": lambda r, a, kw: ("bytes", bytes_packed(r[0]), False),

@@ -122,6 +122,15 @@ int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W
                      const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
                      float* D, int64_t ldd, int fp16_operands, void* stream);
 
+/* backward-data of a STRIDED convolution as implicit GEMMs (no [rows, KH*KW*Ci] intermediate, no col2im): the input
+ * gradient splits into SH*SW parity classes, each a stride-1 convolution of the output-gradient grid with the taps
+ * kh = h + PH (mod SH), kw = w + PW (mod SW), stored to the class's pixels of D [Q, H, W, ldd] (all of D is written).
+ * G [(q,oh,ow), ldg] 16-bit hi(/lo) rows, Wt [(kh,kw,ci), ldw] tap-major; needs H == OH*SH, W == OW*SW and an
+ * OH x OW grid that tiles 128-row blocks.                                                                           */
+int lpb_conv_bwd_strided_tc(const void* G_hi, const void* G_lo, int64_t Q, int OH, int OW, int64_t Co, int64_t ldg,
+                            const void* W_hi, const void* W_lo, int64_t ldw, int Ci, int KH, int KW, int SH, int SW, int PH,
+                            int PW, int H, int W, float* D, int64_t ldd, void* stream);
+
 /* ---- KFAC input factor of a stride-1 'same' convolution without im2col -----------------------------------------
  * D[(t,ci),(t',cj)] (+)= alpha * sum_{n,h,w} x[n,h+kh-PH,w+kw-PW,ci] * x[n,h+kh'-PH,w+kw'-PW,cj]   (zero padding),
  * t = kh*KW + kw, feature (t,ci) at index t*Ci_pad + ci with Ci_pad = Ci rounded up to 64 (D is [KH*KW*Ci_pad]^2, padded

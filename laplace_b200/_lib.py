@@ -29,6 +29,7 @@ SIGNATURES = {
     "lpb_taps_to_param_accumulate": [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp],
     "lpb_diag_conv_sq_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64] + [c_int] * 8 + [c_f32, c_int, c_vp, c_i64, c_vp],
     "lpb_taps_to_param_rect": [c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp],
+    "lpb_conv_bwd_strided_tc": [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_i64] + [c_int] * 9 + [c_vp, c_i64, c_vp],
     "lpb_pack_cast_fused": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_i64, c_vp],
     "lpb_col2im_nhwc": [c_vp, c_i64] + [c_int] * 12 + [c_vp, c_vp],
     "lpb_gemm_nt_f32": [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_vp],

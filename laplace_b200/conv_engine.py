@@ -30,6 +30,7 @@ KIND_FWD = K.F16X3    # forward pass: activations / weights sit inside fp16 rang
                       # ~2e-7 forward error keeps ReLU masks identical to an fp32 forward (a 1e-5 error flips a
                       # few masks per 10^5 units, each flip is a 100 % error on that unit's gradient)
 USE_IMPLICIT = os.environ.get("LPB_NO_IMPLICIT") != "1"
+USE_STRIDED = os.environ.get("LPB_NO_STRIDED") != "1"     # strided reverse passes as per-parity implicit GEMMs
 
 
 class _WeightCache:
@@ -97,6 +98,23 @@ def implicit_ok(mod: nn.Conv2d, H: int, W: int) -> bool:
     return W <= 128 and 128 % W == 0 and H % (128 // W) == 0
 
 
+def strided_ok(mod: nn.Conv2d, H: int, W: int) -> bool:
+    """Strided convolutions whose reverse pass runs as implicit GEMMs per stride parity class: the input extent is an
+    exact multiple of the stride and the output grid tiles 128-row MMA blocks."""
+    if not USE_IMPLICIT or not USE_STRIDED or tuple(mod.dilation) != (1, 1) or tuple(mod.stride) == (1, 1):
+        return False
+    sh, sw = mod.stride
+    kh, kw = mod.kernel_size
+    if H % sh or W % sw or kh * kw > 64:
+        return False
+    OH, OW = (H + 2 * mod.padding[0] - kh) // sh + 1, (W + 2 * mod.padding[1] - kw) // sw + 1
+    if OH * sh != H or OW * sw != W:
+        return False
+    if OH * OW <= 128:
+        return 128 % (OH * OW) == 0
+    return OW <= 128 and 128 % OW == 0 and OH % (128 // OW) == 0
+
+
 def nhwc_rows(x: torch.Tensor, kind: int) -> K.Packed:
     """``x [N, C, H, W]`` (NCHW or channels_last) -> 16-bit hi/lo rows ``[(n,h,w), C]``."""
     N, C, H, W = x.shape
@@ -154,6 +172,9 @@ def _backward_from_rows(G: K.Packed, Q: int, T: int, mod: nn.Conv2d, in_shape, n
         return None
     if implicit_ok(mod, in_shape[2], in_shape[3]):
         return _implicit_rows(G, Q, in_shape[2], in_shape[3], mod, "bwd_taps", mod.in_channels, -1)
+    if strided_ok(mod, in_shape[2], in_shape[3]):
+        OH, OW = K.conv_out_hw(in_shape, mod)
+        return K.conv_bwd_strided(G, Q, OH, OW, _CACHE.get(mod, "bwd_taps"), mod, (Q,) + tuple(in_shape[1:]))
     Wt = _CACHE.get(mod, "bwd_taps")                         # [(kh,kw,ci), Co]
     Dc = torch.empty(Q * T, Wt.rows, device=G.hi.device, dtype=torch.float32)
     K.gemm_nt(G, Wt, Dc, 1.0, accumulate=False)              # [(q,t), (kh,kw,ci)]

@@ -66,6 +66,8 @@ int taps_to_param_accumulate(const float*, int64_t, int, int, int, float*, int64
 int diag_conv_sq(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, int, int,
                  int, int, int, float, int, float*, int64_t, cudaStream_t);
 int taps_to_param_rect(const float*, int64_t, int, int, int, int, float*, int64_t, cudaStream_t);
+int conv_bwd_strided(const void*, const void*, int64_t, int, int, int64_t, int64_t, const void*, const void*, int64_t, int, int, int,
+                     int, int, int, int, int, int, float*, int64_t, cudaStream_t);
 int pack_cast_fused(const float*, int64_t, int64_t, int64_t, const float*, const float*, int64_t, int64_t, void*, void*, int,
                     int64_t, cudaStream_t);
 int col2im_nhwc(const float*, int64_t, const ConvGeom&, float*, cudaStream_t);
@@ -258,6 +260,13 @@ int lpb_conv_nhwc_tc(const void* X_hi, const void* X_lo, int64_t Q, int H, int W
   LPB_REQUIRE(sgn == 1 || sgn == -1, "lpb_conv_nhwc_tc: sgn must be +1 or -1");
   return lpb::conv_nhwc_bf16(X_hi, X_lo, Q, H, W, Kc, ldx, W_hi, W_lo, ldw, N, KH, KW, base_h, base_w, sgn, alpha, D, ldd,
                              fp16_operands, ST(stream));
+}
+
+int lpb_conv_bwd_strided_tc(const void* G_hi, const void* G_lo, int64_t Q, int OH, int OW, int64_t Co, int64_t ldg,
+                            const void* W_hi, const void* W_lo, int64_t ldw, int Ci, int KH, int KW, int SH, int SW, int PH,
+                            int PW, int H, int W, float* D, int64_t ldd, void* stream) {
+  return lpb::conv_bwd_strided(G_hi, G_lo, Q, OH, OW, Co, ldg, W_hi, W_lo, ldw, Ci, KH, KW, SH, SW, PH, PW, H, W, D, ldd,
+                               ST(stream));
 }
 
 int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const float* A, int64_t lda, int d_out, int d_in,

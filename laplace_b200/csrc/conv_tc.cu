@@ -139,14 +139,27 @@ conv_nhwc_tc_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_con
 // per-tile prologue (barrier init, TMEM allocation, first TMA round trip) and epilogue that made the one-tile-per-CTA
 // kernel spend ~1/3 of its time outside the MMA loop on 64-channel layers (9 k-chunks per tile).
 constexpr int CONV_GROUP = 16;
+constexpr int MAX_TAPS = 64;
+
+// taps of one launch: weight row block `w` (rows w*N .. of the tap-major weight matrix) and the shift of the operand box
+struct ConvTaps {
+  int n;
+  short w[MAX_TAPS], dh[MAX_TAPS], dw[MAX_TAPS];
+};
+// where a tile's rows go: mode 0 = the row itself (dense NHWC output); mode 1 = pixel (i, j) of the operand grid
+// (gh x gw per image) lands at (i*sh + ph, j*sw + pw) of an H x W output image (parity classes of a strided reverse pass)
+struct ConvOutMap {
+  int mode, gh, gw, sh, sw, ph, pw, H, W;
+};
 
 template <int NPROD>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
                                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                               int64_t Mrows, int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile, int KH,
-                               int KW, int base_h, int base_w, int sgn, int kchunks, int num_stages, int fp16_operands, int bn,
-                               int tiles_n, int num_items, int tiles_per_img, int rows_per_tile) {
+                               int64_t Mrows, int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile,
+                               const __grid_constant__ ConvTaps taps, const __grid_constant__ ConvOutMap om, int kchunks,
+                               int num_stages, int fp16_operands, int bn, int tiles_n, int num_items, int tiles_per_img,
+                               int rows_per_tile) {
   const int B_BYTES = bn * BK * 2;
   const int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (TILE_BYTES + B_BYTES);
   const int OFF_B_HI = TILE_BYTES, OFF_A_LO = TILE_BYTES + B_BYTES, OFF_B_LO = 2 * TILE_BYTES + B_BYTES;
@@ -158,7 +171,7 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int total = KH * KW * kchunks;
+  const int total = taps.n * kchunks;
   const int ngroups = (total + CONV_GROUP - 1) / CONV_GROUP;
   const int glen = (total + ngroups - 1) / ngroups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,17 +200,16 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
         int q0 = tm * q_per_tile, h0 = 0;
         if (tiles_per_img > 0) { q0 = tm / tiles_per_img; h0 = (tm - q0 * tiles_per_img) * rows_per_tile; }
         for (int it = 0; it < total; ++it) {
-          const int tap = it / kchunks, kc = it - tap * kchunks;
-          const int kh = tap / KW, kw = tap - kh * KW;
+          const int ti = it / kchunks, kc = it - ti * kchunks;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int ch = h0 + base_h + sgn * kh, cw = base_w + sgn * kw;
+          const int ch = h0 + taps.dh[ti], cw = taps.dw[ti], wrow = taps.w[ti] * N + tn * bn;
           tma_load_4d(&tmX_hi, &full_bar[stage], st, kc * BK, cw, ch, q0);
-          tma_load_2d(&tmW_hi, &full_bar[stage], st + OFF_B_HI, kc * BK, tap * N + tn * bn);
+          tma_load_2d(&tmW_hi, &full_bar[stage], st + OFF_B_HI, kc * BK, wrow);
           if (NPROD == 3) {
             tma_load_4d(&tmX_lo, &full_bar[stage], st + OFF_A_LO, kc * BK, cw, ch, q0);
-            tma_load_2d(&tmW_lo, &full_bar[stage], st + OFF_B_LO, kc * BK, tap * N + tn * bn);
+            tma_load_2d(&tmW_lo, &full_bar[stage], st + OFF_B_LO, kc * BK, wrow);
           }
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
@@ -272,11 +284,18 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
       }
       const int64_t row = (int64_t)tm * BM + q * 32 + lane;
       if (row < Mrows) {
+        int64_t orow = row;
+        if (om.mode == 1) {
+          const int64_t img = row / (om.gh * om.gw);
+          const int rem = (int)(row - img * (om.gh * om.gw));
+          const int i = rem / om.gw, j = rem - i * om.gw;
+          orow = (img * om.H + (i * om.sh + om.ph)) * om.W + (j * om.sw + om.pw);
+        }
 #pragma unroll
         for (int chunk = 0; chunk < 4; ++chunk) {
           const int col0 = tn * bn + chunk * 32;
           if (chunk * 32 < bn && col0 < N) {
-            float* drow = D + row * ldd + col0;
+            float* drow = D + orow * ldd + col0;
             const float* v = accv + chunk * 32;
             if (vec_ok && col0 + 32 <= N) {
 #pragma unroll
@@ -318,10 +337,10 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int64_t Q, int H, i
   return 0;
 }
 
-int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
-                   const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
-                   float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
-  LPB_REQUIRE(Q > 0 && H > 0 && W > 0 && Kc > 0 && N > 0 && KH > 0 && KW > 0, "conv_nhwc_bf16: bad extents");
+static int conv_nhwc_core(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
+                          const void* W_lo, int64_t ldw, int64_t w_rows, int N, const tc::ConvTaps& taps, const tc::ConvOutMap& om,
+                          float alpha, float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
+  LPB_REQUIRE(Q > 0 && H > 0 && W > 0 && Kc > 0 && N > 0 && taps.n > 0, "conv_nhwc_bf16: bad extents");
   const bool big = H * W > 128;   // tiles of 128 / W image rows instead of whole images
   LPB_REQUIRE(big ? (128 % W == 0 && H % (128 / W) == 0) : (128 % (H * W) == 0),
               "conv_nhwc_bf16: %dx%d images do not tile 128-row blocks", H, W);
@@ -334,15 +353,68 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
   CUtensorMap tX_hi, tX_lo, tW_hi, tW_lo;
   const int bn = N <= 64 ? 64 : 128;
   if (make_tmap_nhwc(&tX_hi, X_hi, Q, H, W, Kc, ldx, q_per_tile, rows_per_tile)) return 1;
-  if (make_tmap_2d(&tW_hi, W_hi, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
+  if (make_tmap_2d(&tW_hi, W_hi, w_rows, Kc, ldw, bn)) return 1;
   if (x3) {
     if (make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile, rows_per_tile)) return 1;
-    if (make_tmap_2d(&tW_lo, W_lo, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
+    if (make_tmap_2d(&tW_lo, W_lo, w_rows, Kc, ldw, bn)) return 1;
   } else {
     tX_lo = tX_hi; tW_lo = tW_hi;
   }
   const int64_t Mrows = Q * H * W;
   const int64_t tiles_m = big ? Q * tiles_per_img : ceil_div(Q, q_per_tile);
+  const int tiles_n = (int)ceil_div(N, bn);
+  const int kchunks = (int)ceil_div(Kc, tc::BK);
+  const int stage_bytes = (x3 ? 2 : 1) * (tc::TILE_BYTES + bn * tc::BK * 2);
+  const int64_t items = tiles_m * tiles_n;
+  LPB_REQUIRE(items <= 2147483647LL, "conv_nhwc_bf16: too many tiles");
+  const int pstages = (int)imin(8, (196 * 1024) / stage_bytes);
+  const size_t psmem = (size_t)pstages * stage_bytes + (2 * pstages + 4) * sizeof(uint64_t) + 16 + 1024;
+  static bool pattr1 = false, pattr3 = false;
+  if (x3 && !pattr3) {
+    if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024), "conv_nhwc_bf16 attr"))
+      return 1;
+    pattr3 = true;
+  }
+  if (!x3 && !pattr1) {
+    if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024), "conv_nhwc_bf16 attr"))
+      return 1;
+    pattr1 = true;
+  }
+  const unsigned pgrid = (unsigned)imin(items, sm_count());
+  if (x3)
+    tc::conv_nhwc_tc_persistent_kernel<3><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
+        tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, taps, om, kchunks, pstages, fp16_operands, bn, tiles_n,
+        (int)items, tiles_per_img, rows_per_tile);
+  else
+    tc::conv_nhwc_tc_persistent_kernel<1><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
+        tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, taps, om, kchunks, pstages, fp16_operands, bn, tiles_n,
+        (int)items, tiles_per_img, rows_per_tile);
+  LPB_CHECK_LAUNCH("conv_nhwc_bf16 (persistent)");
+  return 0;
+}
+
+// one-tile-per-CTA schedule (A/B timing only, LPB_CONV_MODE=0; whole-image tiles)
+static int conv_nhwc_single(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
+                            const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
+                            float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
+  LPB_REQUIRE(H * W <= 128 && 128 % (H * W) == 0, "conv_nhwc_bf16: LPB_CONV_MODE=0 needs H*W dividing 128");
+  LPB_REQUIRE((ldx % 8) == 0 && (ldw % 8) == 0 && ldx >= Kc && ldw >= Kc, "conv_nhwc_bf16: bad leading dimensions");
+  const bool x3 = X_lo != nullptr;
+  const int q_per_tile = 128 / (H * W);
+  CUtensorMap tX_hi, tX_lo, tW_hi, tW_lo;
+  const int bn = N <= 64 ? 64 : 128;
+  if (make_tmap_nhwc(&tX_hi, X_hi, Q, H, W, Kc, ldx, q_per_tile)) return 1;
+  if (make_tmap_2d(&tW_hi, W_hi, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
+  if (x3) {
+    if (make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile)) return 1;
+    if (make_tmap_2d(&tW_lo, W_lo, (int64_t)KH * KW * N, Kc, ldw, bn)) return 1;
+  } else {
+    tX_lo = tX_hi; tW_lo = tW_hi;
+  }
+  const int64_t Mrows = Q * H * W;
+  const int64_t tiles_m = ceil_div(Q, q_per_tile);
   const int tiles_n = (int)ceil_div(N, bn);
   LPB_REQUIRE(tiles_m <= 2147483647LL && tiles_n <= 65535, "conv_nhwc_bf16: too many tiles");
   const int kchunks = (int)ceil_div(Kc, tc::BK);
@@ -362,42 +434,6 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
       return 1;
     attr1 = true;
   }
-  static int conv_mode = -1;
-  if (conv_mode < 0) {
-    const char* e = getenv("LPB_CONV_MODE");   // 0: one tile per CTA (A/B timing); default: persistent CTAs
-    conv_mode = e ? (atoi(e) != 0 ? 1 : 0) : 1;
-  }
-  if (conv_mode == 1) {
-    const int64_t items = tiles_m * tiles_n;
-    LPB_REQUIRE(items <= 2147483647LL, "conv_nhwc_bf16: too many tiles");
-    const int pstages = (int)imin(8, (196 * 1024) / stage_bytes);
-    const size_t psmem = (size_t)pstages * stage_bytes + (2 * pstages + 4) * sizeof(uint64_t) + 16 + 1024;
-    static bool pattr1 = false, pattr3 = false;
-    if (x3 && !pattr3) {
-      if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          227 * 1024), "conv_nhwc_bf16 attr"))
-        return 1;
-      pattr3 = true;
-    }
-    if (!x3 && !pattr1) {
-      if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          227 * 1024), "conv_nhwc_bf16 attr"))
-        return 1;
-      pattr1 = true;
-    }
-    const unsigned pgrid = (unsigned)imin(items, sm_count());
-    if (x3)
-      tc::conv_nhwc_tc_persistent_kernel<3><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
-          tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, KH, KW, base_h, base_w, sgn, kchunks, pstages,
-          fp16_operands, bn, tiles_n, (int)items, tiles_per_img, rows_per_tile);
-    else
-      tc::conv_nhwc_tc_persistent_kernel<1><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
-          tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, KH, KW, base_h, base_w, sgn, kchunks, pstages,
-          fp16_operands, bn, tiles_n, (int)items, tiles_per_img, rows_per_tile);
-    LPB_CHECK_LAUNCH("conv_nhwc_bf16 (persistent)");
-    return 0;
-  }
-  LPB_REQUIRE(!big, "conv_nhwc_bf16: images larger than 128 pixels need the persistent kernel (LPB_CONV_MODE unset)");
   dim3 grid((unsigned)tiles_m, (unsigned)tiles_n);
   if (x3)
     tc::conv_nhwc_tc_kernel<3><<<grid, tc::NUM_THREADS, smem, st>>>(tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd,
@@ -408,6 +444,81 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
                                                                     q_per_tile, KH, KW, base_h, base_w, sgn, kchunks,
                                                                     num_stages, fp16_operands, bn);
   LPB_CHECK_LAUNCH("conv_nhwc_bf16");
+  return 0;
+}
+
+int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, int64_t Kc, int64_t ldx, const void* W_hi,
+                   const void* W_lo, int64_t ldw, int N, int KH, int KW, int base_h, int base_w, int sgn, float alpha,
+                   float* D, int64_t ldd, int fp16_operands, cudaStream_t st) {
+  LPB_REQUIRE(KH > 0 && KW > 0 && KH * KW <= tc::MAX_TAPS, "conv_nhwc_bf16: between 1 and %d taps", tc::MAX_TAPS);
+  static int conv_mode = -1;
+  if (conv_mode < 0) {
+    const char* e = getenv("LPB_CONV_MODE");   // 0: one tile per CTA (A/B timing); default: persistent CTAs
+    conv_mode = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+  }
+  if (conv_mode == 0 && H * W <= 128)
+    return conv_nhwc_single(X_hi, X_lo, Q, H, W, Kc, ldx, W_hi, W_lo, ldw, N, KH, KW, base_h, base_w, sgn, alpha, D, ldd,
+                            fp16_operands, st);
+  tc::ConvTaps taps = {};
+  taps.n = KH * KW;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      const int t = kh * KW + kw;
+      taps.w[t] = (short)t; taps.dh[t] = (short)(base_h + sgn * kh); taps.dw[t] = (short)(base_w + sgn * kw);
+    }
+  tc::ConvOutMap om = {};
+  return conv_nhwc_core(X_hi, X_lo, Q, H, W, Kc, ldx, W_hi, W_lo, ldw, (int64_t)KH * KW * N, N, taps, om, alpha, D, ldd,
+                        fp16_operands, st);
+}
+
+// Backward-data of a STRIDED convolution as implicit GEMMs: input pixel (h, w) only receives taps with
+// kh = h + PH (mod SH), kw = w + PW (mod SW), so the input gradient splits into SH*SW parity classes, each a stride-1
+// convolution of the output-gradient grid with its own subset of taps, written to the class's pixels of the NHWC result
+// (no [rows, KH*KW*C_in] intermediate, no col2im).  G: gradient rows [(q,oh,ow), Co]; Wt [(kh,kw,ci), Co] tap-major.
+int conv_bwd_strided(const void* G_hi, const void* G_lo, int64_t Q, int OH, int OW, int64_t Co, int64_t ldg, const void* W_hi,
+                     const void* W_lo, int64_t ldw, int Ci, int KH, int KW, int SH, int SW, int PH, int PW, int H, int W,
+                     float* D, int64_t ldd, cudaStream_t st) {
+  LPB_REQUIRE(SH >= 1 && SW >= 1 && KH >= 1 && KW >= 1 && KH * KW <= tc::MAX_TAPS, "conv_bwd_strided: bad geometry");
+  LPB_REQUIRE(H == OH * SH && W == OW * SW, "conv_bwd_strided: input extent must be stride x output extent (got %dx%d vs %dx%d)",
+              H, W, OH, OW);
+  LPB_REQUIRE(ldd >= Ci, "conv_bwd_strided: ldd too small");
+  bool empty_class = false;
+  for (int p = 0; p < SH; ++p)
+    for (int q = 0; q < SW; ++q) {
+      tc::ConvTaps taps = {};
+      for (int kh = 0; kh < KH; ++kh) {
+        if ((p + PH - kh) % SH != 0) continue;            // h = oh*SH - PH + kh with h = i*SH + p
+        for (int kw = 0; kw < KW; ++kw) {
+          if ((q + PW - kw) % SW != 0) continue;
+          const int t = taps.n++;
+          taps.w[t] = (short)(kh * KW + kw);
+          taps.dh[t] = (short)((p + PH - kh) / SH);         // oh = i + dh   (C division: exact here)
+          taps.dw[t] = (short)((q + PW - kw) / SW);
+        }
+      }
+      if (taps.n == 0) empty_class = true;
+    }
+  if (empty_class &&
+      check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, (size_t)Ci * sizeof(float), (size_t)Q * H * W, st), "conv_bwd_strided memset"))
+    return 1;
+  for (int p = 0; p < SH; ++p)
+    for (int q = 0; q < SW; ++q) {
+      tc::ConvTaps taps = {};
+      for (int kh = 0; kh < KH; ++kh) {
+        if ((p + PH - kh) % SH != 0) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          if ((q + PW - kw) % SW != 0) continue;
+          const int t = taps.n++;
+          taps.w[t] = (short)(kh * KW + kw);
+          taps.dh[t] = (short)((p + PH - kh) / SH);
+          taps.dw[t] = (short)((q + PW - kw) / SW);
+        }
+      }
+      if (taps.n == 0) continue;
+      tc::ConvOutMap om = {1, OH, OW, SH, SW, p, q, H, W};
+      if (conv_nhwc_core(G_hi, G_lo, Q, OH, OW, Co, ldg, W_hi, W_lo, ldw, (int64_t)KH * KW * Ci, Ci, taps, om, 1.0f, D, ldd, 0, st))
+        return 1;
+    }
   return 0;
 }
 

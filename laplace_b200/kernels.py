@@ -352,6 +352,20 @@ def conv_nhwc(X: Packed, Q: int, H: int, W: int, Wt: Packed, N: int, KH: int, KW
     return out
 
 
+def conv_bwd_strided(G: Packed, Q: int, OH: int, OW: int, Wt: Packed, mod, in_shape) -> torch.Tensor:
+    """Input gradient of a strided convolution from the output-gradient rows ``G [(q,oh,ow), C_out]`` and the tap-major
+    weights ``Wt [(kh,kw,ci), C_out]``: one implicit GEMM per stride parity class, written in place into the NHWC result
+    (returned as a channels-last view ``[Q, C_in, H, W]``)."""
+    _, Ci, H, W = in_shape
+    kh, kw = mod.kernel_size
+    assert G.kind in (BF16, BF16X3) and G.kind == Wt.kind and G.rows == Q * OH * OW and Wt.rows == kh * kw * Ci and G.K == Wt.K
+    out = torch.empty(Q, H, W, Ci, device=G.hi.device, dtype=torch.float32)
+    _lib.call("lpb_conv_bwd_strided_tc", _ptr(G.hi), _ptr(G.lo), Q, OH, OW, G.K, G.ldk, _ptr(Wt.hi), _ptr(Wt.lo), Wt.ldk, Ci,
+              kh, kw, mod.stride[0], mod.stride[1], mod.padding[0], mod.padding[1], H, W, _ptr(out), out.stride(2), _stream())
+    _bump(mod.stride[0] * mod.stride[1])
+    return out.permute(0, 3, 1, 2)
+
+
 def gemm_tn(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumulate: bool = True,
             symmetric: bool = False) -> torch.Tensor:
     """``out[M,N] (+)= alpha * A^T B`` for ROW-major 16-bit operands ``A [K_rows, M]``, ``B [K_rows, N]``

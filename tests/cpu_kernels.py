@@ -167,7 +167,7 @@ def install(monkeypatch):
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "diag_conv_sq", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "diag_conv_sq", "conv_bwd_strided", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)
@@ -231,6 +231,16 @@ def diag_conv_sq(G, X, Nimg, H, W, mod, out, alpha=1.0):
     per = torch.einsum("cnto,ntp->cnop", g, P)
     out += alpha * (per * per).sum((0, 1))
     return out
+
+
+def conv_bwd_strided(G, Q, OH, OW, Wt, mod, in_shape):
+    _, Ci, H, W = in_shape
+    Co = G.K
+    kh, kw = mod.kernel_size
+    g = G.hi[:, :Co].reshape(Q, OH, OW, Co).permute(0, 3, 1, 2).float()
+    w = Wt.hi[:, :Co].reshape(kh, kw, Ci, Co).permute(3, 2, 0, 1).float()          # [Co, Ci, kh, kw]
+    out = torch.nn.grad.conv2d_input((Q, Ci, H, W), w, g, mod.stride, mod.padding, mod.dilation)
+    return out.contiguous(memory_format=torch.channels_last)
 
 
 def col2im_nhwc(Dc, in_shape, mod):
