@@ -405,8 +405,16 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
              "gemm_tn": "tc::gemm_tc_persistent_kernel<.,1> (tcgen05 SYRK on row-major operands, MN-major descriptors: KFAC factor contractions)",
              "syrk_conv_patches": "tc::gemm_tc_persistent_kernel<.,2> (tcgen05 SYRK on implicit convolution patches, shifted 4-D TMA boxes: KFAC input factors)",
              "conv_nhwc": "tc::conv_nhwc_tc_persistent_kernel (tcgen05 implicit-GEMM convolution, forward + backward-data)"}
+    # DRAM bytes per launch of the dominant family from the committed ncu launch list of the same workload (a number
+    # taken under a profiler is never a bench value; it only annotates the roofline entry)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_run26.json")
+    if args.model == "resnet18" and args.batch == 4096 and args.precision == "bf16x3" and os.path.exists(tpath):
+        traffic = json.load(open(tpath))["families"].get(dom, {}).get("dram_bytes_per_launch")
     return {"bound": "tensor" if tensor else "hbm", "kernel": names.get(dom, "lpb::" + dom + "_kernel"),
-            "achieved": d["achieved"], "peak": peak, "unit": d["unit"], "frac": d["achieved"] / peak, "traffic": None,
+            "achieved": d["achieved"], "peak": peak, "unit": d["unit"], "frac": d["achieved"] / peak, "traffic": traffic,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu launch list of the same command "
+                            "(profiles/r01_ncu_traffic_run26.json)" if traffic else "",
             "peak_source": pk["source"] + (", bf16 sustained" if tensor else ", copy bandwidth"),
             "note": "algorithmic FLOPs (one product per MAC) over CUDA-event time; precision bf16x3 issues 3 tensor-core "
                     "products per algorithmic MAC, so the tensor pipe does 3x the counted work" if tensor and args.precision == "bf16x3" else "",

@@ -133,8 +133,8 @@ int lpb_conv_bwd_strided_tc(const void* G_hi, const void* G_lo, int64_t Q, int O
 
 /* ---- KFAC input factor of a stride-1 'same' convolution without im2col -----------------------------------------
  * D[(t,ci),(t',cj)] (+)= alpha * sum_{n,h,w} x[n,h+kh-PH,w+kw-PW,ci] * x[n,h+kh'-PH,w+kw'-PW,cj]   (zero padding),
- * t = kh*KW + kw, feature (t,ci) at index t*Ci_pad + ci with Ci_pad = Ci rounded up to 64 (D is [KH*KW*Ci_pad]^2, padded
- * rows / columns exactly zero); x given as 16-bit hi(/lo) NHWC rows [(n,h,w), Ci] (ldx).
+ * t = kh*KW + kw; the i-th LIVE tap's feature (t,ci) sits at index i*Ci_pad + ci with Ci_pad = Ci rounded up to 64
+ * (D is [live*Ci_pad]^2, live = lpb_conv_live_taps(...), padded rows / columns exactly zero); x given as 16-bit hi(/lo) NHWC rows [(n,h,w), Ci] (ldx).
  * Replaces unfold + einsum("b t i, b t j -> i j") behind reference laplace/curvature/curvlinops.py:100 for those
  * layers; the 9x larger patch matrix is never formed (shifted 4-D TMA boxes feed the tensor cores directly).
  * Needs H*W dividing 64 or (W | 64 and 64/W | H).  D is symmetric (both triangles written).                      */
@@ -153,9 +153,14 @@ int lpb_diag_conv_sq_tc(const void* G_hi, const void* G_lo, int64_t ldg, const v
                         int accumulate, float* D, int64_t ldd, void* stream);
 int lpb_taps_to_param_rect(const float* Dt, int64_t ldt, int Co, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
                            void* stream);
-/* out[(ci*KK+t), (cj*KK+t')] += T[(t*Ci_pad+ci), (t'*Ci_pad+cj)]: tap-major factor -> parameter order (ci,kh,kw), KK <= 9 */
-int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
-                                 void* stream);
+/* Kernel positions whose window overlaps an H x W image at all (|kh-PH| < H and |kw-PW| < W); the others only read
+ * zero padding.  lpb_syrk_conv_patches_tc computes the LIVE taps only: D is [live*Ci_pad]^2, live taps in ascending
+ * kernel position.                                                                                               */
+int lpb_conv_live_taps(int KH, int KW, int PH, int PW, int H, int W);
+/* out[(ci*KK+t), (cj*KK+t')] += T[(i*Ci_pad+ci), (i'*Ci_pad+cj)] for live taps t = tap(i), t' = tap(i'): tap-major
+ * factor of lpb_syrk_conv_patches_tc -> parameter order (ci,kh,kw); KK = KH*KW <= 9                              */
+int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KH, int KW, int PH, int PW, int H, int W,
+                                 float* out, int64_t ldo, void* stream);
 
 /* ---- reverse-pass element-wise maps of the convolution engine (columns folded into the batch) -----------------
  * out[i] = g[i] * scale[(i / inner) % C]                 frozen BatchNorm as per-channel affine map (backward)   */

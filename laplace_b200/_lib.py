@@ -26,7 +26,8 @@ SIGNATURES = {
     "lpb_pack_cast": [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_i64, c_vp],
     "lpb_col2im": [c_vp, c_i64] + [c_int] * 12 + [c_vp, c_vp],
     "lpb_syrk_conv_patches_tc": [c_vp, c_vp, c_i64, c_i64] + [c_int] * 7 + [c_f32, c_int, c_vp, c_i64, c_int, c_vp],
-    "lpb_taps_to_param_accumulate": [c_vp, c_i64, c_int, c_int, c_int, c_vp, c_i64, c_vp],
+    "lpb_conv_live_taps": [c_int] * 6,
+    "lpb_taps_to_param_accumulate": [c_vp, c_i64] + [c_int] * 8 + [c_vp, c_i64, c_vp],
     "lpb_diag_conv_sq_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64] + [c_int] * 8 + [c_f32, c_int, c_vp, c_i64, c_vp],
     "lpb_taps_to_param_rect": [c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp],
     "lpb_conv_bwd_strided_tc": [c_vp, c_vp, c_i64, c_int, c_int, c_i64, c_i64, c_vp, c_vp, c_i64] + [c_int] * 9 + [c_vp, c_i64, c_vp],

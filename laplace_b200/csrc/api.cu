@@ -62,7 +62,8 @@ int eigh_jacobi(const float*, int, int, float*, float*, int, cudaStream_t);
 void set_gemm_pair_mode(int mode);
 int syrk_conv_patches(const void*, const void*, int64_t, int64_t, int, int, int, int, int, int, int, float, int, float*, int64_t,
                       int, cudaStream_t);
-int taps_to_param_accumulate(const float*, int64_t, int, int, int, float*, int64_t, cudaStream_t);
+int taps_to_param_accumulate(const float*, int64_t, int, int, int, int, int, int, int, int, float*, int64_t, cudaStream_t);
+int syrk_conv_live_taps(int KH, int KW, int PH, int PW, int H, int W);
 int diag_conv_sq(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int, int, int, int, int,
                  int, int, int, float, int, float*, int64_t, cudaStream_t);
 int taps_to_param_rect(const float*, int64_t, int, int, int, int, float*, int64_t, cudaStream_t);
@@ -179,10 +180,13 @@ int lpb_syrk_conv_patches_tc(const void* X_hi, const void* X_lo, int64_t ldx, in
                                 ST(stream));
 }
 
-int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
-                                 void* stream) {
-  LPB_REQUIRE(ldt >= (int64_t)Ci_pad * KK && ldo >= (int64_t)Ci * KK, "lpb_taps_to_param_accumulate: leading dimension too small");
-  return lpb::taps_to_param_accumulate(T, ldt, Ci, Ci_pad, KK, out, ldo, ST(stream));
+int lpb_conv_live_taps(int KH, int KW, int PH, int PW, int H, int W) { return lpb::syrk_conv_live_taps(KH, KW, PH, PW, H, W); }
+
+int lpb_taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KH, int KW, int PH, int PW, int H, int W,
+                                 float* out, int64_t ldo, void* stream) {
+  LPB_REQUIRE(KH > 0 && KW > 0 && KH * KW <= 9, "lpb_taps_to_param_accumulate: kernel window larger than 9 taps");
+  LPB_REQUIRE(ldo >= (int64_t)Ci * KH * KW, "lpb_taps_to_param_accumulate: leading dimension too small");
+  return lpb::taps_to_param_accumulate(T, ldt, Ci, Ci_pad, KH, KW, PH, PW, H, W, out, ldo, ST(stream));
 }
 
 int lpb_diag_conv_sq_tc(const void* G_hi, const void* G_lo, int64_t ldg, const void* X_hi, const void* X_lo, int64_t ldx,

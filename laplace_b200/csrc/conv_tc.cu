@@ -459,13 +459,20 @@ int conv_nhwc_bf16(const void* X_hi, const void* X_lo, int64_t Q, int H, int W, 
   if (conv_mode == 0 && H * W <= 128)
     return conv_nhwc_single(X_hi, X_lo, Q, H, W, Kc, ldx, W_hi, W_lo, ldw, N, KH, KW, base_h, base_w, sgn, alpha, D, ldd,
                             fp16_operands, st);
+  // taps whose shifted window lies entirely outside the image (|shift| >= extent: 3x3 kernels on 1x1 / 2x2 maps)
+  // only ever read the zero padding -- drop them from the launch
   tc::ConvTaps taps = {};
-  taps.n = KH * KW;
   for (int kh = 0; kh < KH; ++kh)
     for (int kw = 0; kw < KW; ++kw) {
-      const int t = kh * KW + kw;
-      taps.w[t] = (short)t; taps.dh[t] = (short)(base_h + sgn * kh); taps.dw[t] = (short)(base_w + sgn * kw);
+      const int dh = base_h + sgn * kh, dw = base_w + sgn * kw;
+      if (dh >= H || dh <= -H || dw >= W || dw <= -W) continue;
+      const int t = taps.n++;
+      taps.w[t] = (short)(kh * KW + kw); taps.dh[t] = (short)dh; taps.dw[t] = (short)dw;
     }
+  if (taps.n == 0) {   // every tap reads padding only: the output is zero
+    return check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)Q * H * W, st),
+                      "conv_nhwc_bf16 memset");
+  }
   tc::ConvOutMap om = {};
   return conv_nhwc_core(X_hi, X_lo, Q, H, W, Kc, ldx, W_hi, W_lo, ldw, (int64_t)KH * KW * N, N, taps, om, alpha, D, ldd,
                         fp16_operands, st);
@@ -482,38 +489,33 @@ int conv_bwd_strided(const void* G_hi, const void* G_lo, int64_t Q, int OH, int 
   LPB_REQUIRE(H == OH * SH && W == OW * SW, "conv_bwd_strided: input extent must be stride x output extent (got %dx%d vs %dx%d)",
               H, W, OH, OW);
   LPB_REQUIRE(ldd >= Ci, "conv_bwd_strided: ldd too small");
+  // taps of parity class (p, q); a tap whose shifted window lies entirely outside the gradient grid reads padding only
+  auto class_taps = [&](int p, int q) {
+    tc::ConvTaps taps = {};
+    for (int kh = 0; kh < KH; ++kh) {
+      if ((p + PH - kh) % SH != 0) continue;              // h = oh*SH - PH + kh with h = i*SH + p
+      for (int kw = 0; kw < KW; ++kw) {
+        if ((q + PW - kw) % SW != 0) continue;
+        const int dh = (p + PH - kh) / SH, dw = (q + PW - kw) / SW;   // oh = i + dh (exact division)
+        if (dh >= OH || dh <= -OH || dw >= OW || dw <= -OW) continue;
+        const int t = taps.n++;
+        taps.w[t] = (short)(kh * KW + kw);
+        taps.dh[t] = (short)dh;
+        taps.dw[t] = (short)dw;
+      }
+    }
+    return taps;
+  };
   bool empty_class = false;
   for (int p = 0; p < SH; ++p)
-    for (int q = 0; q < SW; ++q) {
-      tc::ConvTaps taps = {};
-      for (int kh = 0; kh < KH; ++kh) {
-        if ((p + PH - kh) % SH != 0) continue;            // h = oh*SH - PH + kh with h = i*SH + p
-        for (int kw = 0; kw < KW; ++kw) {
-          if ((q + PW - kw) % SW != 0) continue;
-          const int t = taps.n++;
-          taps.w[t] = (short)(kh * KW + kw);
-          taps.dh[t] = (short)((p + PH - kh) / SH);         // oh = i + dh   (C division: exact here)
-          taps.dw[t] = (short)((q + PW - kw) / SW);
-        }
-      }
-      if (taps.n == 0) empty_class = true;
-    }
+    for (int q = 0; q < SW; ++q)
+      if (class_taps(p, q).n == 0) empty_class = true;
   if (empty_class &&
       check_cuda(cudaMemset2DAsync(D, ldd * sizeof(float), 0, (size_t)Ci * sizeof(float), (size_t)Q * H * W, st), "conv_bwd_strided memset"))
     return 1;
   for (int p = 0; p < SH; ++p)
     for (int q = 0; q < SW; ++q) {
-      tc::ConvTaps taps = {};
-      for (int kh = 0; kh < KH; ++kh) {
-        if ((p + PH - kh) % SH != 0) continue;
-        for (int kw = 0; kw < KW; ++kw) {
-          if ((q + PW - kw) % SW != 0) continue;
-          const int t = taps.n++;
-          taps.w[t] = (short)(kh * KW + kw);
-          taps.dh[t] = (short)((p + PH - kh) / SH);
-          taps.dw[t] = (short)((q + PW - kw) / SW);
-        }
-      }
+      const tc::ConvTaps taps = class_taps(p, q);
       if (taps.n == 0) continue;
       tc::ConvOutMap om = {1, OH, OW, SH, SW, p, q, H, W};
       if (conv_nhwc_core(G_hi, G_lo, Q, OH, OW, Co, ldg, W_hi, W_lo, ldw, (int64_t)KH * KW * Ci, Ci, taps, om, 1.0f, D, ldd, 0, st))

@@ -103,10 +103,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
 #pragma unroll
               for (int b = 0; b < 2; ++b) {
                 const int fb = tile * 2 + b;
-                const int tap = fb / pg.blocks_per_tap;
+                const int live = fb / pg.blocks_per_tap;
+                const int tap = pg.tap_of[live < pg.num_taps ? live : 0];
                 const int kh = tap / pg.KW, kw = tap - kh * pg.KW;
                 // feature blocks past the last tap read channel coordinate Ci: entirely out of bounds = zeros
-                const int ci0 = tap < pg.num_taps ? (fb - tap * pg.blocks_per_tap) * 64 : pg.Ci;
+                const int ci0 = live < pg.num_taps ? (fb - live * pg.blocks_per_tap) * 64 : pg.Ci;
                 tma_load_4d(map, &full_bar[stage], dst + b * (TILE_BYTES / 2), ci0, kw - pg.PW, h0 + kh - pg.PH, n0);
               }
             } else if (MN) {
@@ -381,7 +382,15 @@ int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q
   // channel counts that are not a multiple of 64 are padded per tap: feature (t, ci) sits at t * Ci_pad + ci, the
   // TMA unit zero-fills channel coordinates >= Ci, so the padded rows / columns of D come out exactly zero
   const int Ci_pad = (int)ceil_div(Ci, 64) * 64;
-  pg.KW = KW; pg.PH = PH; pg.PW = PW; pg.Ci = Ci; pg.num_taps = KH * KW; pg.blocks_per_tap = Ci_pad / 64;
+  pg.KW = KW; pg.PH = PH; pg.PW = PW; pg.Ci = Ci; pg.blocks_per_tap = Ci_pad / 64;
+  LPB_REQUIRE(KH * KW <= 16, "syrk_conv_patches: at most 16 taps");
+  // taps whose window lies entirely in the padding (|shift| >= image extent: 3x3 kernels on 1x1 maps) contribute zero
+  // rows / columns: only the `num_taps` live ones are computed, D is [num_taps * Ci_pad]^2 over the live taps in
+  // ascending kernel position (live_taps() tells the caller which)
+  pg.num_taps = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw)
+      if (kh - PH < H && PH - kh < H && kw - PW < W && PW - kw < W) pg.tap_of[pg.num_taps++] = (unsigned char)(kh * KW + kw);
   int box_h, box_n;
   if (HW >= 64) {
     LPB_REQUIRE(64 % W == 0 && H % (64 / W) == 0, "syrk_conv_patches: %dx%d images do not tile 64-row chunks", H, W);
@@ -392,8 +401,8 @@ int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q
     pg.rows_per_chunk = H; pg.chunks_per_img = 0; pg.imgs_per_chunk = 64 / HW;
     box_h = H; box_n = pg.imgs_per_chunk;
   }
-  const int64_t d = (int64_t)KH * KW * Ci_pad;
-  LPB_REQUIRE(ldd >= d, "syrk_conv_patches: ldd too small (D is [KH*KW*Ci_pad]^2, Ci_pad = C_in rounded up to 64)");
+  const int64_t d = (int64_t)pg.num_taps * Ci_pad;
+  LPB_REQUIRE(ldd >= d, "syrk_conv_patches: ldd too small (D is [live_taps*Ci_pad]^2, Ci_pad = C_in rounded up to 64)");
   const int64_t kchunks64 = HW >= 64 ? Q * pg.chunks_per_img : ceil_div(Q, (int64_t)pg.imgs_per_chunk);
   LPB_REQUIRE(kchunks64 < (1LL << 31), "syrk_conv_patches: too many sample rows");
   const int total_kchunks = (int)kchunks64;
@@ -436,6 +445,8 @@ int diag_conv_sq(const void* G_hi, const void* G_lo, int64_t ldg, const void* X_
   pg.KW = KW; pg.PH = PH; pg.PW = PW; pg.Ci = Ci; pg.num_taps = KH * KW; pg.blocks_per_tap = Ci_pad / 64;
   pg.rows_per_chunk = 64 / W; pg.chunks_per_img = HW / 64; pg.imgs_per_chunk = 0;
   pg.n_images = (int)Nimg; pg.group_chunks = pg.chunks_per_img;
+  LPB_REQUIRE(KH * KW <= 16, "diag_conv_sq: at most 16 taps");
+  for (int t = 0; t < KH * KW; ++t) pg.tap_of[t] = (unsigned char)t;
   LPB_REQUIRE(pg.group_chunks <= 64, "diag_conv_sq: images larger than 4096 pixels are not supported");
   const int64_t Ncols = (int64_t)KH * KW * Ci_pad;
   LPB_REQUIRE(ldd >= Ncols, "diag_conv_sq: ldd too small");
@@ -489,33 +500,54 @@ int taps_to_param_rect(const float* Dt, int64_t ldt, int Co, int Ci, int Ci_pad,
 // out[(ci*KK + t), (cj*KK + t')] += T[(t*Cp + ci), (t'*Cp + cj)]   (KK = KH*KW <= 9, Cp = padded channel stride of T).
 // One CTA per (ci, 32 cj's): the KK x KK x 32 block is read in 128-byte runs, staged in shared memory and written as
 // KK runs of 32*KK floats.
+// number of kernel positions whose window overlaps a H x W image at all (the others only ever read zero padding)
+int syrk_conv_live_taps(int KH, int KW, int PH, int PW, int H, int W) {
+  int n = 0;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw)
+      if (kh - PH < H && PH - kh < H && kw - PW < W && PW - kw < W) ++n;
+  return n;
+}
+
+struct TapMap {
+  int n;                 // live taps (rows / columns of T per channel block)
+  unsigned char of[16];  // live index -> kernel position
+};
+
 __global__ void __launch_bounds__(256) taps_to_param_kernel(const float* __restrict__ T, int64_t ldt, int Ci, int Cp, int KK,
-                                                            float* __restrict__ out, int64_t ldo) {
+                                                            TapMap tm, float* __restrict__ out, int64_t ldo) {
   __shared__ float s[9 * 9 * 32];
   const int ci = blockIdx.y, cj0 = blockIdx.x * 32;
   const int ncj = min(32, Ci - cj0);
-  for (int e = threadIdx.x; e < KK * KK * 32; e += blockDim.x) {
-    const int cjl = e & 31, tt = e >> 5;          // tt = t * KK + t'
-    const int t = tt / KK, t2 = tt - t * KK;
+  const int L = tm.n;
+  for (int e = threadIdx.x; e < L * L * 32; e += blockDim.x) {
+    const int cjl = e & 31, tt = e >> 5;          // tt = i * L + i'  (live indices)
+    const int t = tt / L, t2 = tt - t * L;
     if (cjl < ncj) s[e] = T[(int64_t)(t * Cp + ci) * ldt + t2 * Cp + cj0 + cjl];
   }
   __syncthreads();
-  const int run = ncj * KK;
-  for (int e = threadIdx.x; e < KK * run; e += blockDim.x) {
+  const int run = ncj * L;
+  for (int e = threadIdx.x; e < L * run; e += blockDim.x) {
     const int t = e / run, r = e - t * run;
-    const int cjl = r / KK, t2 = r - cjl * KK;
-    float* dst = out + (int64_t)(ci * KK + t) * ldo + (int64_t)cj0 * KK + r;
-    *dst += s[(t * KK + t2) * 32 + cjl];
+    const int cjl = r / L, t2 = r - cjl * L;
+    float* dst = out + (int64_t)(ci * KK + tm.of[t]) * ldo + (int64_t)(cj0 + cjl) * KK + tm.of[t2];
+    *dst += s[(t * L + t2) * 32 + cjl];
   }
 }
 
-int taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KK, float* out, int64_t ldo,
-                             cudaStream_t st) {
+int taps_to_param_accumulate(const float* T, int64_t ldt, int Ci, int Ci_pad, int KH, int KW, int PH, int PW, int H, int W,
+                             float* out, int64_t ldo, cudaStream_t st) {
+  const int KK = KH * KW;
   LPB_REQUIRE(Ci_pad >= Ci, "taps_to_param_accumulate: padded channel stride smaller than the channel count");
+  TapMap tm = {};
+  for (int kh = 0; kh < KH; ++kh)     // same live-tap rule as syrk_conv_patches
+    for (int kw = 0; kw < KW; ++kw)
+      if (kh - PH < H && PH - kh < H && kw - PW < W && PW - kw < W) tm.of[tm.n++] = (unsigned char)(kh * KW + kw);
+  LPB_REQUIRE(ldt >= (int64_t)tm.n * Ci_pad, "taps_to_param_accumulate: ldt too small");
   LPB_REQUIRE(KK >= 1 && KK <= 9, "taps_to_param_accumulate: kernel window larger than 9 taps");
   LPB_REQUIRE(Ci > 0 && Ci <= 65535, "taps_to_param_accumulate: bad channel count");
   dim3 grid((unsigned)ceil_div(Ci, 32), (unsigned)Ci);
-  taps_to_param_kernel<<<grid, 256, 0, st>>>(T, ldt, Ci, Ci_pad, KK, out, ldo);
+  taps_to_param_kernel<<<grid, 256, 0, st>>>(T, ldt, Ci, Ci_pad, KK, tm, out, ldo);
   LPB_CHECK_LAUNCH("taps_to_param_accumulate");
   return 0;
 }

@@ -399,12 +399,15 @@ def syrk_conv_patches(X: Packed, Q: int, H: int, W: int, mod, out: torch.Tensor,
     Ci = X.K
     d = Ci * kh * kw
     Ci_pad = -(-Ci // 64) * 64
-    dp = Ci_pad * kh * kw
+    ph, pw = mod.padding
+    live = sum(1 for a in range(kh) for b in range(kw) if abs(a - ph) < H and abs(b - pw) < W)   # == lpb_conv_live_taps
+    dp = Ci_pad * live
     assert out.shape == (d, d) and X.rows == Q * H * W and X.kind in (BF16, BF16X3, F16X3)
     T = torch.empty(dp, dp, device=out.device, dtype=torch.float32)
     _lib.call("lpb_syrk_conv_patches_tc", _ptr(X.hi), _ptr(X.lo), X.ldk, Q, H, W, Ci, kh, kw, mod.padding[0], mod.padding[1],
               alpha, 0, _ptr(T), T.stride(0), 1 if X.kind == F16X3 else 0, _stream())
-    _lib.call("lpb_taps_to_param_accumulate", _ptr(T), T.stride(0), Ci, Ci_pad, kh * kw, _ptr(out), out.stride(0), _stream())
+    _lib.call("lpb_taps_to_param_accumulate", _ptr(T), T.stride(0), Ci, Ci_pad, kh, kw, ph, pw, H, W, _ptr(out), out.stride(0),
+              _stream())
     _bump(2)
     return out
 
