@@ -42,3 +42,14 @@ def test_product_path_refuses_cpu_tensors():
     model = torch.nn.Sequential(torch.nn.Linear(3, 2))
     with pytest.raises(RuntimeError):
         B200GGN(model, "classification").kron(torch.randn(4, 3), torch.tensor([0, 1, 0, 1]), N=4)
+
+
+def test_live_tap_rule_matches_python_wrapper():
+    """``lpb_conv_live_taps`` (host-only helper): kernel positions whose window overlaps the image at all -- the rule the
+    Python wrapper of the im2col-free factor uses to size its scratch buffer."""
+    lib = _lib.load()
+    for kh, kw, ph, pw, H, W in [(3, 3, 1, 1, 1, 1), (3, 3, 1, 1, 2, 2), (3, 3, 1, 1, 8, 8), (1, 1, 0, 0, 1, 1), (3, 1, 1, 0, 1, 4),
+                                 (3, 3, 1, 1, 1, 5)]:
+        want = sum(1 for a in range(kh) for b in range(kw) if abs(a - ph) < H and abs(b - pw) < W)
+        assert lib.lpb_conv_live_taps(kh, kw, ph, pw, H, W) == want
+    assert lib.lpb_conv_live_taps(3, 3, 1, 1, 1, 1) == 1 and lib.lpb_conv_live_taps(3, 3, 1, 1, 2, 2) == 9

@@ -110,7 +110,9 @@ def test_layer_gradients_match_fp64_autograd(name, kw):
 @pytest.mark.parametrize("geom", [(64, 8, 8, 3, 70), (128, 4, 4, 3, 130), (64, 2, 2, 3, 33), (256, 1, 1, 3, 200), (64, 16, 16, 3, 5),
                                   (64, 8, 8, 1, 40), (128, 16, 8, 3, 9), (64, 32, 32, 3, 3),
                                   # channel counts padded to 64 per tap (zero-filled by the TMA unit)
-                                  (160, 8, 8, 3, 20), (96, 4, 4, 3, 50), (48, 8, 8, 1, 10)])
+                                  (160, 8, 8, 3, 20), (96, 4, 4, 3, 50), (48, 8, 8, 1, 10),
+                                  # degenerate maps: kernel positions that only see padding are dropped (1 resp. 3 live taps)
+                                  (128, 1, 1, 3, 70), (128, 1, 4, 3, 17)])
 @pytest.mark.parametrize("kind,tol", [(K.BF16X3, 3e-5), (K.F16X3, 1e-5), (K.BF16, 6e-3)])
 def test_syrk_conv_patches_vs_unfold(geom, kind, tol):
     """im2col-free A factor (shifted 4-D TMA boxes feeding the MN-major SYRK) == fp64 unfold + P^T P, in the parameter
