@@ -162,20 +162,19 @@ class B200Kron(Kron):
         return total
 
 
-N_EIGH_STREAMS = 4
+N_EIGH_STREAMS = 1
 
 
 def _symeig_concurrent(items, eigvals, eigvecs):
-    """Large factors: one cuSOLVER ``syevd`` each (a single call leaves most of the GPU idle), spread over a few
-    streams, largest first, so that independent factors overlap."""
-    if not items[0][2].is_cuda or len(items) == 1:
+    """Large factors: one cuSOLVER ``syevd`` each, largest first.  Measured on B200 (ResNet-18's 29 large factors):
+    585 ms issued back to back on the current stream vs 640-770 ms spread over 4 streams -- and the side streams' private
+    allocator pools made the time erratic (0.7-4 s depending on what the caching allocator held) -- so the default is
+    the serial order; ``N_EIGH_STREAMS > 1`` re-enables the overlap."""
+    items = sorted(items, key=lambda t: -t[2].shape[0])
+    if not items[0][2].is_cuda or len(items) == 1 or N_EIGH_STREAMS <= 1:
         for i, j, H in items:
             eigvals[i][j], eigvecs[i][j] = symeig_large(H)
         return
-    items = sorted(items, key=lambda t: -t[2].shape[0])
-    # cuSOLVER allocates its workspaces outside PyTorch's caching allocator: hand cached blocks back first (measured:
-    # a decompose right after large-batch steps took 4 s instead of 0.7 s when the cache held most of the HBM)
-    torch.cuda.empty_cache()
     cur = torch.cuda.current_stream()
     streams = [torch.cuda.Stream() for _ in range(min(N_EIGH_STREAMS, len(items)))]
     for s_ in streams:

@@ -1,0 +1,6 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -5 | tee gpurun_out/r29_tests.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep smoke | tee gpurun_out/r29_smoke.log
+timeout 300 python tools/step_breakdown.py --batch 4096 2>&1 | grep -v -i Warn | tail -22 | tee gpurun_out/r29_breakdown.log
+timeout 1200 python bench.py --predictive 2>&1 | tail -1 | tee gpurun_out/r29_bench.log | cut -c1-300
