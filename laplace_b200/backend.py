@@ -80,6 +80,11 @@ class _B200Mixin:
         # KFAC path only: reverse pass of conv -> frozen BN -> ReLU chains as one node per convolution (conv_engine.py)
         self.fuse_elementwise = fuse_elementwise
         self._fused = False
+        # KFAC path: input (A) factors on a side stream, concurrent with the reverse pass
+        import os
+
+        self.overlap_factors = os.environ.get("LPB_NO_OVERLAP") != "1"
+        self._side = None
         self._layers: list[_Layer] | None = None
         self._unsupported: list[str] = []
         self._hooks = []
@@ -162,6 +167,11 @@ class _B200Mixin:
             # the engine's forward uses fp16 hi/lo operands: an activation beyond +-65504 would surface here
             torch._assert_async(torch.isfinite(f).all())
         return f
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     def _conv_patch(self, fuse: bool = False):
         """fp32-accurate convolution passes on the tensor cores (laplace_b200/conv_engine.py) instead of cuDNN's
@@ -356,25 +366,7 @@ class _B200Mixin:
         loss = self.factor * self.lossfunc(fd, y)
         cols = cols_fn(fd, y)
         acts = self._acts
-        try:
-            grads = self._backward(f, cols)
-        except RuntimeError as e:
-            from . import conv_engine as _ce
-
-            if not (self._fused and isinstance(e, _ce.FusionConflict)):
-                raise
-            # a fused intermediate has a second consumer in this model: keep the chains unfused from now on
-            self.fuse_elementwise = False
-            f = self._forward(x, fuse=False)
-            acts = self._acts
-            grads = self._backward(f, cols)
-        if self._fused and not (cols.shape[0] == 1 or getattr(self, "last_backward_mode", "") == "batched"):
-            # the column-batched reverse pass was not available: the fused chains keep gradients only as packed rows
-            # of ONE pass, so redo the passes unfused (one reverse pass per column, gradients as tensors)
-            f = self._forward(x, fuse=False)
-            acts = self._acts
-            grads = self._backward(f, cols)
-        self._acts = {}
+        out_t = {L.name: (math.prod(self._outs[L.name].shape[2:]) if L.is_conv else 1) for L in self._layers}
         dims = []
         for L in self._layers:
             if L.has_w:
@@ -383,16 +375,92 @@ class _B200Mixin:
                 dims.append([L.d_out])
         kron = B200Kron.zeros(dims, fd.device, torch.float32)
         sq = math.sqrt(self.factor)
-        idx = 0
+        slots, idx = {}, 0   # layer name -> index of its first Kron block
+        for L in self._layers:
+            slots[L.name] = idx
+            idx += (1 if L.has_w else 0) + (1 if L.has_b else 0)
+        fwd_stash = {}
+        if self.conv_engine and not reduce and self.precision in ("auto", "bf16x3"):
+            from . import conv_engine
+
+            fwd_stash = conv_engine.STASH   # operands the forward packed (patch rows "P", NHWC input rows "X")
+
+        def input_factors():
+            """A factors: they need the layer inputs only, so they are issued right after the forward -- on a side
+            stream, where the tensor-bound SYRKs overlap the HBM-bound stretches of the reverse pass."""
+            for L in self._layers:
+                if not L.has_w:
+                    continue
+                a = acts[L.name]
+                Af = kron.kfacs[slots[L.name]][1]
+                rows = fwd_stash.get(id(L.mod), {})
+                Prows, Xs = rows.get("P"), rows.get("X")
+                if (Xs is not None and Xs[1] == M and K.conv_patches_ok(Xs[0].K, Xs[2], Xs[3], *L.mod.kernel_size)):
+                    # implicit-path convolution: the A factor straight from the NHWC input rows the forward packed
+                    X, _, Hh, Ww = Xs
+                    K.syrk_conv_patches(X, M, Hh, Ww, L.mod, Af, alpha=sq / (N * Hh * Ww))
+                    continue
+                if Prows is None and L.is_conv and len(fwd_stash) > 0:
+                    # build the patch rows once (the row-major pack is ~2x cheaper than the transposing K-major one)
+                    af = a.float() if a.dtype != torch.float32 else a
+                    Prows = K.pack_conv_rows(af, L.mod, K.BF16X3)
+                if Prows is not None and Prows.rows % M != 0:
+                    Prows = None
+                if Prows is not None:
+                    T = Prows.rows // M
+                    K.gemm_tn(Prows, Prows, Af, alpha=sq / (N * T), accumulate=True, symmetric=True)
+                else:
+                    k_rows = M * out_t[L.name] if L.is_conv else (a.numel() // a.shape[-1])
+                    ak = self._kind(L.d_in, M if reduce else k_rows)
+                    A, T = self._pack_act(L, a, ak, reduce)
+                    Teff = 1 if reduce else T
+                    # A = factor^(1/2) * (M/N) * 1/(M*T) * sum a a^T   (curvlinops.py:46-53, matrix.py:116-118)
+                    K.gemm_nt(A, A, Af, alpha=sq / (N * Teff), accumulate=True, symmetric=True)
+
+        side = main = None
+        if fd.is_cuda and self.overlap_factors:
+            main = torch.cuda.current_stream()
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                input_factors()
+        else:
+            input_factors()
+
+        def join():
+            if side is not None:
+                main.wait_stream(side)
+
+        try:
+            try:
+                grads = self._backward(f, cols)
+            except RuntimeError as e:
+                from . import conv_engine as _ce
+
+                if not (self._fused and isinstance(e, _ce.FusionConflict)):
+                    raise
+                # a fused intermediate has a second consumer in this model: keep the chains unfused from now on
+                self.fuse_elementwise = False
+                join()   # the re-run forward clears the operands the side stream may still be reading
+                f = self._forward(x, fuse=False)
+                grads = self._backward(f, cols)
+            if self._fused and not (cols.shape[0] == 1 or getattr(self, "last_backward_mode", "") == "batched"):
+                # the column-batched reverse pass was not available: the fused chains keep gradients only as packed
+                # rows of ONE pass, so redo the passes unfused (one reverse pass per column, gradients as tensors)
+                join()
+                f = self._forward(x, fuse=False)
+                grads = self._backward(f, cols)
+        finally:
+            join()
+        self._acts = {}
         stash = {}
         if (self.conv_engine and not reduce and self.precision in ("auto", "bf16x3")
                 and (cols.shape[0] == 1 or getattr(self, "last_backward_mode", "") == "batched")):
             from . import conv_engine
 
-            stash = conv_engine.STASH   # row-major operands the engine already packed for this batch
+            stash = conv_engine.STASH   # gradient rows "G" the engine packed during the reverse pass
         for L, g in zip(self._layers, grads):
-            a = acts[L.name]
-            ncols = cols.shape[0]
+            idx = slots[L.name]
             rows = stash.get(id(L.mod), {})
             Grows = rows.get("G")
             if g is None:
@@ -416,43 +484,12 @@ class _B200Mixin:
                     K.gemm_nt(G, G, out, alpha=alpha, accumulate=True, symmetric=True)
 
             if L.has_w:
-                Bf, Af = kron.kfacs[idx]
-                Prows = rows.get("P")
-                Xs = rows.get("X")
-                a_done = False
-                if (Xs is not None and Xs[1] == M
-                        and K.conv_patches_ok(Xs[0].K, Xs[2], Xs[3], *L.mod.kernel_size)):
-                    # implicit-path convolution: the A factor straight from the NHWC input rows the forward packed
-                    X, _, Hh, Ww = Xs
-                    K.syrk_conv_patches(X, M, Hh, Ww, L.mod, Af, alpha=sq / (N * Hh * Ww))
-                    a_done = True
-                elif Prows is None and L.is_conv and stash is not None and len(stash) > 0:
-                    # implicit-path convolution: build the patch rows once (row-major pack is ~2x cheaper than the
-                    # transposing K-major one) and contract them with the MN-major SYRK
-                    af = a.float() if a.dtype != torch.float32 else a
-                    Prows = K.pack_conv_rows(af, L.mod, K.BF16X3)
-                if Prows is not None and Prows.rows % M != 0:
-                    Prows = None
-                if a_done:
-                    pass
-                elif Prows is not None:
-                    T = Prows.rows // M
-                    K.gemm_tn(Prows, Prows, Af, alpha=sq / (N * T), accumulate=True, symmetric=True)
-                else:
-                    k_rows = (g.numel() // (ncols * L.d_out)) if L.is_conv else (a.numel() // a.shape[-1])
-                    ak = self._kind(L.d_in, M if reduce else k_rows)
-                    A, T = self._pack_act(L, a, ak, reduce)
-                    Teff = 1 if reduce else T
-                    # A = factor^(1/2) * (M/N) * 1/(M*T) * sum a a^T   (curvlinops.py:46-53, matrix.py:116-118)
-                    K.gemm_nt(A, A, Af, alpha=sq / (N * Teff), accumulate=True, symmetric=True)
+                Bf = kron.kfacs[idx][0]
                 syrk_B(Bf, sq * weight)
-                idx += 1
                 if L.has_b:
-                    kron.kfacs[idx][0].copy_(Bf).mul_(sq)  # bias block: factor * B   (len(F) == 1)
-                    idx += 1
+                    kron.kfacs[idx + 1][0].copy_(Bf).mul_(sq)  # bias block: factor * B   (len(F) == 1)
             elif L.has_b:
                 syrk_B(kron.kfacs[idx][0], self.factor * weight)
-                idx += 1
         dtype = next(self.model.parameters()).dtype
         if dtype != torch.float32:
             kron = B200Kron([[H.to(dtype) for H in F] for F in kron.kfacs])

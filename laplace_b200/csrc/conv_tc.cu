@@ -159,7 +159,7 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
                                int64_t Mrows, int N, float alpha, float* __restrict__ D, int64_t ldd, int q_per_tile,
                                const __grid_constant__ ConvTaps taps, const __grid_constant__ ConvOutMap om, int kchunks,
                                int num_stages, int fp16_operands, int bn, int tiles_n, int num_items, int tiles_per_img,
-                               int rows_per_tile, int rotate) {
+                               int rows_per_tile) {
   const int B_BYTES = bn * BK * 2;
   const int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (TILE_BYTES + B_BYTES);
   const int OFF_B_HI = TILE_BYTES, OFF_A_LO = TILE_BYTES + B_BYTES, OFF_B_LO = 2 * TILE_BYTES + B_BYTES;
@@ -199,12 +199,7 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
         // small images: a tile is q_per_tile whole images; large images: rows_per_tile image rows of one image
         int q0 = tm * q_per_tile, h0 = 0;
         if (tiles_per_img > 0) { q0 = tm / tiles_per_img; h0 = (tm - q0 * tiles_per_img) * rows_per_tile; }
-        // every CTA needs the same weight tiles; walking the (tap, chunk) list from a CTA-dependent start keeps the
-        // 148 CTAs from pulling the same 16 KB of weights through one L2 slice at the same moment (the sum is order-free)
-        const int rot = rotate ? (int)((blockIdx.x * 5u) % (unsigned)total) : 0;
-        for (int it0 = 0; it0 < total; ++it0) {
-          int it = it0 + rot;
-          if (it >= total) it -= total;
+        for (int it = 0; it < total; ++it) {
           const int ti = it / kchunks, kc = it - ti * kchunks;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
@@ -388,19 +383,14 @@ static int conv_nhwc_core(const void* X_hi, const void* X_lo, int64_t Q, int H, 
     pattr1 = true;
   }
   const unsigned pgrid = (unsigned)imin(items, sm_count());
-  static int rotate = -1;
-  if (rotate < 0) {
-    const char* e = getenv("LPB_CONV_ROTATE");   // 0 disables the per-CTA rotation of the tap order (A/B timing)
-    rotate = e ? (atoi(e) != 0 ? 1 : 0) : 1;
-  }
   if (x3)
     tc::conv_nhwc_tc_persistent_kernel<3><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
         tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, taps, om, kchunks, pstages, fp16_operands, bn, tiles_n,
-        (int)items, tiles_per_img, rows_per_tile, rotate);
+        (int)items, tiles_per_img, rows_per_tile);
   else
     tc::conv_nhwc_tc_persistent_kernel<1><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
         tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, taps, om, kchunks, pstages, fp16_operands, bn, tiles_n,
-        (int)items, tiles_per_img, rows_per_tile, rotate);
+        (int)items, tiles_per_img, rows_per_tile);
   LPB_CHECK_LAUNCH("conv_nhwc_bf16 (persistent)");
   return 0;
 }

@@ -92,14 +92,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const ItemGeom it = decode_item(item, num_tiles, symmetric, tiles_m, tiles_n, total_kchunks, kchunks_per_split);
-        // Implicit patches: the tiles that share a K-range would all pull the SAME few KB of activations (every tap
-        // reads the same image) at the same moment -- an L2 hot spot that halved the layer-1 rate.  The sum over
-        // k-chunks is order-free, so each tile walks its range from a different starting chunk (cyclically).
-        const int nk = it.kc_end - it.kc_begin;
-        const int rot = (LOADER == 2 && pg.rotate) ? (int)(((int64_t)(item % num_tiles) * nk) / num_tiles) : 0;
-        for (int c = 0; c < nk; ++c) {
-          int kc = it.kc_begin + c + rot;
-          if (kc >= it.kc_end) kc -= nk;
+        for (int kc = it.kc_begin; kc < it.kc_end; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], it.diag ? STAGE_BYTES / 2 : STAGE_BYTES);
@@ -400,14 +393,6 @@ int syrk_conv_patches(const void* X_hi, const void* X_lo, int64_t ldx, int64_t Q
   for (int kh = 0; kh < KH; ++kh)
     for (int kw = 0; kw < KW; ++kw)
       if (kh - PH < H && PH - kh < H && kw - PW < W && PW - kw < W) pg.tap_of[pg.num_taps++] = (unsigned char)(kh * KW + kw);
-  {
-    static int rotate = -1;
-    if (rotate < 0) {
-      const char* e = getenv("LPB_SYRK_ROTATE");   // 0 disables the per-tile rotation of the chunk order (A/B timing)
-      rotate = e ? (atoi(e) != 0 ? 1 : 0) : 1;
-    }
-    pg.rotate = rotate;
-  }
   int box_h, box_n;
   if (HW >= 64) {
     LPB_REQUIRE(64 % W == 0 && H % (64 / W) == 0, "syrk_conv_patches: %dx%d images do not tile 64-row chunks", H, W);

@@ -20,7 +20,6 @@ struct PatchGeom {
   int KW, PH, PW, Ci, num_taps, blocks_per_tap, chunks_per_img, rows_per_chunk, imgs_per_chunk;
   unsigned char tap_of[16];   // live tap i -> kernel position kh * KW + kw (taps that only read padding are dropped)
   int n_images;     // loader 3: sample rows (col, n) wrap around the images every n_images samples (0: no wrap)
-  int rotate;       // loader 2: start each tile's K-range at a tile-dependent chunk (de-phases L2 accesses)
   int group_chunks; // > 0: TMEM groups of exactly this many k-chunks (= one sample), SQUARED before they are summed
 };
 
