@@ -7,13 +7,17 @@ run the C-times-batched reverse pass of a ResNet-18 at ~3 TFLOP/s (78 % of a KFA
 engine keeps autograd for the graph and every element-wise / pooling / normalisation op, but computes the two
 convolution products itself:
 
-* forward        ``out[co, (n,t)]   = W[co, :] . patches[(n,t), :]``           (patch-major im2col + GEMM-NT)
-* backward-data  ``Dc[(ci,kh,kw), (q,t)] = W^T[(ci,kh,kw), :] . g[(q,t), :]`` + col2im gather
+* forward        stride-1 "same" convolutions: implicit GEMM on NHWC rows (shifted 4-D TMA boxes, no im2col);
+                 anything else: patch-major im2col + GEMM-NT ``out[(n,t), co] = patches[(n,t), :] . W[co, :]``
+* backward-data  stride 1: the same implicit GEMM with flipped taps; stride > 1: one implicit GEMM per stride parity
+                 class, written in place into the NHWC input gradient; anything else:
+                 ``Dc[(q,t), (kh,kw,ci)] = g[(q,t), :] . W^T[(kh,kw,ci), :]`` + ``col2im_nhwc`` gather
 
-both with bf16 hi/lo operands and three tensor-core products per tile (relative error ~2^-16, fp32
-accumulation), i.e. fp32-accurate at tensor-core speed.  The reverse pass for all curvature columns is ONE
-call per layer: ``torch.func.vmap`` over ``autograd.grad`` reaches ``_ConvBwdData.vmap``, which folds the
-column dimension into the batch.
+both with 16-bit hi/lo operands and three tensor-core products per tile (relative error ~2^-16, fp32
+accumulation), i.e. fp32-accurate at tensor-core speed.  Everything the engine emits or consumes is
+channels-last.  The reverse pass for all curvature columns is ONE call per layer: ``torch.func.vmap`` over
+``autograd.grad`` reaches ``_ConvBwdData.vmap`` (or the fused ``_ConvFusedBwd.vmap``), which folds the column
+dimension into the batch.
 """
 from __future__ import annotations
 
