@@ -98,12 +98,7 @@ class B200Laplace:
         self.mean = parameters_to_vector(self.params).detach()
         N = len(train_loader.dataset)
         self.loss, H = 0.0, None
-        for data in train_loader:
-            if isinstance(data, MutableMapping):
-                X, y = data, data[self.backend.dict_key_y].to(self._device)
-            else:
-                X, y = data
-                X, y = X.to(self._device, non_blocking=True), y.to(self._device, non_blocking=True)
+        for X, y in self._device_batches(train_loader):
             self.model.zero_grad()
             if self.structure == "kron":
                 loss_b, H_b = self.backend.kron(X, y, N=N, **self.fisher_kwargs)
@@ -124,6 +119,49 @@ class B200Laplace:
         else:
             self.H = H
         return self
+
+    def _device_batches(self, loader):
+        """Yield ``(X, y)`` on the model's device.  Host batches are copied on a side stream one batch ahead, so the
+        host-to-device transfer of batch ``i + 1`` (2 ms for 4096 CIFAR-sized images over PCIe) overlaps the curvature
+        kernels of batch ``i``; the reference does one blocking ``.to(device)`` per batch (baselaplace.py:974)."""
+        dev = self._device
+
+        def to_dev(data):
+            if isinstance(data, MutableMapping):
+                return data, data[self.backend.dict_key_y].to(dev, non_blocking=True)
+            X, y = data
+            return X.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+
+        if dev.type != "cuda":
+            for data in loader:
+                yield to_dev(data)
+            return
+        main = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+
+        def fetch(data):
+            with torch.cuda.stream(copy):
+                X, y = to_dev(data)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            return X, y, ev
+
+        it = iter(loader)
+        try:
+            nxt = fetch(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            X, y, ev = nxt
+            main.wait_event(ev)
+            for t in (X, y):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(main)   # allocated on the copy stream, consumed on the compute stream
+            try:
+                nxt = fetch(next(it))
+            except StopIteration:
+                nxt = None
+            yield X, y
 
     def decompose(self):
         self.H = self.H_facs.decompose(damping=self.damping)
