@@ -11,6 +11,7 @@ directly; this class is not needed.
 from __future__ import annotations
 
 import math
+import os
 from collections.abc import MutableMapping
 
 import torch
@@ -83,6 +84,7 @@ class B200Laplace:
         self.loss, self.n_data = 0.0, 0
         self._Sigma = None
         self._ll_cache = None
+        self._copy_stream = None
 
     @property
     def _device(self):
@@ -132,12 +134,16 @@ class B200Laplace:
             X, y = data
             return X.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
 
-        if dev.type != "cuda":
+        if dev.type != "cuda" or os.environ.get("LPB_NO_PREFETCH") == "1":
             for data in loader:
                 yield to_dev(data)
             return
         main = torch.cuda.current_stream(dev)
-        copy = torch.cuda.Stream(dev)
+        if self._copy_stream is None:
+            # one copy stream per instance: its allocator pool stays warm across fit() calls (a fresh stream starts with
+            # an empty pool and pays synchronising cudaMallocs for the first batches)
+            self._copy_stream = torch.cuda.Stream(dev)
+        copy = self._copy_stream
 
         def fetch(data):
             with torch.cuda.stream(copy):
