@@ -225,3 +225,43 @@ def test_diag_tensor_core_conv_path(cpu_kernels):
         assert rel_fro(de, deref) < 1e-5
     finally:
         K.diag_conv_sq = orig
+
+
+def test_engine_path_predicates():
+    """Which kernel family a convolution is routed to (pure host logic; the kernels' own argument checks mirror these)."""
+    from laplace_b200 import conv_engine as ce, kernels as K
+
+    c3 = torch.nn.Conv2d(64, 64, 3, 1, 1)
+    c3s2 = torch.nn.Conv2d(64, 128, 3, 2, 1)
+    c1s2 = torch.nn.Conv2d(64, 128, 1, 2, 0)
+    c7s2 = torch.nn.Conv2d(3, 64, 7, 2, 3)
+    # stride-1 "same": whole images tiling 128 rows, or 128 / W image rows of a larger image
+    assert all(ce.implicit_ok(c3, h, w) for h, w in [(1, 1), (2, 2), (4, 4), (8, 8), (16, 8), (16, 16), (32, 32), (64, 64)])
+    assert not any(ce.implicit_ok(c3, h, w) for h, w in [(3, 3), (6, 6), (12, 12), (6, 48), (7, 7)])
+    assert not ce.implicit_ok(c3s2, 8, 8) and not ce.implicit_ok(torch.nn.Conv2d(8, 8, 3, 1, 0), 8, 8)
+    # strided reverse passes: input extent = stride x output extent, output grid tiles 128 rows
+    assert ce.strided_ok(c3s2, 8, 8) and ce.strided_ok(c1s2, 8, 8) and ce.strided_ok(c7s2, 32, 32) and ce.strided_ok(c3s2, 2, 2)
+    assert not ce.strided_ok(c3s2, 5, 5) and not ce.strided_ok(c3, 8, 8) and not ce.strided_ok(c3s2, 12, 12)
+    # im2col-free input factors: <= 9 taps, images tiling 64-row chunks, channel padding to 64 wastes <= 1/3
+    assert K.conv_patches_ok(64, 8, 8, 3, 3) and K.conv_patches_ok(160, 32, 32, 3, 3) and K.conv_patches_ok(512, 1, 1, 3, 3)
+    assert K.conv_patches_ok(48, 8, 8, 1, 1) and not K.conv_patches_ok(80, 8, 8, 3, 3) and not K.conv_patches_ok(3, 32, 32, 3, 3)
+    assert not K.conv_patches_ok(64, 8, 8, 5, 5) and not K.conv_patches_ok(64, 6, 6, 3, 3)
+    # tensor-core diagonal: whole 64-pixel chunks per image
+    assert K.diag_conv_ok(160, 32, 32, 3, 3) and K.diag_conv_ok(64, 8, 8, 3, 3) and K.diag_conv_ok(16, 16, 8, 1, 1)
+    assert not K.diag_conv_ok(128, 4, 4, 3, 3) and not K.diag_conv_ok(8, 8, 8, 3, 3) and not K.diag_conv_ok(64, 12, 12, 3, 3)
+
+
+def test_fit_batches_on_cpu_match_plain_iteration(golden, cpu_kernels):
+    """``B200Laplace._device_batches`` (copy-stream prefetch on CUDA) degrades to plain iteration elsewhere and handles
+    empty loaders and HF-style mapping batches."""
+    from laplace_b200.posterior import B200Laplace
+
+    model, X, y, _ = load(golden, "mlp", "classification", dtype=torch.float32)
+    la = B200Laplace(model, "classification", "all", "kron")
+    batches = [(X[:4], y[:4]), (X[4:], y[4:])]
+    got = list(la._device_batches(batches))
+    assert len(got) == 2 and all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(got, batches))
+    assert list(la._device_batches([])) == []
+    m = {"input_ids": X[:3], "labels": y[:3]}
+    (Xm, ym), = list(la._device_batches([m]))
+    assert Xm is m and torch.equal(ym, y[:3])
