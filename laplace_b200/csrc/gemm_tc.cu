@@ -270,6 +270,10 @@ static int gemm_tc(bool mn, const void* A_hi, const void* A_lo, int64_t lda, con
                    int64_t M, int64_t N, int64_t K, float alpha, int accumulate, float* D, int64_t ldd, int symmetric,
                    int fp16_operands, cudaStream_t st) {
   LPB_REQUIRE(!symmetric || M == N, "gemm_nt_bf16: symmetric needs M == N");
+  // TMA coordinates are 32-bit: the contraction index (sample rows) and the feature extents must fit
+  LPB_REQUIRE(K < (1LL << 31) - 64 && M < (1LL << 31) - 256 && N < (1LL << 31) - 256,
+              "gemm_nt_bf16: extent beyond 32-bit tensor-map coordinates (M=%lld N=%lld K=%lld)", (long long)M, (long long)N,
+              (long long)K);
   LPB_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "gemm_nt_bf16: leading dimensions must be multiples of 8 elements");
   LPB_REQUIRE(((uintptr_t)A_hi % 16) == 0 && ((uintptr_t)B_hi % 16) == 0 && ((uintptr_t)A_lo % 16) == 0 &&
                   ((uintptr_t)B_lo % 16) == 0,
