@@ -126,3 +126,35 @@ def test_subnetwork_laplace(golden, cpu_kernels, laplace_mod):
     lr = laplace_mod.Laplace(model, "classification", "subnetwork", "full", subnetwork_indices=idx, backend=GGNInterface)
     lr.fit(loader)
     assert rel_fro(la.H, lr.H) < 1e-5
+
+
+def test_kron_laplace_with_fused_conv_chains(cpu_kernels, laplace_mod, monkeypatch):
+    """The large-batch code paths (fused conv -> frozen BN -> ReLU reverse chains, strided / implicit convolutions,
+    im2col-free input factors, side-stream bookkeeping) behind the UNMODIFIED reference front end: ``Laplace(...).fit``
+    accumulates the same Kronecker factors as the oracle and the GLM predictive runs."""
+    from laplace_b200 import B200GGN, B200Kron, conv_engine
+    from oracle import curvature_oracle as co
+
+    monkeypatch.setattr(conv_engine, "ELEMENTWISE_MIN_BATCH", 0)
+    torch.manual_seed(3)
+    bn = torch.nn.BatchNorm2d(64)
+    model = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 3, 1, 1, bias=False), bn, torch.nn.ReLU(),
+                                torch.nn.Conv2d(64, 64, 3, 2, 1, bias=False), torch.nn.ReLU(), torch.nn.Conv2d(64, 8, 3, 1, 1),
+                                torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(8, 3)).eval()
+    bn.running_mean.normal_(0, 0.1), bn.running_var.uniform_(0.5, 1.5)
+    for p in bn.parameters():
+        p.requires_grad_(False)
+    X, y = torch.randn(12, 3, 8, 8), torch.randint(3, (12,))
+    la = laplace_mod.Laplace(model, "classification", "all", "kron", backend=B200GGN, prior_precision=1.3)
+    la.fit(DataLoader(TensorDataset(X, y), batch_size=6))
+    assert isinstance(la.H_facs, B200Kron) and la.backend._fused and la.backend.fuse_elementwise
+    kfs = None
+    md = model.double()
+    for i in (0, 6):
+        _, kf = co.kfac_factors(md, "classification", X[i:i + 6].double(), y[i:i + 6], N=12)
+        kfs = kf if kfs is None else [[a + b for a, b in zip(Fa, Fb)] for Fa, Fb in zip(kfs, kf)]
+    model.float()
+    worst = max(rel_fro(H, Ho) for F, Fo in zip(la.H_facs.kfacs, kfs) for H, Ho in zip(F, Fo))
+    assert worst < 1e-4, worst
+    probs = la(X[:5], pred_type="glm", link_approx="probit")
+    assert probs.shape == (5, 3) and torch.allclose(probs.sum(-1), torch.ones(5), atol=1e-5)
