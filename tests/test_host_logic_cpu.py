@@ -148,6 +148,12 @@ def test_convolution_engine_paths_on_model_zoo(cpu_kernels, monkeypatch, name, k
     _, kf = co.kfac_factors(model, "classification", X, y, N=4)
     worst = max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo))
     assert worst < 1e-5, worst
+    # empirical Fisher: a single curvature column through the same (fused) chains
+    ef = B200EF(model, "classification")
+    _, kron_ef = ef.kron(X, y, N=4)
+    _, kf_ef = co.kfac_factors(model, "classification", X, y, N=4, fisher="empirical")
+    worst_ef = max(rel_fro(H, Ho) for F, Fo in zip(kron_ef.kfacs, kf_ef) for H, Ho in zip(F, Fo))
+    assert worst_ef < 1e-5, worst_ef
     # diag / jacobian-based paths run through the same engine
     _, d = be.diag(X, y)
     Js, f = co.jacobians(model, X)
