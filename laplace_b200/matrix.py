@@ -169,11 +169,26 @@ def _symeig_concurrent(items, eigvals, eigvecs):
     """Large factors: one cuSOLVER ``syevd`` each, largest first.  Measured on B200 (ResNet-18's 29 large factors):
     585 ms issued back to back on the current stream vs 640-770 ms spread over 4 streams -- and the side streams' private
     allocator pools made the time erratic (0.7-4 s depending on what the caching allocator held) -- so the default is
-    the serial order; ``N_EIGH_STREAMS > 1`` re-enables the overlap."""
+    the serial order; ``N_EIGH_STREAMS > 1`` re-enables the overlap.
+
+    Factors with structurally dead coordinates are compacted first (``_symeig_compact``): the input factor of a 3x3
+    convolution on a 1x1 feature map has 8 of its 9 kernel positions looking at padding only, i.e. a 4608 x 4608 matrix
+    whose non-zero part is 512 x 512 -- the dense ``eigh`` spends 77 ms on it, the compact one 7 ms."""
     items = sorted(items, key=lambda t: -t[2].shape[0])
-    if not items[0][2].is_cuda or len(items) == 1 or N_EIGH_STREAMS <= 1:
-        for i, j, H in items:
-            eigvals[i][j], eigvecs[i][j] = symeig_large(H)
+    live = None
+    if COMPACT_DEAD_COORDINATES:
+        # one host read for all factors: how many coordinates carry any mass (PSD: zero diagonal <=> zero row/column)
+        live = torch.stack([(H.diagonal() != 0).sum() for _, _, H in items]).tolist()
+    serial = not items[0][2].is_cuda or len(items) == 1 or N_EIGH_STREAMS <= 1
+
+    def one(k, H):
+        if live is not None and live[k] <= COMPACT_MAX_LIVE_FRACTION * H.shape[0]:
+            return _symeig_compact(H)
+        return symeig_large(H)
+
+    if serial:
+        for k, (i, j, H) in enumerate(items):
+            eigvals[i][j], eigvecs[i][j] = one(k, H)
         return
     cur = torch.cuda.current_stream()
     streams = [torch.cuda.Stream() for _ in range(min(N_EIGH_STREAMS, len(items)))]
@@ -181,10 +196,56 @@ def _symeig_concurrent(items, eigvals, eigvecs):
         s_.wait_stream(cur)
     for k, (i, j, H) in enumerate(items):
         with torch.cuda.stream(streams[k % len(streams)]):
-            eigvals[i][j], eigvecs[i][j] = symeig_large(H)
+            eigvals[i][j], eigvecs[i][j] = one(k, H)
             H.record_stream(streams[k % len(streams)])
     for s_ in streams:
         cur.wait_stream(s_)
+
+
+COMPACT_DEAD_COORDINATES = True
+COMPACT_MAX_LIVE_FRACTION = 0.75
+
+
+def _symeig_compact(H: torch.Tensor):
+    """Eigendecomposition of a PSD matrix whose rows / columns outside ``idx = {i : H_ii != 0}`` vanish identically:
+    ``eigh`` of the live block, embedded.  Dead coordinates get eigenvalue 0 and unit eigenvectors (any orthonormal
+    basis of the null space is an equally valid output of the reference's dense ``eigh``); eigenvalues stay ascending
+    (the dead zeros first, then the clamped, non-negative live spectrum)."""
+    n = H.shape[0]
+    alive = H.diagonal() != 0
+    idx = torch.nonzero(alive).squeeze(1)
+    dead = torch.nonzero(~alive).squeeze(1)
+    k = idx.numel()
+    if k == 0:
+        return torch.zeros(n, dtype=H.dtype, device=H.device), torch.eye(n, dtype=H.dtype, device=H.device)
+    Hs = H.index_select(0, idx).index_select(1, idx)
+    Ls, Ws = symeig_large(Hs)
+    L = torch.cat([torch.zeros(n - k, dtype=Ls.dtype, device=H.device), Ls])
+    W = torch.zeros(n, n, dtype=Ws.dtype, device=H.device)
+    W[dead, torch.arange(n - k, device=H.device)] = 1
+    W[idx.unsqueeze(1), (n - k) + torch.arange(k, device=H.device).unsqueeze(0)] = Ws
+    return L, W
+
+
+# torch.linalg.eigh routes fp32 CUDA matrices of 32..512 rows to cuSOLVER's Jacobi solver (syevj) and everything larger to
+# the divide-and-conquer one (syevd); on B200 syevd is ~2.5x faster just above the threshold (576: 6.7 ms) than syevj
+# just below it (512: 17 ms).  Matrices in PAD_EIGH_RANGE are therefore bordered with a negative diagonal block up to 513
+# rows: the border decouples exactly, sorts first, and is dropped.
+PAD_EIGH_RANGE = (385, 512)
+PAD_EIGH_TO = 513
+_PAD_ON_CPU = False   # tests flip this to exercise the bordering logic without a GPU
+
+
+def _eigh_padded(H: torch.Tensor):
+    n = H.shape[0]
+    p = PAD_EIGH_TO - n
+    Hp = torch.zeros(PAD_EIGH_TO, PAD_EIGH_TO, dtype=H.dtype, device=H.device)
+    Hp[:n, :n] = H
+    # strictly below the spectrum of a PSD H by far more than any rounding error of its eigenvalues
+    border = -(H.diagonal().abs().max() + 1.0)
+    Hp[n:, n:] = torch.diag_embed(border.expand(p))
+    L, W = torch.linalg.eigh(Hp, UPLO="U")
+    return L[p:], W[:n, p:]
 
 
 def symeig_large(H: torch.Tensor):
@@ -192,7 +253,10 @@ def symeig_large(H: torch.Tensor):
     declared as such in DESIGN.md) with the reference's post-processing (utils/utils.py:207-228): jitter retry,
     clamp at 0, NaN -> 0; raises ``LinAlgError`` instead of the reference's ``exit()`` (SURVEY App. B #8)."""
     try:
-        L, W = torch.linalg.eigh(H, UPLO="U")
+        if (H.is_cuda or _PAD_ON_CPU) and H.dtype == torch.float32 and PAD_EIGH_RANGE[0] <= H.shape[0] <= PAD_EIGH_RANGE[1]:
+            L, W = _eigh_padded(H)
+        else:
+            L, W = torch.linalg.eigh(H, UPLO="U")
     except RuntimeError:
         eye = torch.eye(H.shape[0], device=H.device, dtype=H.dtype)
         try:

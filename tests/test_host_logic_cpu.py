@@ -271,3 +271,43 @@ def test_fit_batches_on_cpu_match_plain_iteration(golden, cpu_kernels):
     m = {"input_ids": X[:3], "labels": y[:3]}
     (Xm, ym), = list(la._device_batches([m]))
     assert Xm is m and torch.equal(ym, y[:3])
+
+
+def test_compact_and_bordered_eigendecompositions(cpu_kernels, monkeypatch):
+    """``decompose()`` shortcuts for large factors: (a) coordinates with a zero diagonal (kernel positions that only see
+    padding) are split off and only the live block goes through ``eigh``; (b) fp32 matrices of 385..512 rows are
+    bordered to 513 rows to reach cuSOLVER's faster solver.  Both must return a valid ascending eigendecomposition."""
+    from laplace_b200 import matrix as mx
+
+    torch.manual_seed(0)
+    n, k = 90, 30
+    idx = torch.randperm(n)[:k].sort().values
+    X = torch.randn(200, k, dtype=torch.float64)
+    H = torch.zeros(n, n, dtype=torch.float64)
+    H[idx.unsqueeze(1), idx.unsqueeze(0)] = X.t() @ X
+    L, W = mx._symeig_compact(H)
+    assert torch.all(L[1:] >= L[:-1]) and torch.all(L[: n - k] == 0)
+    assert torch.allclose(W.t() @ W, torch.eye(n, dtype=torch.float64), atol=1e-10)
+    assert torch.allclose(W @ torch.diag(L) @ W.t(), H, atol=1e-8 * float(H.abs().max()))
+    assert torch.allclose(L, torch.linalg.eigvalsh(H).clamp(min=0), atol=1e-8 * float(H.abs().max()))
+    # through B200Kron.decompose: same posterior functionals with and without the shortcut
+    A = torch.randn(50, 12, dtype=torch.float64)
+    kron = B200Kron([[A.t() @ A, H.clone()]])
+    Wt = torch.randn(3, 2, 12 * n, dtype=torch.float64)
+    outs = []
+    for flag in (True, False):
+        monkeypatch.setattr(mx, "COMPACT_DEAD_COORDINATES", flag)
+        P = kron.decompose() * 1.0 + torch.tensor(0.3, dtype=torch.float64)
+        outs.append((P.inv_square_form(Wt.clone()), P.logdet()))
+    # (the rotation GEMMs run in fp32 in both cases)
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5) and torch.allclose(outs[0][1], outs[1][1], rtol=1e-6)
+    # (b) bordered eigh (exercised on CPU through the test switch)
+    monkeypatch.setattr(mx, "_PAD_ON_CPU", True)
+    Y = torch.randn(700, 400)
+    G = (Y.t() @ Y) * 37.0
+    Lp, Wp = mx.symeig_large(G)
+    Lr = torch.linalg.eigvalsh(G.double())
+    assert Lp.shape == (400,) and Wp.shape == (400, 400) and torch.all(Lp[1:] >= Lp[:-1])
+    assert torch.allclose(Lp.double(), Lr, rtol=1e-4, atol=1e-4 * float(Lr.max()))
+    assert torch.allclose(Wp.t() @ Wp, torch.eye(400), atol=1e-4)
+    assert rel_fro(Wp @ torch.diag(Lp) @ Wp.t(), G) < 1e-5
