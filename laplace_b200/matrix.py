@@ -233,6 +233,7 @@ def _symeig_compact(H: torch.Tensor):
 # rows: the border decouples exactly, sorts first, and is dropped.
 PAD_EIGH_RANGE = (385, 512)
 PAD_EIGH_TO = 513
+PAD_EIGH = False      # opt-in until it has been timed and its effect on the 1e-5 predictive gate checked on the GPU
 _PAD_ON_CPU = False   # tests flip this to exercise the bordering logic without a GPU
 
 
@@ -253,7 +254,8 @@ def symeig_large(H: torch.Tensor):
     declared as such in DESIGN.md) with the reference's post-processing (utils/utils.py:207-228): jitter retry,
     clamp at 0, NaN -> 0; raises ``LinAlgError`` instead of the reference's ``exit()`` (SURVEY App. B #8)."""
     try:
-        if (H.is_cuda or _PAD_ON_CPU) and H.dtype == torch.float32 and PAD_EIGH_RANGE[0] <= H.shape[0] <= PAD_EIGH_RANGE[1]:
+        if ((PAD_EIGH and H.is_cuda) or _PAD_ON_CPU) and H.dtype == torch.float32 \
+                and PAD_EIGH_RANGE[0] <= H.shape[0] <= PAD_EIGH_RANGE[1]:
             L, W = _eigh_padded(H)
         else:
             L, W = torch.linalg.eigh(H, UPLO="U")
