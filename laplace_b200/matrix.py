@@ -183,7 +183,12 @@ def _symeig_concurrent(items, eigvals, eigvecs):
 
     def one(k, H):
         if live is not None and live[k] <= COMPACT_MAX_LIVE_FRACTION * H.shape[0]:
-            return _symeig_compact(H)
+            try:
+                return _symeig_compact(H)
+            except RuntimeError as e:   # same result through the dense route; say so instead of hiding it
+                import warnings
+
+                warnings.warn(f"laplace_b200: compact eigendecomposition failed ({e}); using the dense one")
         return symeig_large(H)
 
     if serial:
