@@ -115,6 +115,38 @@ def test_kfac_invariants_at_scale():
     assert rel_fro(k7.diag(), 7 * k1.diag()) < 1e-4
 
 
+def test_large_batch_paths_agree_with_unfused_explicit_paths():
+    """Bench-shaped batch (full-width ResNet-18, B = 1024: fused conv->BN->ReLU reverse chains, persistent implicit /
+    strided convolutions, im2col-free input factors on a side stream) against the same backend with every one of those
+    switched off (separate element-wise kernels, patch-row SYRKs): identical factors up to operand rounding, batch
+    additivity across the two code paths, symmetric PSD blocks.  (B = 4096: tools/gpu_probe_scale.py, 3.4e-6.)"""
+    from laplace_b200 import kernels as K
+
+    model = models.make("resnet18").to(DEV)
+    torch.manual_seed(3)
+    X, y = torch.randn(1024, 3, 32, 32, device=DEV), torch.randint(10, (1024,), device=DEV)
+    be = B200GGN(model, "classification", precision="bf16x3")
+    _, k1 = be.kron(X, y, N=50000)
+    assert be._fused and be.last_backward_mode == "batched"
+    ok = K.conv_patches_ok
+    K.conv_patches_ok = lambda *a: False
+    try:
+        be2 = B200GGN(model, "classification", precision="bf16x3", fuse_elementwise=False)
+        be2.overlap_factors = False
+        _, ka = be2.kron(X[:512], y[:512], N=50000)
+        _, kb = be2.kron(X[512:], y[512:], N=50000)
+    finally:
+        K.conv_patches_ok = ok
+    k2 = ka + kb
+    worst = 0.0
+    for F1, F2 in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(F1, F2):
+            assert torch.isfinite(a).all()
+            worst = max(worst, rel_fro(a, b))
+            assert rel_fro(a, a.t()) < 1e-5 and float(a.diagonal().min()) >= 0
+    assert worst < 3e-5, worst
+
+
 @pytest.mark.parametrize("kind", ["mlp", "conv"])
 @pytest.mark.parametrize("lik", ["classification", "regression"])
 def test_kron_posterior_predictive(golden, kind, lik):
