@@ -4,7 +4,7 @@ Public surface (mirrors ``laplace.curvature``): ``B200GGN``, ``B200EF`` plus the
 they return.  See DESIGN.md / INTEGRATION.md.
 """
 from .backend import B200EF, B200GGN
-from .matrix import B200Kron, B200KronDecomposed
+from .matrix import B200Kron, B200KronDecomposed, adopt
 
-__all__ = ["B200GGN", "B200EF", "B200Kron", "B200KronDecomposed"]
+__all__ = ["B200GGN", "B200EF", "B200Kron", "B200KronDecomposed", "adopt"]
 __version__ = "0.1.0"

@@ -91,6 +91,7 @@ class _B200Mixin:
         self._capturing = False
         self._acts: dict[str, torch.Tensor] = {}
         self._outs: dict[str, torch.Tensor] = {}
+        self._out_state: dict[str, tuple] = {}
 
     # ------------------------------------------------------------------ layer plan
     def _plan(self) -> list[_Layer]:
@@ -136,9 +137,49 @@ class _B200Mixin:
     def _make_hook(self, name):
         def hook(mod, inp, out):
             if self._capturing:
+                if name in self._outs:
+                    # the reference's hook-based KFAC sums the contributions of every call; this backend captures one
+                    # (input, output) pair per module, so say so instead of silently keeping the last call only
+                    raise ValueError(f"B200 backend: module {name!r} is called more than once per forward pass (weight "
+                                     "sharing across calls); give every call its own module")
                 self._acts[name] = inp[0].detach()
                 self._outs[name] = out
+                self._out_state[name] = (out._version, out.grad_fn)
         return hook
+
+    # in-place ops that leave d(result)/d(tensor) = identity: the gradient w.r.t. the modified tensor IS the gradient
+    # w.r.t. the layer output (e.g. torchvision's ``out += identity``)
+    _INPLACE_IDENTITY = ("AddBackward", "SubBackward")
+
+    def _check_outputs_intact(self):
+        """``autograd.grad(f, out)`` differentiates w.r.t. the CURRENT version of ``out``: if an in-place activation ran
+        on the captured layer output (``F.relu_``, ``x.clamp_()`` ...) the result would silently lack that activation's
+        mask.  Module-level ``inplace=True`` flags are switched off while capturing (``_no_inplace``); anything that
+        still modified a captured output in place is reported."""
+        for name, out in self._outs.items():
+            ver, fn = self._out_state.get(name, (out._version, out.grad_fn))
+            if out._version == ver:
+                continue
+            new = type(out.grad_fn).__name__ if out.grad_fn is not None else "None"
+            if out.grad_fn is not fn and new.startswith(self._INPLACE_IDENTITY):
+                continue
+            raise RuntimeError(f"B200 backend: the output of layer {name!r} was modified in place after the layer ran "
+                               f"(autograd node {new}); its gradient would miss that operation. Use the out-of-place form.")
+
+    class _no_inplace:
+        """Switch off ``inplace=True`` on activation / dropout modules for the duration of a captured forward pass."""
+
+        def __init__(self, model):
+            self.mods = [m for m in model.modules() if getattr(m, "inplace", False) is True]
+
+        def __enter__(self):
+            for m in self.mods:
+                m.inplace = False
+
+        def __exit__(self, *exc):
+            for m in self.mods:
+                m.inplace = True
+            return False
 
     # ------------------------------------------------------------------ forward / backward
     def _device_check(self, t: torch.Tensor):
@@ -148,7 +189,7 @@ class _B200Mixin:
 
     def _forward(self, x, fuse: bool = False):
         self._plan()
-        self._acts, self._outs = {}, {}
+        self._acts, self._outs, self._out_state = {}, {}, {}
         self._fused = bool(fuse and self.conv_engine)
         if self.conv_engine:
             from . import conv_engine
@@ -156,10 +197,11 @@ class _B200Mixin:
             conv_engine.STASH.clear()
         self._capturing = True
         try:
-            with torch.enable_grad(), self._model_numerics(), self._conv_patch(self._fused):
+            with torch.enable_grad(), self._model_numerics(), self._no_inplace(self.model), self._conv_patch(self._fused):
                 f = self.model(x)
         finally:
             self._capturing = False
+        self._check_outputs_intact()
         if f.ndim != 2:
             raise ValueError(f"the B200 backend supports (batch, outputs) model outputs, got shape {tuple(f.shape)}")
         self._device_check(f)

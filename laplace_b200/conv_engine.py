@@ -28,6 +28,7 @@ from . import kernels as K
 
 import math
 import os
+import weakref
 
 KIND = K.BF16X3       # reverse pass: gradients span many orders of magnitude -> bf16 hi/lo (8-bit exponent)
 KIND_FWD = K.F16X3    # forward pass: activations / weights sit inside fp16 range -> fp16 hi/lo (22 bits); the
@@ -38,17 +39,20 @@ USE_STRIDED = os.environ.get("LPB_NO_STRIDED") != "1"     # strided reverse pass
 
 
 class _WeightCache:
-    """Packed weights are reused across batches (weights are constant during ``fit``)."""
+    """Packed weights are reused across batches (weights are constant during ``fit``).  Entries live in a
+    ``WeakKeyDictionary`` keyed by the module (they die with it: no leak across models, no stale hit when a new model
+    re-uses a freed module's ``id``) and are valid only for the very tensor object, storage and version they were
+    packed from."""
 
     def __init__(self):
-        self.store = {}
+        self.store = weakref.WeakKeyDictionary()
 
-    def get(self, mod: nn.Conv2d, which: str):
+    def get(self, mod: nn.Module, which: str):
         w = mod.weight
-        key = (id(mod), which)
-        tag = (w.data_ptr(), w._version, tuple(w.shape))
-        hit = self.store.get(key)
-        if hit is not None and hit[0] == tag:
+        per_mod = self.store.setdefault(mod, {})
+        tag = (w.data_ptr(), w._version, tuple(w.shape), w.device)
+        hit = per_mod.get(which)
+        if hit is not None and hit[0] == tag and hit[2]() is w:
             return hit[1]
         w2 = w.detach().reshape(w.shape[0], -1)
         w2 = w2 if w2.dtype == torch.float32 else w2.float()
@@ -68,7 +72,7 @@ class _WeightCache:
             w4 = w4.permute(*perm).reshape(-1, w4.shape[1] if which == "fwd_taps" else w4.shape[0]).contiguous()
             packed = K.pack_cast(w4, KIND_FWD if which == "fwd_taps" else KIND)
         packed.inv_scale = 1.0 / scale
-        self.store[key] = (tag, packed)
+        per_mod[which] = (tag, packed, weakref.ref(w))
         return packed
 
 
@@ -553,17 +557,18 @@ ELEMENTWISE_MIN_NUMEL = 1 << 23   # ... or a single activation of >= 8 M element
 def _device_bound(x: torch.Tensor) -> bool:
     return x.shape[0] >= ELEMENTWISE_MIN_BATCH or x.numel() >= ELEMENTWISE_MIN_NUMEL
 
-_BN_CACHE: dict = {}
+_BN_CACHE = weakref.WeakKeyDictionary()   # module -> (tag, (scale, shift)); dies with the module
 
 
 def _bn_affine(m: nn.BatchNorm2d):
-    tag = (m.running_var.data_ptr(), m.running_var._version, m.running_mean._version,
-           None if m.weight is None else m.weight._version, None if m.bias is None else m.bias._version, m.running_var.device)
-    hit = _BN_CACHE.get(id(m))
+    tag = (m.running_var.data_ptr(), m.running_var._version, m.running_mean.data_ptr(), m.running_mean._version,
+           None if m.weight is None else (m.weight.data_ptr(), m.weight._version),
+           None if m.bias is None else (m.bias.data_ptr(), m.bias._version), m.running_var.device, m.eps)
+    hit = _BN_CACHE.get(m)
     if hit is not None and hit[0] == tag:
         return hit[1]
     out = _bn_affine_compute(m)
-    _BN_CACHE[id(m)] = (tag, out)
+    _BN_CACHE[m] = (tag, out)
     return out
 
 

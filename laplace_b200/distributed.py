@@ -4,6 +4,11 @@ curvature at the end.  Every curvature structure of the path is a 
 
 ``N`` passed to the backend must stay the GLOBAL dataset size (the ``M/N`` rescale of the KFAC ``A`` factors,
 curvature/curvlinops.py:46-53, baselaplace.py:964) -- ``ShardedLoader`` keeps ``len(loader.dataset)`` global.
+
+Exchange (SURVEY 8(e) "v2"): all-reduce of the flat factor buffer, then every rank eigendecomposes only the factors it
+owns (greedy balance on ``n^3``) and the eigenvectors / eigenvalues are replicated with ONE all-gather of equally sized
+per-rank slabs -- each byte of ``Q`` crosses NVLink once (the round-1 version all-reduced a zero-padded buffer: world
+times the traffic, and the reduction arithmetic on top).
 """
 from __future__ import annotations
 
@@ -16,27 +21,62 @@ from .matrix import B200Kron
 class ShardedLoader:
     """Rank ``r`` of ``world`` sees batches ``r, r + world, ...`` of an underlying loader; ``.dataset`` is
     the full dataset so that ``len(loader.dataset)`` is the global ``N``.  No sample is repeated or dropped
-    (unlike ``DistributedSampler`` padding), so the sharded sum equals the single-process sum."""
+    (unlike ``DistributedSampler`` padding), so the sharded sum equals the single-process sum.
+
+    Correct only if every rank iterates the SAME batch sequence (``shuffle=False``, or a generator seeded identically on
+    all ranks): ``fingerprint`` (batch count + a checksum of the first batch, filled in by iterating) is compared
+    across ranks by ``fit_distributed`` and a mismatch raises instead of silently duplicating / dropping samples."""
 
     def __init__(self, loader, rank: int, world: int):
         self.loader, self.rank, self.world = loader, rank, world
         self.dataset = loader.dataset
+        self.fingerprint = None
+
+    @staticmethod
+    def _checksum(batch) -> float:
+        x = batch[0] if isinstance(batch, (tuple, list)) else next(iter(batch.values()))
+        if not torch.is_tensor(x) or x.numel() == 0:
+            return 0.0
+        return float(x.reshape(-1)[:4096].double().sum())
 
     def __iter__(self):
+        n, first = 0, 0.0
         for i, batch in enumerate(self.loader):
+            if i == 0:
+                first = self._checksum(batch)
+            n += 1
             if i % self.world == self.rank:
                 yield batch
+        self.fingerprint = (float(n), first)
 
     def __len__(self):
         n = len(self.loader)
         return (n - self.rank + self.world - 1) // self.world
 
 
+def _active(group=None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def check_same_order(loader: ShardedLoader, device, group=None) -> None:
+    """Raise if the ranks did not iterate the same batch sequence (see ``ShardedLoader``)."""
+    if not _active(group) or loader.fingerprint is None:
+        return
+    world = dist.get_world_size(group)
+    mine = torch.tensor(loader.fingerprint, device=device, dtype=torch.float64)
+    allf = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allf, mine, group=group)
+    for r, other in enumerate(allf):
+        if not torch.equal(other, allf[0]):
+            raise RuntimeError("ShardedLoader: rank %d iterated a different batch sequence than rank 0 (shuffle without a "
+                               "shared seed?); the sharded fit would duplicate or drop samples" % r)
+
+
 def allreduce_curvature(H, loss=None, group=None):
     """Sum the accumulated curvature over ranks in place: a ``B200Kron`` is reduced through its single flat
     fp32 buffer (one NCCL launch), dense/diagonal curvature as the tensor itself.  ``loss`` (0-dim tensor) is
     reduced alongside.  Works with the ``gloo`` backend on CPU for tests."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    if not _active(group):
         return H, loss
     if isinstance(H, B200Kron) and H._flat is not None:
         dist.all_reduce(H._flat, op=dist.ReduceOp.SUM, group=group)
@@ -51,61 +91,72 @@ def allreduce_curvature(H, loss=None, group=None):
     return H, loss
 
 
+def factor_owners(sizes, world: int):
+    """Greedy balance of the eigendecomposition cost (``n^3``) over ``world`` ranks, largest first.  Deterministic: every
+    rank computes the same table."""
+    order = sorted(range(len(sizes)), key=lambda k: (-sizes[k], k))
+    load, owner = [0.0] * world, [0] * len(sizes)
+    for k in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[k] = r
+        load[r] += float(sizes[k]) ** 3
+    return owner
+
+
 def decompose_sharded(kron, damping: bool = False, group=None):
-    """``Kron.decompose`` with the factors partitioned over the ranks (greedy balance on ``n^3``): every rank
-    eigendecomposes only its share, one all-reduce of a zero-padded flat ``Q`` buffer (+ eigenvalues) replicates the
-    result (SURVEY 8(e) "exchange v2").  Falls back to the local decomposition for a single process."""
+    """``Kron.decompose`` with the factors partitioned over the ranks: every rank eigendecomposes only its share through
+    the same code path as the single-process ``decompose`` and ONE all-gather of per-rank slabs (``Q`` and ``lambda`` of
+    the owned factors back to back, padded to the largest slab) replicates the result.  Falls back to the local
+    decomposition for a single process."""
     from .matrix import B200KronDecomposed
 
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    if not _active(group):
         return kron.decompose(damping=damping)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     mats = [(i, j, H) for i, F in enumerate(kron.kfacs) for j, H in enumerate(F)]
-    order = sorted(range(len(mats)), key=lambda k: -mats[k][2].shape[0])
-    load, owner = [0.0] * world, [0] * len(mats)
-    for k in order:
-        r = min(range(world), key=lambda q: load[q])
-        owner[k] = r
-        load[r] += float(mats[k][2].shape[0]) ** 3
-    # local decomposition of the owned factors, through the same code path as the single-process one
-    mine = [k for k in range(len(mats)) if owner[k] == rank]
-    sub = B200Kron([[mats[k][2]] for k in mine]) if mine else None
-    local = sub.decompose(damping=damping) if sub is not None else None
+    sizes = [int(m[2].shape[0]) for m in mats]
+    owner = factor_owners(sizes, world)
+    owned = [[k for k in range(len(mats)) if owner[k] == r] for r in range(world)]
+    slab = max(sum(sizes[k] * (sizes[k] + 1) for k in ks) for ks in owned)     # n*n eigenvectors + n eigenvalues each
     dev, dt = mats[0][2].device, mats[0][2].dtype
-    sizes = [m[2].shape[0] for m in mats]
-    Qflat = torch.zeros(sum(n * n for n in sizes), device=dev, dtype=dt)
-    Lflat = torch.zeros(sum(sizes), device=dev, dtype=dt)
-    qoff, loff, offs = 0, 0, []
-    for n in sizes:
-        offs.append((qoff, loff))
-        qoff += n * n
-        loff += n
+    mine = owned[rank]
+    local = B200Kron([[mats[k][2]] for k in mine]).decompose(damping=damping) if mine else None
+    send = torch.zeros(slab, device=dev, dtype=dt)
+    off = 0
     for pos, k in enumerate(mine):
         n = sizes[k]
-        Qflat[offs[k][0]:offs[k][0] + n * n].copy_(local.eigenvectors[pos][0].reshape(-1))
-        Lflat[offs[k][1]:offs[k][1] + n].copy_(local.eigenvalues[pos][0])
-    dist.all_reduce(Qflat, group=group)
-    dist.all_reduce(Lflat, group=group)
+        send[off:off + n * n].copy_(local.eigenvectors[pos][0].reshape(-1))
+        send[off + n * n:off + n * n + n].copy_(local.eigenvalues[pos][0])
+        off += n * (n + 1)
+    recv = torch.empty(world * slab, device=dev, dtype=dt)
+    dist.all_gather_into_tensor(recv, send, group=group)
     eigvecs = [[None] * len(F) for F in kron.kfacs]
     eigvals = [[None] * len(F) for F in kron.kfacs]
-    for k, (i, j, H) in enumerate(mats):
-        n = sizes[k]
-        eigvecs[i][j] = Qflat[offs[k][0]:offs[k][0] + n * n].view(n, n)
-        eigvals[i][j] = Lflat[offs[k][1]:offs[k][1] + n]
+    for r, ks in enumerate(owned):
+        off = r * slab
+        for k in ks:
+            i, j, _ = mats[k]
+            n = sizes[k]
+            eigvecs[i][j] = recv[off:off + n * n].view(n, n)
+            eigvals[i][j] = recv[off + n * n:off + n * n + n]
+            off += n * (n + 1)
     return B200KronDecomposed(eigvecs, eigvals, damping=damping)
 
 
 def fit_distributed(la, train_loader, group=None):
-    """``B200Laplace.fit`` sharded over the ranks of ``group``: local accumulation, one all-reduce, then the
-    (replicated) decomposition.  Returns ``la``."""
+    """``B200Laplace.fit`` sharded over the ranks of ``group``: local accumulation, one all-reduce, then the sharded
+    decomposition.  A rank whose shard is empty contributes zeros.  Returns ``la``."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    la.fit(ShardedLoader(train_loader, rank, world), decompose=False)
+    shard = ShardedLoader(train_loader, rank, world)
+    la.fit(shard, decompose=False)
+    check_same_order(shard, la._device, group)
     H = la.H_facs if la.structure == "kron" else la.H
-    loss = la.loss if torch.is_tensor(la.loss) else None
+    if H is None:
+        H = la.zero_curvature()
+    loss = la.loss if torch.is_tensor(la.loss) else torch.zeros((), device=la._device)
     H, loss = allreduce_curvature(H, loss, group)
-    if loss is not None:
-        la.loss = loss
+    la.loss = loss
     if la.structure == "kron":
         la.H_facs = H
         la.H = decompose_sharded(H, damping=la.damping, group=group)

@@ -17,7 +17,11 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from . import compat
+
 try:  # pragma: no cover - depends on the environment
+    if not compat.enable_reference():
+        raise ImportError("reference front end not available")
     from laplace.curvature import CurvatureInterface, EFInterface, GGNInterface  # type: ignore
     from laplace.utils.matrix import Kron, KronDecomposed  # type: ignore
 

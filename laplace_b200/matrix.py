@@ -32,6 +32,13 @@ def _is_scalar(s) -> bool:
     return torch.is_tensor(s) and s.numel() == 1 and s.ndim <= 1
 
 
+def _root(s, k: int):
+    """``s ** (1/k)`` for a Python number or a (possibly autograd-tracked) 0-/1-element tensor."""
+    if torch.is_tensor(s):
+        return torch.pow(s.reshape(()), 1.0 / k)
+    return math.pow(s, 1.0 / k)
+
+
 def _as_f32(t: torch.Tensor) -> torch.Tensor:
     return t if t.dtype == torch.float32 else t.float()
 
@@ -59,6 +66,19 @@ class B200Kron(Kron):
             kfacs.append(blk)
         return cls(kfacs, flat)
 
+    @classmethod
+    def from_kfacs(cls, kfacs) -> "B200Kron":
+        """Copy a list-of-lists of square factors (``state_dict()["H"]`` of a ``KronLaplace``, baselaplace.py:1867-1871)
+        into one flat device buffer."""
+        ref = kfacs[0][0]
+        if any(H.ndim != 2 for F in kfacs for H in F) or ref.dtype != torch.float32:
+            return cls([[H for H in F] for F in kfacs])
+        out = cls.zeros([[int(H.shape[0]) for H in F] for F in kfacs], ref.device, ref.dtype)
+        for Fo, Fi in zip(out.kfacs, kfacs):
+            for Ho, Hi in zip(Fo, Fi):
+                Ho.copy_(Hi)
+        return out
+
     def dims(self):
         return [[int(H.shape[0]) for H in F] for F in self.kfacs]
 
@@ -74,6 +94,16 @@ class B200Kron(Kron):
         if self._same_layout(other):
             out = B200Kron.zeros(self.dims(), self._flat.device, self._flat.dtype)
             torch.add(self._flat, other._flat, out=out._flat)
+            return out
+        if self._flat is not None and len(self.kfacs) == len(other.kfacs) and all(
+                len(Fi) == len(Fj) and all(Hi.shape == Hj.shape for Hi, Hj in zip(Fi, Fj))
+                for Fi, Fj in zip(self.kfacs, other.kfacs)):
+            # the other operand is a plain reference ``Kron`` (``la.H`` before the first batch, baselaplace.py:985): the
+            # sum lives in a fresh flat buffer so that later batches take the fused ``__iadd__`` / single all-reduce
+            out = B200Kron.zeros(self.dims(), self._flat.device, self._flat.dtype)
+            for Fo, Fi, Fj in zip(out.kfacs, self.kfacs, other.kfacs):
+                for Ho, Hi, Hj in zip(Fo, Fi, Fj):
+                    torch.add(Hi, Hj.to(Hi.dtype) if Hj.dtype != Hi.dtype else Hj, out=Ho)
             return out
         kfacs = [[Hi.add(Hj) for Hi, Hj in zip(Fi, Fj)] for Fi, Fj in zip(self.kfacs, other.kfacs)]
         return B200Kron(kfacs)
@@ -95,8 +125,10 @@ class B200Kron(Kron):
     def __mul__(self, scalar):
         if not _is_scalar(scalar):
             raise ValueError("Input not valid python or torch scalar.")
-        s = float(scalar)
-        return B200Kron([[math.pow(s, 1.0 / len(F)) * Hi for Hi in F] for F in self.kfacs])
+        # tensor scalars stay tensors (utils/matrix.py:116-118 uses ``pow(scalar, 1/len(F))``): the autograd graph to a
+        # differentiable ``sigma_noise`` / temperature survives and no host sync is forced
+        s = scalar if torch.is_tensor(scalar) else float(scalar)
+        return B200Kron([[_root(s, len(F)) * Hi for Hi in F] for F in self.kfacs])
 
     __rmul__ = __mul__
 
@@ -118,7 +150,7 @@ class B200Kron(Kron):
         large = []
         for n, group in by_size.items():
             dtype = group[0][2].dtype
-            if n <= K.EIGH_MAX_N and group[0][2].is_cuda:
+            if n <= K.EIGH_MAX_N and group[0][2].is_cuda and EIGH_FP64_MAX_N < n:
                 stack = torch.stack([_as_f32(H) for _, _, H in group])
                 ev, Q = K.eigh_jacobi(stack)
                 for b, (i, j, _) in enumerate(group):
@@ -162,6 +194,17 @@ class B200Kron(Kron):
         return total
 
 
+def adopt(la):
+    """Re-wrap the Kronecker factors of a fitted / loaded ``KronLaplace`` as ``B200Kron`` and decompose them with this
+    package's kernels.  Needed after ``la.load_state_dict(...)`` only: the reference rebuilds ``H_facs`` as a plain
+    ``Kron`` there (baselaplace.py:1873-1879), so the posterior would run on its torch code path.  Returns ``la``."""
+    facs = getattr(la, "H_facs", None)
+    if facs is not None and isinstance(facs, Kron) and not isinstance(facs, B200Kron):
+        la.H_facs = B200Kron.from_kfacs(facs.kfacs)
+        la.H = la.H_facs.decompose(damping=getattr(la, "damping", False))
+    return la
+
+
 N_EIGH_STREAMS = 1
 
 
@@ -191,6 +234,9 @@ def _symeig_concurrent(items, eigvals, eigvecs):
                 warnings.warn(f"laplace_b200: compact eigendecomposition failed ({e}); using the dense one")
         return symeig_large(H)
 
+    if N_EIGH_THREADS > 1 and items[0][2].is_cuda and len(items) > 1:
+        _symeig_threaded(items, one, eigvals, eigvecs)
+        return
     if serial:
         for k, (i, j, H) in enumerate(items):
             eigvals[i][j], eigvecs[i][j] = one(k, H)
@@ -205,6 +251,55 @@ def _symeig_concurrent(items, eigvals, eigvecs):
             H.record_stream(streams[k % len(streams)])
     for s_ in streams:
         cur.wait_stream(s_)
+
+
+# The library eigensolver synchronises with the host between its phases, so factors issued from ONE thread run strictly
+# one after another even on separate streams, each keeping a fraction of the SMs busy.  Worker threads (the GIL is
+# released inside ``torch.linalg.eigh``) with one stream each let the phases of different factors interleave on the device.
+N_EIGH_THREADS = int(__import__("os").environ.get("LPB_EIGH_THREADS", "1"))
+_EIGH_POOL = {}
+
+
+def _symeig_threaded(items, one, eigvals, eigvecs):
+    import queue
+    import threading
+
+    dev = items[0][2].device
+    cur = torch.cuda.current_stream(dev)
+    nthreads = min(N_EIGH_THREADS, len(items))
+    streams = _EIGH_POOL.setdefault((dev, nthreads), [torch.cuda.Stream(dev) for _ in range(nthreads)])
+    q = queue.SimpleQueue()
+    for k, it in enumerate(items):          # largest first: `items` is sorted by size
+        q.put((k, it))
+    errors = []
+
+    def work(stream):
+        try:
+            torch.cuda.set_device(dev)
+            stream.wait_stream(cur)
+            with torch.cuda.stream(stream):
+                while True:
+                    try:
+                        k, (i, j, H) = q.get_nowait()
+                    except queue.Empty:
+                        break
+                    L, W = one(k, H)
+                    for t in (L, W):
+                        t.record_stream(cur)     # allocated on the worker's stream, consumed on the caller's
+                    H.record_stream(stream)
+                    eigvals[i][j], eigvecs[i][j] = L, W
+        except BaseException as e:  # noqa: BLE001 -- re-raised in the caller's thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(s_,), daemon=True) for s_ in streams]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for s_ in streams:
+        cur.wait_stream(s_)
+    if errors:
+        raise errors[0]
 
 
 COMPACT_DEAD_COORDINATES = True
@@ -254,7 +349,19 @@ def _eigh_padded(H: torch.Tensor):
     return L[p:], W[:n, p:]
 
 
+# Factors of at most this many rows are decomposed in fp64 (library eigh on an upcast copy, results rounded back to
+# the factor dtype).  0 = off.  Experiment knob: how much of the predictive error is the fp32 eigendecomposition.
+EIGH_FP64_MAX_N = int(__import__("os").environ.get("LPB_EIGH_FP64_MAX_N", "0"))
+
+
 def symeig_large(H: torch.Tensor):
+    if H.shape[0] <= EIGH_FP64_MAX_N and H.dtype != torch.float64:
+        L, W = torch.linalg.eigh(H.double(), UPLO="U")
+        return torch.nan_to_num(L.clamp(min=0.0)).to(H.dtype), torch.nan_to_num(W).to(H.dtype)
+    return _symeig_large(H)
+
+
+def _symeig_large(H: torch.Tensor):
     """Factors beyond the Jacobi kernel's limit: cuSOLVER ``syevd`` via ``torch.linalg.eigh`` (LIBRARY call,
     declared as such in DESIGN.md) with the reference's post-processing (utils/utils.py:207-228): jitter retry,
     clamp at 0, NaN -> 0; raises ``LinAlgError`` instead of the reference's ``exit()`` (SURVEY App. B #8)."""
@@ -330,8 +437,10 @@ class B200KronDecomposed(KronDecomposed):
     def __mul__(self, scalar):
         if not _is_scalar(scalar):
             raise ValueError("Invalid argument, can only multiply Kron with scalar.")
-        s = float(scalar)
-        ev = [[math.pow(s, 1.0 / len(ls)) * l for l in ls] for ls in self.eigenvalues]
+        # utils/matrix.py:372-376: ``pow(scalar, 1/len(ls)) * eigval`` -- a tensor scalar (``_H_factor`` with a
+        # differentiable ``sigma_noise``) keeps its graph, so d logdet / d sigma_noise flows like in the reference
+        s = scalar if torch.is_tensor(scalar) else float(scalar)
+        ev = [[_root(s, len(ls)) * l for l in ls] for ls in self.eigenvalues]
         out = B200KronDecomposed(self.eigenvectors, ev, self.deltas)
         out._cache = self._cache
         return out

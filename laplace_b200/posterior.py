@@ -172,6 +172,19 @@ class B200Laplace:
     def decompose(self):
         self.H = self.H_facs.decompose(damping=self.damping)
 
+    def zero_curvature(self):
+        """The curvature of an empty data shard, laid out like a fitted one (``Kron.init_from_model``,
+        utils/matrix.py:33-77: ``[out x out, in x in]`` per weight, ``[n x n]`` per bias, ``parameters()`` order)."""
+        dev = self._device
+        if self.structure == "kron":
+            dims = []
+            for p in self.params:
+                dims.append([p.shape[0]] if p.ndim == 1 else [p.shape[0], int(p.numel() // p.shape[0])])
+            return B200Kron.zeros(dims, dev, torch.float32)
+        if self.structure == "full":
+            return torch.zeros(self.n_params, self.n_params, device=dev)
+        return torch.zeros(self.n_params, device=dev)
+
     # ------------------------------------------------------------------ posterior
     @property
     def posterior_precision(self):

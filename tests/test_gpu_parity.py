@@ -11,6 +11,11 @@ from oracle import curvature_oracle as co
 from oracle import kron_oracle as ko
 from tests.fixtures import load, rel_fro
 
+
+def var_err(f_var, ref):
+    """Largest deviation relative to the largest reference variance."""
+    return float((f_var.cpu().double() - ref).abs().max() / ref.abs().max())
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 CASES = [(k, l) for k in ("mlp", "conv") for l in ("classification", "regression")]
@@ -95,58 +100,6 @@ def test_kfac_model_zoo_vs_oracle(name, kw, B, precision):
     assert worst < FACTOR_TOL, worst
 
 
-def test_kfac_invariants_at_scale():
-    """Reference invariants (tests/test_curv_backends_curvlinops.py:207-333) at a size the oracle cannot reach:
-    batch additivity, 7x normalisation, symmetry / PSD of every factor, on the full-width ResNet-18 shape."""
-    model = models.make("resnet18").to(DEV)
-    torch.manual_seed(2)
-    X, y = torch.randn(96, 3, 32, 32, device=DEV), torch.randint(10, (96,), device=DEV)
-    be = B200GGN(model, "classification", precision="bf16x3")
-    _, whole = be.kron(X, y, N=96)
-    _, a = be.kron(X[:40], y[:40], N=96)
-    _, b = be.kron(X[40:], y[40:], N=96)
-    parts = a + b
-    for Fw, Fp in zip(whole.kfacs, parts.kfacs):
-        for hw, hp in zip(Fw, Fp):
-            assert rel_fro(hp, hw) < 1e-4
-            assert rel_fro(hw, hw.t()) < 1e-6 and float(hw.diagonal().min()) >= 0
-    _, k7 = be.kron(X[:16].repeat(7, 1, 1, 1), y[:16].repeat(7), N=7 * 16)
-    _, k1 = be.kron(X[:16], y[:16], N=16)
-    assert rel_fro(k7.diag(), 7 * k1.diag()) < 1e-4
-
-
-def test_large_batch_paths_agree_with_unfused_explicit_paths():
-    """Bench-shaped batch (full-width ResNet-18, B = 1024: fused conv->BN->ReLU reverse chains, persistent implicit /
-    strided convolutions, im2col-free input factors on a side stream) against the same backend with every one of those
-    switched off (separate element-wise kernels, patch-row SYRKs): identical factors up to operand rounding, batch
-    additivity across the two code paths, symmetric PSD blocks.  (B = 4096: tools/gpu_probe_scale.py, 3.4e-6.)"""
-    from laplace_b200 import kernels as K
-
-    model = models.make("resnet18").to(DEV)
-    torch.manual_seed(3)
-    X, y = torch.randn(1024, 3, 32, 32, device=DEV), torch.randint(10, (1024,), device=DEV)
-    be = B200GGN(model, "classification", precision="bf16x3")
-    _, k1 = be.kron(X, y, N=50000)
-    assert be._fused and be.last_backward_mode == "batched"
-    ok = K.conv_patches_ok
-    K.conv_patches_ok = lambda *a: False
-    try:
-        be2 = B200GGN(model, "classification", precision="bf16x3", fuse_elementwise=False)
-        be2.overlap_factors = False
-        _, ka = be2.kron(X[:512], y[:512], N=50000)
-        _, kb = be2.kron(X[512:], y[512:], N=50000)
-    finally:
-        K.conv_patches_ok = ok
-    k2 = ka + kb
-    worst = 0.0
-    for F1, F2 in zip(k1.kfacs, k2.kfacs):
-        for a, b in zip(F1, F2):
-            assert torch.isfinite(a).all()
-            worst = max(worst, rel_fro(a, b))
-            assert rel_fro(a, a.t()) < 1e-5 and float(a.diagonal().min()) >= 0
-    assert worst < 3e-5, worst
-
-
 @pytest.mark.parametrize("kind", ["mlp", "conv"])
 @pytest.mark.parametrize("lik", ["classification", "regression"])
 def test_kron_posterior_predictive(golden, kind, lik):
@@ -163,12 +116,12 @@ def test_kron_posterior_predictive(golden, kind, lik):
     la = B200Laplace(model, lik, "all", "kron", prior_precision=0.7).fit(DataLoader(TensorDataset(Xd, yd), batch_size=5))
     f_mu, f_var = la.glm_predictive_distribution(Xd)
     assert torch.allclose(f_mu.cpu().double(), f, atol=1e-5)
-    assert float((f_var.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+    assert var_err(f_var, ref) < VAR_TOL, var_err(f_var, ref)
     assert torch.allclose(la.log_det_posterior_precision.cpu().double(), ko.kron_logdet(ls, delta), rtol=1e-4)
     # dense (factor-free) route through the rotation GEMMs gives the same variances
     Jd, _ = la.backend.jacobians(Xd)
     dense = la.posterior_precision.inv_square_form(Jd.clone())
-    assert float((dense.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+    assert var_err(dense, ref) < VAR_TOL, var_err(dense, ref)
 
 
 @pytest.mark.parametrize("hs", ["full", "diag"])
@@ -179,7 +132,7 @@ def test_full_diag_posterior_vs_golden(golden, hs, lik):
     la = B200Laplace(model, lik, "all", hs, prior_precision=0.7).fit(DataLoader(TensorDataset(X, y), batch_size=4))
     f_mu, f_var = la.glm_predictive_distribution(X)
     ref = rec[f"la_{hs}_f_var"]
-    assert float((f_var.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+    assert var_err(f_var, ref) < VAR_TOL, var_err(f_var, ref)
     if lik == "classification":
         assert torch.allclose(la(X).cpu().double(), rec[f"la_{hs}_probit"], atol=1e-5)
 
@@ -195,7 +148,7 @@ def test_last_layer_full_vs_golden(golden, lik):
     f_mu, f_var = la.glm_predictive_distribution(X)
     Sigma = ko.full_posterior_covariance(rec["ll_ggn_full"], torch.full((la.n_params,), 0.7, dtype=torch.float64))
     ref = ko.full_functional_variance(rec["ll_Js"], Sigma)
-    assert float((f_var.cpu().double() - ref).abs().max() / ref.abs().max()) < 5 * VAR_TOL
+    assert var_err(f_var, ref) < VAR_TOL, var_err(f_var, ref)
     ef = B200Laplace(model, lik, "last_layer", "full", backend=B200EF).fit(DataLoader(TensorDataset(X, y), batch_size=4))
     Gs, fr = co.gradients(rec["ll_Js"], rec["ll_f"], rec["y"], lik)
     fac = co.likelihood_factor(lik)
@@ -219,8 +172,9 @@ def test_last_layer_full_resnet_structured_vs_dense():
 
 def test_config1_mlp_parity_anchor():
     """BASELINE configs[0] (the parity anchor): MLP 784->128->10, N=1000, B=128, KFAC-GGN fit + GLM predictive.
-    Factors within 1e-4 rel-fro, predictive variances within 1e-5 of the largest variance (fp32 pipeline vs fp64 oracle
-    fed with the SAME factors, i.e. the posterior-side kernels in isolation) and 1e-4 end to end."""
+    Factors within 1e-4 rel-fro; predictive variances within 1e-5 of the largest variance both against the oracle algebra
+    on OUR eigendecomposition (posterior-side kernels in isolation) and end to end against the fp64 oracle's own
+    factors and decomposition (measured 3.6e-6, profiles/r02_predictive_error.md)."""
     torch.manual_seed(0)
     model = models.make("mlp")
     # data seed 2: with seed 1 one hidden unit of sample batch 6 has an fp64 pre-activation of 1.5e-7 -- below the
@@ -254,5 +208,5 @@ def test_config1_mlp_parity_anchor():
     Qo, lo = ko.decompose(kfs)
     ref = ko.kron_inv_square_form(Qo, lo, delta, Js)
     err_e2e = float((f_var.cpu().double() - ref).abs().max() / ref.abs().max())
-    assert err_e2e < 1e-4, f"end-to-end predictive variance error {err_e2e:.2e}"
+    assert err_e2e < VAR_TOL, f"end-to-end predictive variance error {err_e2e:.2e}"
     assert torch.allclose(f_mu.cpu().double(), f, atol=1e-5)
