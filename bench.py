@@ -44,11 +44,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--precision", default="bf16x3", choices=["auto", "fp32", "bf16", "bf16x3"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "bf16x3"])
     ap.add_argument("--model", default="resnet18")
     ap.add_argument("--cpu-samples", type=int, default=256, help="samples of the bounded CPU-baseline run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--predictive", action="store_true", help="also time the GLM predictive (reported under config)")
+    ap.add_argument("--no-predictive", action="store_true", help="skip the GLM-predictive legs")
     ap.add_argument("--model-tf32", action="store_true", help="let cuDNN/cuBLAS use TF32 in the model's own passes")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = min(cores, 16), the measured optimum)")
     return ap.parse_args()
@@ -179,7 +179,10 @@ def run_ours(args):
 
     from laplace_b200 import B200GGN
     from laplace_b200 import kernels as K
-    from laplace_b200.distributed import allreduce_curvature
+    from laplace_b200 import matrix
+    from laplace_b200.data import PrefetchLoader
+    from laplace_b200.distributed import allreduce_curvature, decompose_sharded
+    from laplace_b200.interface import HAVE_REFERENCE
     from laplace_b200.posterior import B200Laplace
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,7 +196,8 @@ def run_ours(args):
     B, Ksteps, W = args.batch, args.steps, max(3, args.warmup)
     N_total = 50000
     model = make_model(args.model).to(dev)
-    be = B200GGN(model, "classification", precision=args.precision, model_tf32=args.model_tf32)
+    be_kwargs = {"precision": args.precision, "model_tf32": args.model_tf32}
+    be = B200GGN(model, "classification", **be_kwargs)
     shape = input_shape(args.model)
     torch.manual_seed(1 + rank)
     n_batches = min(8, W + Ksteps)  # pool of distinct batches; factor buffers (376 MB) dwarf the 126 MB L2 anyway
@@ -212,6 +216,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(fn):
+        """CUDA-event time of fn() on the current stream, barrier + synchronize on both sides, max over ranks."""
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn()
+        e.record()
+        barrier()
+        return max_over_ranks(s.elapsed_time(e)), out
+
     # ---------------- device-resident run ----------------
     H = None
 
@@ -228,25 +242,56 @@ def run_ours(args):
         clocks.start()
     for i in range(W):
         step(i)
+    # the exchange is part of the timed region: warm the very collective it uses (NCCL builds its channels / registers
+    # the buffer on the first call of a given size -- 75 ms for the 376 MB factor buffer when it was left cold)
+    scratch = None
+    if world > 1:
+        scratch = torch.zeros_like(H._flat)
+        for _ in range(2):
+            dist.all_reduce(scratch)
     barrier()
     l0 = K.LAUNCHES
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(Ksteps):
-        step(W + i)
-    allreduce_curvature(H)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+
+    def timed_steps():
+        for i in range(Ksteps):
+            step(W + i)
+        allreduce_curvature(H)
+
+    ms_total, _ = timed(timed_steps)
     launches = K.LAUNCHES - l0
     clk = clocks.stop() if rank == 0 else None
     value = world * Ksteps * B / (ms_total / 1e3)
+    exchange = {"call": "none (single process)", "bytes": 0, "ms": 0.0}
+    if world > 1:
+        ms_coll, _ = timed(lambda: dist.all_reduce(scratch))
+        exchange = {"call": "ncclAllReduce(sum, fp32) of the flat Kronecker-factor buffer, once after the K steps, inside the "
+                            "timed region", "bytes": int(scratch.numel() * 4), "ms": round(ms_coll, 3),
+                    "busbw_GBps": round(2 * (world - 1) / world * scratch.numel() * 4 / (ms_coll / 1e3) / 1e9, 1)}
+        del scratch
+
+    # ---------------- once-per-fit eigendecomposition (inside KronLaplace.fit, baselaplace.py:1809), sharded over ranks ----
+    extras = {}
+
+    def decompose_once():
+        return decompose_sharded(H) if world > 1 else H.decompose()
+
+    t0 = time.perf_counter()
+    ms_cold, _ = timed(decompose_once)
+    ms_dec, Hd = timed(decompose_once)
+    extras["decompose_ms_first_call_cold"] = round(ms_cold, 1)
+    extras["decompose_ms_once_per_fit"] = round(ms_dec, 1)
+    extras["decompose_how"] = (f"factors sharded over {world} ranks (greedy n^3 balance), local eigh, one all-gather of Q/lambda"
+                               if world > 1 else "single process") + \
+        f"; n<=128 hand-written Jacobi kernel, larger: library syevd on {matrix.N_EIGH_THREADS} host threads, dead-coordinate " \
+        f"compaction {'on' if matrix.COMPACT_DEAD_COORDINATES else 'off'}, 385..512 padded to 513 {'on' if matrix.PAD_EIGH else 'off'}"
+    fit_s = N_total / value + ms_dec / 1e3
+    extras["fit_50k_samples_per_sec_incl_decompose"] = round(N_total / fit_s, 1)
+    del Hd
 
     # ---------------- roofline of the dominant kernel (separate short pass, CUDA events around each launch) -----
     roof = measure_roofline(be, K, Xs, ys, N_total, args, dev)
 
-    # ---------------- end-to-end through the public API with pinned host batches ----------------
+    # ---------------- end to end through the public API with pinned host batches ----------------
     Xh = [x.cpu().pin_memory() for x in Xs]
     yh = [y.cpu().pin_memory() for y in ys]
 
@@ -260,54 +305,62 @@ def run_ours(args):
         def __init__(self, n, off):
             self.n, self.off = n, off
 
+        def __len__(self):
+            return self.n
+
         def __iter__(self):
             for i in range(self.n):
                 j = (self.off + i) % n_batches
                 yield Xh[j], yh[j]
 
-    la = B200Laplace(model, "classification", "all", "kron", backend=B200GGN, backend_kwargs={"precision": args.precision, "model_tf32": args.model_tf32})
-    la.fit(HostLoader(W, 0), decompose=False)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    la.fit(HostLoader(Ksteps, W), decompose=False)
-    allreduce_curvature(la.H_facs)
-    loss_host = float(la.loss)  # device -> host read of the step result
-    e3.record()
-    barrier()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    if HAVE_REFERENCE:
+        # the UNMODIFIED reference front end: Laplace(...) constructs the backend (baselaplace.py:179-194); the per-batch
+        # loop is ParametricLaplace.fit (baselaplace.py:904-987) -- KronLaplace.fit adds only the decomposition, which is
+        # timed above -- fed by a loader that stages batch i+1 on a copy stream (laplace_b200/data.py)
+        import laplace
+        from laplace.baselaplace import ParametricLaplace
+
+        la = laplace.Laplace(model, "classification", "all", "kron", backend=B200GGN, backend_kwargs=be_kwargs)
+        api = "laplace.Laplace(model, 'classification', 'all', 'kron', backend=B200GGN) [unmodified reference front end, " \
+              "baseline/_ref]; timed: ParametricLaplace.fit(la, PrefetchLoader(host batches)) + all-reduce + loss read"
+
+        def run_fit(n, off):
+            ParametricLaplace.fit(la, PrefetchLoader(HostLoader(n, off), dev))
+            return la.H
+    else:
+        la = B200Laplace(model, "classification", "all", "kron", backend=B200GGN, backend_kwargs=be_kwargs)
+        api = "laplace_b200.posterior.B200Laplace.fit (host-side mirror: the reference package is not importable here)"
+
+        def run_fit(n, off):
+            la.fit(HostLoader(n, off), decompose=False)
+            return la.H_facs
+
+    run_fit(W, 0)
+    state = {}
+
+    def e2e_steps():
+        Hk = run_fit(Ksteps, W)
+        allreduce_curvature(Hk)
+        state["loss"] = float(la.loss)  # device -> host read of the step result
+
+    ms_e2e, _ = timed(e2e_steps)
     e2e_value = world * Ksteps * B / (ms_e2e / 1e3)
     h2d = Xh[0].numel() * 4 + yh[0].numel() * 8
 
-    extras = {}
-    if rank == 0:
-        # The legs below annotate the line (once-per-fit decomposition, the contraction kernel alone, predictive); a
-        # failure in one of them must not lose the headline measurement, so each is recorded as an error string instead.
-        def leg(name, fn):
-            try:
-                fn()
-            except Exception as e:  # noqa: BLE001 -- reported, not swallowed
-                extras[name + "_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+    # The legs below annotate the line (predictive, small-batch line, the contraction kernel alone); a failure in one of
+    # them must not lose the headline measurement, so each is recorded as an error string instead.
+    def leg(name, fn):
+        try:
+            fn()
+        except Exception as e:  # noqa: BLE001 -- reported, not swallowed
+            extras[name + "_error"] = f"{type(e).__name__}: {str(e)[:300]}"
 
-        def decompose_leg():
-            # warm-up: one untimed decompose() (pages in cuSOLVER's syevd kernels for every factor size -- seconds on a
-            # cold process), then the timed one; the cold figure is kept next to it
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            la.decompose()
-            torch.cuda.synchronize()
-            extras["decompose_ms_first_call_cold"] = (time.perf_counter() - t0) * 1e3
-            t0 = time.perf_counter()
-            la.decompose()
-            torch.cuda.synchronize()
-            extras["decompose_ms_once_per_fit"] = (time.perf_counter() - t0) * 1e3
-            # BASELINE config: one fit() over N = 50 000 samples = N / value seconds of per-batch work + one decompose
-            extras["fit_50k_samples_per_sec_incl_decompose"] = N_total / (N_total / value + extras["decompose_ms_once_per_fit"] / 1e3)
-
-        leg("decompose", decompose_leg)
+    pred = {}
+    if not args.no_predictive:
+        leg("predictive", lambda: pred.update(measure_predictive(model, dev, world, timed, args)))
+    if rank == 0 and world == 1:
+        leg("b512", lambda: extras.__setitem__("batch_512", measure_small_batch(be, dev, shape, N_total)))
         leg("jtj_syrk_kernel", lambda: extras.__setitem__("jtj_syrk_kernel", measure_syrk_probe(K, dev)))
-        if args.predictive:
-            leg("predictive", lambda: extras.update(measure_predictive(model, dev, B200Laplace, B200GGN, args)))
 
     if rank == 0:
         cpu = None
@@ -320,24 +373,46 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ksteps, "warmup": W,
             "ms_per_step": ms_total / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16x3": "bf16 (hi/lo split, 3 products, fp32 accumulate)", "bf16": "bf16", "fp32": "f32",
-                      "auto": "bf16x3/f32 auto"}[args.precision],
+                      "auto": "fp16/bf16 hi/lo split operands, fp32 accumulate (3 products; input factors over >= 16384 "
+                              "rows: 1 fp16 product)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": workload_name(args), "batch_per_gpu": B, "global_batch": B * world, "N_dataset": N_total,
                        "parallelism": f"dp{world}", "precision": args.precision,
                        "model_passes": "tf32 (PyTorch default)" if args.model_tf32 else "fp32 (TF32 disabled in cuDNN/cuBLAS)",
                        "l2": "distinct batch every step; per-step working set (factor buffers 376 MB + staging) exceeds the 126 MB L2",
-                       "exchange": "one all-reduce of the flat factor buffer after the K steps, inside the timed region",
-                       **extras},
+                       "exchange": exchange, "e2e_api": api, **extras},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / Ksteps, "loss": loss_host},
+                    "ms_per_step": ms_e2e / Ksteps, "loss": state.get("loss")},
             "gpu_launches": launches,
             "roofline": roof,
+            "predictive": pred or None,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_small_batch(be, dev, shape, N_total, B=512, steps=10):
+    """SURVEY 8(d) quotes cfg2 at B = 512: the same step at that batch size (host-bound: ~1500 launches per step)."""
+    torch.manual_seed(11)
+    Xs = [torch.randn(B, *shape, device=dev) for _ in range(4)]
+    ys = [torch.randint(10, (B,), device=dev) for _ in range(4)]
+    H = None
+    for i in range(3):
+        _, k = be.kron(Xs[i % 4], ys[i % 4], N=N_total)
+        H = k if H is None else H.__iadd__(k)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        _, k = be.kron(Xs[i % 4], ys[i % 4], N=N_total)
+        H += k
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    return {"ms_per_step": round(ms, 3), "samples_per_sec": round(B / (ms / 1e3), 1)}
 
 
 def measure_roofline(be, K, Xs, ys, N_total, args, dev):
@@ -465,40 +540,88 @@ def measure_syrk_probe(K, dev):
     return out
 
 
-def measure_predictive(model, dev, B200Laplace, B200GGN, args):
-    """GLM predictive samples/s of the last-layer full posterior (BASELINE configs[2])."""
-    torch.manual_seed(5)
-    Xf = torch.randn(2048, *input_shape(args.model), device=dev)
-    yf = torch.randint(10, (2048,), device=dev)
-    la = B200Laplace(model, "classification", "last_layer", "full", backend=B200GGN)
-    la.fit(torch.utils.data.DataLoader(torch.utils.data.TensorDataset(Xf, yf), batch_size=512))
-    la(Xf[:512])
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(4):
-        la(Xf[i * 512:(i + 1) * 512])
-    torch.cuda.synchronize()
-    out = {"glm_predictive_ll_full_samples_per_sec": 2048 / (time.perf_counter() - t0)}
-    # BASELINE configs[0]: MLP 784->128->10, N = 1000, KFAC-GGN fit + GLM predictive over the same 1000 points
-    from laplace_b200 import models
+def measure_predictive(model, dev, world, timed, args):
+    """GLM-predictive samples/s (the metric's second half).  Every rank predicts its own shard of test points, no
+    collective; the aggregate is world x points / max-over-ranks time.
 
+    * BASELINE configs[2]: ResNet-18 shape, last-layer full GGN posterior (P = 5130), probit predictive of 10 000 test
+      points per GPU in batches of 1000, after a fit on 2048 points;
+    * BASELINE configs[0]: MLP 784-128-10, all-weights Kron posterior, 1000 points (fit incl. decomposition timed too).
+
+    Through the unmodified reference front end when it is importable (``la(x, pred_type="glm", link_approx="probit")``),
+    through the host-side mirror otherwise -- `api` says which."""
+    from laplace_b200 import B200GGN, models
+    from laplace_b200.interface import HAVE_REFERENCE
+    from laplace_b200.posterior import B200Laplace
+
+    TD, DL = torch.utils.data.TensorDataset, torch.utils.data.DataLoader
+    if HAVE_REFERENCE:
+        import laplace
+
+        def make(m, sub, hs):
+            return laplace.Laplace(m, "classification", sub, hs, backend=B200GGN)
+
+        def predict(la, x):
+            return la(x, pred_type="glm", link_approx="probit")
+        api = "laplace.Laplace(..., backend=B200GGN): la.fit(loader); la(x, pred_type='glm', link_approx='probit')"
+    else:
+        def make(m, sub, hs):
+            return B200Laplace(m, "classification", sub, hs, backend=B200GGN)
+
+        def predict(la, x):
+            return la(x)
+        api = "laplace_b200.posterior.B200Laplace (mirror; reference not importable)"
+    out = {"api": api}
+    if args.model == "resnet18":
+        torch.manual_seed(5)
+        shape = input_shape(args.model)
+        Xf, yf = torch.randn(2048, *shape, device=dev), torch.randint(10, (2048,), device=dev)
+        n_test, bs = 10000, 1000
+        Xt = torch.randn(n_test, *shape, device=dev)
+        la = make(model, "last_layer", "full")
+        la.fit(DL(TD(Xf, yf), batch_size=512))
+        predict(la, Xt[:bs])                       # warm-up: posterior covariance, gathered blocks, allocator
+        predict(la, Xt[:bs])
+
+        def run():
+            acc = 0.0
+            for i in range(0, n_test, bs):
+                acc = acc + predict(la, Xt[i:i + bs]).sum()
+            return float(acc)                      # device -> host read of the result
+
+        ms, _ = timed(run)
+        rate = world * n_test / (ms / 1e3)
+        D, C = 512, 10
+        flops = 2.0 * (D + 1) * (C * C * (D + 1)) + 2.0 * C * C * (D + 1)   # [phi;1] against the gathered blocks + pair dots
+        peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        out["ll_full_resnet18"] = {
+            "samples_per_sec": round(rate, 1), "test_points_per_gpu": n_test, "batch": bs, "ms_total": round(ms, 2),
+            "includes": "backbone forward (convolution engine) + structured J Sigma J^T + probit link, result read back",
+            "roofline": {"bound": "fp32 SIMT FMA (gemm_nt_f32: [phi;1] x gathered covariance blocks)",
+                         "algorithmic_flops_per_sample": flops, "achieved": round(flops * rate / world / 1e12, 2),
+                         "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(flops * rate / world / 1e12 / peak, 3),
+                         "peak_source": "nominal: 148 SMs x 128 fp32 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 entry)",
+                         "dense_equivalent_flops_per_sample": 2.0 * C * 5130 ** 2 + 2.0 * C * C * 5130}}
+        del la, Xt
+    # BASELINE configs[0]
     mlp = models.make("mlp").to(dev)
     torch.manual_seed(6)
     Xm, ym = torch.randn(1000, 784, device=dev), torch.randint(10, (1000,), device=dev)
-    lam = B200Laplace(mlp, "classification", "all", "kron", backend=B200GGN)
-    loader = torch.utils.data.DataLoader(torch.utils.data.TensorDataset(Xm, ym), batch_size=128)
+    lam = make(mlp, "all", "kron")
+    loader = DL(TD(Xm, ym), batch_size=128)
     lam.fit(loader)
-    lam(Xm[:500])
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    lam.fit(loader)
-    torch.cuda.synchronize()
-    out["mlp_kron_fit_1k_samples_per_sec_incl_decompose"] = 1000 / (time.perf_counter() - t0)
-    t0 = time.perf_counter()
-    for i in range(0, 1000, 500):
-        lam(Xm[i:i + 500])
-    torch.cuda.synchronize()
-    out["mlp_kron_glm_predictive_samples_per_sec"] = 1000 / (time.perf_counter() - t0)
+    predict(lam, Xm[:500])
+    ms_fit, _ = timed(lambda: lam.fit(loader))
+
+    def run_mlp():
+        acc = 0.0
+        for i in range(0, 1000, 500):
+            acc = acc + predict(lam, Xm[i:i + 500]).sum()
+        return float(acc)
+
+    ms_pred, _ = timed(run_mlp)
+    out["mlp_kron"] = {"fit_1k_samples_per_sec_incl_decompose": round(world * 1000 / (ms_fit / 1e3), 1),
+                       "glm_predictive_samples_per_sec": round(world * 1000 / (ms_pred / 1e3), 1), "batch": 500}
     return out
 
 

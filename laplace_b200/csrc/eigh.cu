@@ -6,7 +6,7 @@
 
 namespace lpb {
 
-__global__ void __launch_bounds__(256) eigh_jacobi_kernel(const float* __restrict__ Ain, int n, float* __restrict__ evals,
+__global__ void __launch_bounds__(512) eigh_jacobi_kernel(const float* __restrict__ Ain, int n, float* __restrict__ evals,
                                                           float* __restrict__ Qout, int max_sweeps) {
   extern __shared__ float sm[];
   const int np = (n + 1) & ~1;  // even player count for the round-robin schedule
@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(const float* __restric
   float* cs = V + np * ld;       // 2 * (np/2)
   int* pq = reinterpret_cast<int*>(cs + np);  // 2 * (np/2)
   __shared__ int rotated;
+  __shared__ float abs_floor;
   __shared__ int order[256];
   const float* Ab = Ain + (int64_t)blockIdx.x * n * n;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -26,6 +27,15 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(const float* __restric
     if (i < n && j < n) a = (i <= j) ? Ab[(int64_t)i * n + j] : Ab[(int64_t)j * n + i];  // UPLO = 'U'
     A[i * ld + j] = a;
     V[i * ld + j] = (i == j) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // off-diagonal entries below 2e-8 * max|diag| are at the rounding level of the rotations that touch their rows
+    // (6e-8 of the large entries): chasing them with the relative criterion alone never terminates for the
+    // (large, tiny) eigenvalue pairs of a rank-deficient PSD factor and burns all max_sweeps
+    float dmax = 0.f;
+    for (int i = 0; i < n; ++i) dmax = fmaxf(dmax, fabsf(A[i * ld + i]));
+    abs_floor = 2e-8f * dmax;
   }
   __syncthreads();
 
@@ -42,7 +52,7 @@ __global__ void __launch_bounds__(256) eigh_jacobi_kernel(const float* __restric
         if (p > q) { int t = p; p = q; q = t; }
         const float app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
         float c = 1.f, s = 0.f;
-        if (fabsf(apq) > 1e-30f && fabsf(apq) > 6e-8f * sqrtf(fabsf(app * aqq))) {
+        if (fabsf(apq) > 1e-30f && fabsf(apq) > abs_floor && fabsf(apq) > 6e-8f * sqrtf(fabsf(app * aqq))) {
           // angles in double: a float rsqrt leaves c^2 + s^2 = 1 +- 1e-7 with a systematic sign, which
           // compounds over the ~2n rotations that touch every element per sweep
           const double tau = ((double)aqq - (double)app) / (2.0 * (double)apq);
@@ -123,7 +133,7 @@ int eigh_jacobi(const float* A, int batch, int n, float* evals, float* Q, int ma
       return 1;
     attr_set = true;
   }
-  eigh_jacobi_kernel<<<batch, 256, smem, st>>>(A, n, evals, Q, max_sweeps > 0 ? max_sweeps : 30);
+  eigh_jacobi_kernel<<<batch, np >= 96 ? 512 : 256, smem, st>>>(A, n, evals, Q, max_sweeps > 0 ? max_sweeps : 30);
   LPB_CHECK_LAUNCH("eigh_jacobi");
   return 0;
 }

@@ -14,6 +14,8 @@ import torch
 from . import _lib
 
 F32, BF16, BF16X3, F16X3 = 0, 1, 2, 3  # out_kind of the pack kernels (LPB_OUT_*)
+F16 = 4                                # host-side only: the hi half of an F16X3 operand used alone (one fp16 product)
+FP16_KINDS = (F16X3, F16)
 KIND_OF = {"fp32": F32, "bf16": BF16, "bf16x3": BF16X3, "fp16x3": F16X3}
 
 LAUNCHES = 0  # number of native kernel launches issued through this module (bench.py reads it)
@@ -53,6 +55,13 @@ class Packed:
     @property
     def ldk(self) -> int:
         return self.hi.shape[1]
+
+
+def hi_only(P: Packed) -> Packed:
+    """The leading 16-bit half of a hi/lo operand as a single-product operand (no copy)."""
+    if P.lo is None:
+        return P
+    return Packed(P.hi, None, F16 if P.kind == F16X3 else BF16, P.rows, P.K)
 
 
 def round_up(x: int, m: int) -> int:
@@ -372,11 +381,11 @@ def gemm_tn(A: Packed, B: Packed, out: torch.Tensor, alpha: float = 1.0, accumul
     (``Packed.rows`` = sample rows, ``Packed.K`` = features): the tcgen05 kernel with MN-major descriptors."""
     _check(out, name="out")
     M, N = out.shape
-    assert A.kind in (BF16, BF16X3, F16X3) and A.kind == B.kind and A.K == M and B.K == N and A.rows == B.rows
+    assert A.kind in (BF16, BF16X3, F16X3, F16) and A.kind == B.kind and A.K == M and B.K == N and A.rows == B.rows
     if symmetric:
         assert A.hi.data_ptr() == B.hi.data_ptr() and M == N
     _lib.call("lpb_gemm_tn_tc", _ptr(A.hi), _ptr(A.lo), A.ldk, _ptr(B.hi), _ptr(B.lo), B.ldk, M, N, A.rows, alpha,
-              1 if accumulate else 0, _ptr(out), out.stride(0), 1 if symmetric else 0, 1 if A.kind == F16X3 else 0, _stream())
+              1 if accumulate else 0, _ptr(out), out.stride(0), 1 if symmetric else 0, 1 if A.kind in FP16_KINDS else 0, _stream())
     _bump()
     return out
 
@@ -402,10 +411,10 @@ def syrk_conv_patches(X: Packed, Q: int, H: int, W: int, mod, out: torch.Tensor,
     ph, pw = mod.padding
     live = sum(1 for a in range(kh) for b in range(kw) if abs(a - ph) < H and abs(b - pw) < W)   # == lpb_conv_live_taps
     dp = Ci_pad * live
-    assert out.shape == (d, d) and X.rows == Q * H * W and X.kind in (BF16, BF16X3, F16X3)
+    assert out.shape == (d, d) and X.rows == Q * H * W and X.kind in (BF16, BF16X3, F16X3, F16)
     T = torch.empty(dp, dp, device=out.device, dtype=torch.float32)
     _lib.call("lpb_syrk_conv_patches_tc", _ptr(X.hi), _ptr(X.lo), X.ldk, Q, H, W, Ci, kh, kw, mod.padding[0], mod.padding[1],
-              alpha, 0, _ptr(T), T.stride(0), 1 if X.kind == F16X3 else 0, _stream())
+              alpha, 0, _ptr(T), T.stride(0), 1 if X.kind in FP16_KINDS else 0, _stream())
     _lib.call("lpb_taps_to_param_accumulate", _ptr(T), T.stride(0), Ci, Ci_pad, kh, kw, ph, pw, H, W, _ptr(out), out.stride(0),
               _stream())
     _bump(2)

@@ -256,7 +256,7 @@ def _symeig_concurrent(items, eigvals, eigvecs):
 # The library eigensolver synchronises with the host between its phases, so factors issued from ONE thread run strictly
 # one after another even on separate streams, each keeping a fraction of the SMs busy.  Worker threads (the GIL is
 # released inside ``torch.linalg.eigh``) with one stream each let the phases of different factors interleave on the device.
-N_EIGH_THREADS = int(__import__("os").environ.get("LPB_EIGH_THREADS", "1"))
+N_EIGH_THREADS = int(__import__("os").environ.get("LPB_EIGH_THREADS", "4"))   # measured: 315 (1) / 236 (2) / 209 (4) / 209 ms (8)
 _EIGH_POOL = {}
 
 
@@ -331,9 +331,10 @@ def _symeig_compact(H: torch.Tensor):
 # the divide-and-conquer one (syevd); on B200 syevd is ~2.5x faster just above the threshold (576: 6.7 ms) than syevj
 # just below it (512: 17 ms).  Matrices in PAD_EIGH_RANGE are therefore bordered with a negative diagonal block up to 513
 # rows: the border decouples exactly, sorts first, and is dropped.
-PAD_EIGH_RANGE = (385, 512)
+PAD_EIGH_RANGE = (129, 512)
 PAD_EIGH_TO = 513
-PAD_EIGH = False      # opt-in until it has been timed and its effect on the 1e-5 predictive gate checked on the GPU
+PAD_EIGH = True       # measured on B200 (profiles/r02_eigh.md): 256: 5.3 (syevj) vs 5.6 ms padded, 384: 9.8 vs 5.6,
+                      # 512: 14.7 vs 5.6; the whole ResNet-18 decomposition 410 -> 315 ms
 _PAD_ON_CPU = False   # tests flip this to exercise the bordering logic without a GPU
 
 
@@ -393,6 +394,14 @@ class JacobianFactors:
 
     def __init__(self, blocks, n_batch: int, n_out: int, sizes):
         self.blocks, self.n_batch, self.n_out, self.sizes = blocks, n_batch, n_out, sizes
+        self._proj = (None, {})
+
+    def projections(self, basis_key) -> dict:
+        """Per-block eigenbasis projections of these Jacobians for ONE decomposition (identified by the rotation cache all
+        its scaled / shifted copies share).  A different decomposition starts an empty cache."""
+        if self._proj[0] is not basis_key:
+            self._proj = (basis_key, {})
+        return self._proj[1]
 
 
 class B200KronDecomposed(KronDecomposed):
@@ -544,37 +553,49 @@ class B200KronDecomposed(KronDecomposed):
 
     def _structured_isf(self, fac: JacobianFactors) -> torch.Tensor:
         """``f_var[n,c,k] = sum_blocks sum_ij Zc[i,j] Zk[i,j] / spec[i,j]`` with the per-layer rank structure:
-        for ``J = g (x) a``: ``sum_i gt_c[i] gt_k[i] m[i]``, ``gt = Q1^T g``, ``m = (Q2^T a)^2 @ (1/spec)^T``."""
+        for ``J = g (x) a``: ``sum_i gt_c[i] gt_k[i] m[i]``, ``gt = Q1^T g``, ``m = (Q2^T a)^2 @ (1/spec)^T``.
+
+        The eigenbasis projections (``gt``, ``(Q2^T a)^2``, rotated dense blocks) depend on the Jacobian and on ``Q`` only,
+        not on ``deltas`` or the eigenvalue scaling: they are cached on ``fac`` (keyed by this decomposition's shared
+        rotation cache), so a sweep over prior precisions on the same validation batch -- ``optimize_prior_precision``'s
+        grid search, baselaplace.py:516-561 -- pays for them once."""
         Nn, C = fac.n_batch, fac.n_out
         dev = self.eigenvectors[0][0].device
         out = torch.zeros(Nn, C, C, device=dev, dtype=torch.float32)
+        proj = fac.projections(self._cache)
         for i, (blk, ls, delta) in enumerate(zip(fac.blocks, self.eigenvalues, self._delta_list())):
             inv_spec = torch.reciprocal(_as_f32(self._spectrum(ls, delta))).contiguous()
             kind = blk[0]
             if kind == "outer" and len(ls) == 2:
-                g, a = blk[1], blk[2]                                    # [C, Nn, d_out], [Nn, d_in]
-                d_out = g.shape[2]
-                gt = self._gemm(g.reshape(C * Nn, d_out), self._Q32(i, 0, True)).view(C, Nn, d_out)
-                at = self._gemm(a, self._Q32(i, 1, True))
-                m = self._gemm(at * at, inv_spec)                        # [Nn, d_out]
-                gtn = gt.permute(1, 0, 2)                                # [Nn, C, d_out] view
+                if i not in proj:
+                    g, a = blk[1], blk[2]                                # [C, Nn, d_out], [Nn, d_in]
+                    d_out = g.shape[2]
+                    gt = self._gemm(g.reshape(C * Nn, d_out), self._Q32(i, 0, True)).view(C, Nn, d_out)
+                    at = self._gemm(a, self._Q32(i, 1, True))
+                    proj[i] = (gt.permute(1, 0, 2), at * at)             # [Nn, C, d_out] view, [Nn, d_in]
+                gtn, at2 = proj[i]
+                m = self._gemm(at2, inv_spec)                            # [Nn, d_out]
                 K.batched_pair_dot(gtn, gtn, m, out, accumulate=True)
             elif kind == "vec" and len(ls) == 1:
-                g = blk[1]
-                d_out = g.shape[2]
-                gt = self._gemm(g.reshape(C * Nn, d_out), self._Q32(i, 0, True)).view(C, Nn, d_out)
-                gtn = gt.permute(1, 0, 2)
+                if i not in proj:
+                    g = blk[1]
+                    d_out = g.shape[2]
+                    gt = self._gemm(g.reshape(C * Nn, d_out), self._Q32(i, 0, True)).view(C, Nn, d_out)
+                    proj[i] = (gt.permute(1, 0, 2),)
+                gtn = proj[i][0]
                 K.batched_pair_dot(gtn, gtn, inv_spec, out, accumulate=True)
             else:
-                J = blk[1] if kind == "dense" else materialize_block(blk, Nn, C)
-                p = J.shape[2]
-                if len(ls) == 1:
-                    Z = self._gemm(J.reshape(Nn * C, p), self._Q32(i, 0, True)).view(Nn, C, p)
-                    K.batched_pair_dot(Z, Z, inv_spec, out, accumulate=True)
-                else:
-                    p1, p2 = ls[0].numel(), ls[1].numel()
-                    Zt = self._rotate_in(i, J.reshape(Nn * C, p1, p2)).reshape(Nn, C, p)
-                    K.batched_pair_dot(Zt, Zt, inv_spec.t().contiguous().reshape(-1), out, accumulate=True)
+                if i not in proj:
+                    J = blk[1] if kind == "dense" else materialize_block(blk, Nn, C)
+                    p = J.shape[2]
+                    if len(ls) == 1:
+                        proj[i] = (self._gemm(J.reshape(Nn * C, p), self._Q32(i, 0, True)).view(Nn, C, p),)
+                    else:
+                        p1, p2 = ls[0].numel(), ls[1].numel()
+                        proj[i] = (self._rotate_in(i, J.reshape(Nn * C, p1, p2)).reshape(Nn, C, p),)
+                Z = proj[i][0]
+                w = inv_spec if len(ls) == 1 else inv_spec.t().contiguous().reshape(-1)
+                K.batched_pair_dot(Z, Z, w, out, accumulate=True)
         return out
 
     # -- cold-path helpers (utils/matrix.py:490-556) ---------------------------------------------

@@ -123,3 +123,29 @@ def probit_predictive(f_mu, f_var):
     """``_glm_forward_call`` probit link (baselaplace.py:662-664)."""
     kappa = 1.0 / torch.sqrt(1.0 + math.pi / 8.0 * torch.diagonal(f_var, dim1=1, dim2=2))
     return torch.softmax(kappa * f_mu, dim=-1)
+
+
+def gridsearch_prior_precision(eigvecs, eigvals, Js_batches, f_batches, y_batches, interval, H_factor: float = 1.0,
+                               running_metric: bool = False):
+    """CPU restatement of ``BaseLaplace._gridsearch`` (baselaplace.py:516-561) + ``utils.validate``
+    (utils/utils.py:39-101) for a Kron posterior, classification, probit GLM predictive, ``RunningNLLMetric``
+    (utils/metrics.py): per grid value the NLL of the probit predictive over all validation batches.  With
+    ``running_metric`` the metric is never reset between grid values, exactly like the reference's loop.
+    Returns ``(best, losses)``."""
+    ls = scale_eigenvalues(eigvals, H_factor)
+    losses, tot, cnt = [], 0.0, 0
+    for pp in interval:
+        delta = torch.as_tensor(pp, dtype=torch.float64)
+        s, n = 0.0, 0
+        for Js, f, y in zip(Js_batches, f_batches, y_batches):
+            fv = kron_inv_square_form(eigvecs, ls, delta, Js)
+            probs = probit_predictive(f, fv)
+            s += float(torch.nn.functional.nll_loss(probs.log(), y, reduction="sum"))
+            n += len(y)
+        if running_metric:
+            tot, cnt = tot + s, cnt + n
+            losses.append(tot / cnt)
+        else:
+            losses.append(s / n)
+    losses = torch.tensor(losses, dtype=torch.float64)
+    return interval[int(torch.argmin(losses))], losses

@@ -161,3 +161,76 @@ def test_kron_laplace_with_fused_conv_chains(cpu_kernels, laplace_mod, monkeypat
     assert worst < 1e-4, worst
     probs = la(X[:5], pred_type="glm", link_approx="probit")
     assert probs.shape == (5, 3) and torch.allclose(probs.sum(-1), torch.ones(5), atol=1e-5)
+
+
+def _small_problem(seed=0):
+    torch.manual_seed(seed)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+    X, y = torch.randn(64, 5), torch.randint(3, (64,))
+    Xv, yv = torch.randn(40, 5), torch.randint(3, (40,))
+    return model, X, y, Xv, yv
+
+
+def test_prior_precision_gridsearch_on_cached_projections(cpu_kernels, laplace_mod):
+    """the reference's grid search (baselaplace.py:516-561) re-derives Jacobians for each grid value; inside
+    ``backend.cached_jacobians()`` -- and in ``laplace_b200.tuning`` -- every validation batch pays once.  Same winner,
+    same loss curve as the fp64 restatement of the reference loop (running, never-reset metric included)."""
+    from laplace_b200 import B200GGN
+    from laplace_b200.tuning import gridsearch_prior_precision
+    from oracle import curvature_oracle as co
+    from oracle import kron_oracle as ko
+
+    model, X, y, Xv, yv = _small_problem()
+    la = laplace_mod.Laplace(model, "classification", "all", "kron", backend=B200GGN)
+    la.fit(DataLoader(TensorDataset(X, y), batch_size=16))
+    vl = DataLoader(TensorDataset(Xv, yv), batch_size=20)
+    calls = {"n": 0}
+    orig = la.backend._jacobians_impl
+    la.backend._jacobians_impl = lambda x: (calls.__setitem__("n", calls["n"] + 1), orig(x))[1]
+    G = 12
+    with pytest.warns(UserWarning):
+        la.optimize_prior_precision(pred_type="glm", method="gridsearch", val_loader=vl, grid_size=G)
+    ref_pp, n_ref = la.prior_precision.clone(), calls["n"]
+    calls["n"] = 0
+    with la.backend.cached_jacobians(), pytest.warns(UserWarning):
+        la.optimize_prior_precision(pred_type="glm", method="gridsearch", val_loader=vl, grid_size=G)
+    assert torch.equal(la.prior_precision, ref_pp) and n_ref == 2 * G and calls["n"] == 2
+    calls["n"] = 0
+    best, losses = gridsearch_prior_precision(la, vl, grid_size=G, running_metric=True)
+    assert calls["n"] == 2 and torch.allclose(best, ref_pp.squeeze())
+    md = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3)).double()
+    md.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    kfs = None
+    for i in range(0, 64, 16):
+        _, kf = co.kfac_factors(md, "classification", X[i:i + 16].double(), y[i:i + 16], N=64)
+        kfs = kf if kfs is None else [[a + b for a, b in zip(Fa, Fb)] for Fa, Fb in zip(kfs, kf)]
+    Qs, ls = ko.decompose(kfs)
+    Jb, fb, yb = [], [], []
+    for i in range(0, 40, 20):
+        J, f = co.jacobians(md, Xv[i:i + 20].double())
+        Jb.append(J), fb.append(f), yb.append(yv[i:i + 20])
+    for running in (True, False):
+        bo, lo = ko.gridsearch_prior_precision(Qs, ls, Jb, fb, yb, torch.logspace(-4, 4, G).double(), running_metric=running)
+        b2, l2 = gridsearch_prior_precision(la, vl, grid_size=G, running_metric=running, set_result=False)
+        assert torch.allclose(l2, lo, atol=1e-5) and torch.allclose(b2.double(), bo)
+
+
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_marglik_training_with_b200_backend(cpu_kernels, laplace_mod, lik):
+    """the reference's ``marglik_training`` (marglik_training.py:34-58, 277-301) takes the backend as a
+    plain class argument; with ``backend=B200GGN`` it fits every ``marglik_frequency`` epochs through our kernels and
+    differentiates the marginal likelihood w.r.t. prior precision AND ``sigma_noise`` through ``B200KronDecomposed``."""
+    from laplace.marglik_training import marglik_training
+
+    from laplace_b200 import B200GGN, B200Kron
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+    X = torch.randn(64, 5)
+    y = torch.randint(3, (64,)) if lik == "classification" else torch.randn(64, 3)
+    la, model, margliks, losses = marglik_training(model, DataLoader(TensorDataset(X, y), batch_size=16), lik, "kron",
+                                                   backend=B200GGN, n_epochs=4, marglik_frequency=2, n_hypersteps=3)
+    assert isinstance(la.H_facs, B200Kron) and len(margliks) == 6 and all(torch.isfinite(torch.tensor(margliks)))
+    assert margliks[-1] < margliks[0]                      # the hyper-steps decrease the negative log marginal likelihood
+    if lik == "regression":
+        assert float(la.sigma_noise) != 1.0                # the gradient w.r.t. sigma_noise reached the optimiser

@@ -161,3 +161,85 @@ def test_kron_laplace_resnet_through_reference_front_end(lap):
     assert worst < FACTOR_TOL, worst
     probs = la(X[:8].to(DEV), pred_type="glm", link_approx="probit")
     assert probs.shape == (8, 10) and torch.allclose(probs.sum(-1), torch.ones(8, device=DEV), atol=1e-5)
+
+
+def test_prior_precision_gridsearch_gpu(lap):
+    """SURVEY 8(f)1 on the device: the reference's own grid search (one Jacobian pass per grid value), the same call inside
+    ``backend.cached_jacobians()`` and ``laplace_b200.tuning.gridsearch_prior_precision`` (one pass per validation batch)
+    pick the same prior precision, and the loss curve matches the fp64 restatement of the reference loop to 1e-5."""
+    from laplace_b200 import B200GGN
+    from laplace_b200.tuning import gridsearch_prior_precision
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(20, 64), torch.nn.ReLU(), torch.nn.Linear(64, 5))
+    X, y = torch.randn(256, 20), torch.randint(5, (256,))
+    Xv, yv = torch.randn(96, 20), torch.randint(5, (96,))
+    md = torch.nn.Sequential(torch.nn.Linear(20, 64), torch.nn.ReLU(), torch.nn.Linear(64, 5)).double()
+    md.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
+    kfs = None
+    for i in range(0, 256, 64):
+        _, kf = co.kfac_factors(md, "classification", X[i:i + 64].double(), y[i:i + 64], N=256)
+        kfs = kf if kfs is None else [[a + b for a, b in zip(Fa, Fb)] for Fa, Fb in zip(kfs, kf)]
+    Qs, ls = ko.decompose(kfs)
+    Jb, fb, yb = [], [], []
+    for i in range(0, 96, 48):
+        J, f = co.jacobians(md, Xv[i:i + 48].double())
+        Jb.append(J), fb.append(f), yb.append(yv[i:i + 48])
+    G = 16
+    la = lap.Laplace(model.to(DEV), "classification", "all", "kron", backend=B200GGN)
+    la.fit(_loader(X, y, 64))
+    vl = _loader(Xv, yv, 48)
+    calls = {"n": 0}
+    orig = la.backend._jacobians_impl
+    la.backend._jacobians_impl = lambda x: (calls.__setitem__("n", calls["n"] + 1), orig(x))[1]
+    with pytest.warns(UserWarning):
+        la.optimize_prior_precision(pred_type="glm", method="gridsearch", val_loader=vl, grid_size=G)
+    ref_pp, n_ref = la.prior_precision.clone(), calls["n"]
+    calls["n"] = 0
+    with la.backend.cached_jacobians(), pytest.warns(UserWarning):
+        la.optimize_prior_precision(pred_type="glm", method="gridsearch", val_loader=vl, grid_size=G)
+    assert torch.equal(la.prior_precision, ref_pp) and n_ref == 2 * G and calls["n"] == 2
+    for running in (True, False):
+        bo, lo = ko.gridsearch_prior_precision(Qs, ls, Jb, fb, yb, torch.logspace(-4, 4, G).double(), running_metric=running)
+        b2, l2 = gridsearch_prior_precision(la, vl, grid_size=G, running_metric=running, set_result=False)
+        assert torch.allclose(l2, lo, atol=1e-5, rtol=1e-5), (l2 - lo).abs().max()
+        assert torch.allclose(b2.double().cpu(), bo)
+    assert torch.allclose(ref_pp.cpu().double().squeeze(), ko.gridsearch_prior_precision(
+        Qs, ls, Jb, fb, yb, torch.logspace(-4, 4, G).double(), running_metric=True)[0])
+    # method="marglik": Adam on the device-side, differentiable log marginal likelihood (baselaplace.py:430-484)
+    la.optimize_prior_precision(pred_type="glm", method="marglik", n_steps=20, prior_structure="layerwise")
+    assert la.prior_precision.shape == (la.n_layers,) and torch.isfinite(la.prior_precision).all()
+
+
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_marglik_training_gpu(lap, lik):
+    """the reference's ``marglik_training`` loop with ``backend=B200GGN`` on the device."""
+    from laplace.marglik_training import marglik_training
+
+    from laplace_b200 import B200GGN, B200Kron
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(5, 32), torch.nn.Tanh(), torch.nn.Linear(32, 3)).to(DEV)
+    X = torch.randn(128, 5)
+    y = torch.randint(3, (128,)) if lik == "classification" else torch.randn(128, 3)
+    la, model, margliks, losses = marglik_training(model, _loader(X, y, 32), lik, "kron", backend=B200GGN, n_epochs=4,
+                                                   marglik_frequency=2, n_hypersteps=3)
+    assert isinstance(la.H_facs, B200Kron) and la.H_facs.kfacs[0][0].is_cuda
+    assert len(margliks) == 6 and margliks[-1] < margliks[0]
+    if lik == "regression":
+        assert float(la.sigma_noise) != 1.0
+    # the marginal likelihood the loop optimised equals the fp64 restatement at the trained weights
+    md = torch.nn.Sequential(torch.nn.Linear(5, 32), torch.nn.Tanh(), torch.nn.Linear(32, 3)).double()
+    md.load_state_dict({k: v.detach().cpu().double() for k, v in model.state_dict().items()})
+    yd = y if lik == "classification" else y.double()
+    kfs = None
+    for i in range(0, 128, 32):
+        _, kf = co.kfac_factors(md, lik, X[i:i + 32].double(), yd[i:i + 32], N=128)
+        kfs = kf if kfs is None else [[a + b for a, b in zip(Fa, Fb)] for Fa, Fb in zip(kfs, kf)]
+    for F, Fo in zip(la.H_facs.kfacs, kfs):
+        for H, Ho in zip(F, Fo):
+            assert rel_fro(H.cpu(), Ho) < FACTOR_TOL
+    _, ls = ko.decompose(kfs)
+    h = 1.0 / float(la.sigma_noise) ** 2 / float(la.temperature)
+    ld_ref = ko.kron_logdet(ko.scale_eigenvalues(ls, h), la.prior_precision.detach().cpu().double())
+    assert torch.allclose(la.log_det_posterior_precision.detach().cpu().double(), ld_ref, rtol=1e-5)
