@@ -182,6 +182,16 @@ int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const floa
                                int T, int Nn, int ncols, float scale, float* out, int64_t out_ld, int64_t js_stride_n,
                                int64_t js_stride_c, void* stream);
 
+/* Kron GLM-predictive quadratic form of a weight-sharing layer without the dense Jacobian (replaces the per-(n,c) dense
+ * rotations of KronDecomposed._bmm / inv_square_form, utils/matrix.py:406-461, for convolution / token-shared layers):
+ *   out[n,c,k] += sum_ij w(i,j) Z_c[i,j] Z_k[i,j],  Z_c[i,j] = sum_t Gt[i, c*g_stride_c + n*T + t] * At[j, n*T + t],
+ *   w = 1/(l1[i]*l2[j] + delta)  (damping != 0: 1/((l1[i]+sqrt(delta))*(l2[j]+sqrt(delta)))).
+ * Gt [d_out, ldg], At [d_in, lda]: eigenbasis-rotated output-gradient / unfolded-input rows, K-major fp32; out [Nn, C, C]
+ * (accumulated into; C <= 12).                                                                                      */
+int lpb_kron_conv_quadform(const float* Gt, int64_t ldg, int64_t g_stride_c, const float* At, int64_t lda, int d_out, int d_in,
+                           int T, int Nn, int C, const float* l1, const float* l2, float delta, int damping, float* out,
+                           void* stream);
+
 /* ---- Jacobian writers (reference CurvatureInterface.jacobians / last_layer_jacobians) ----- */
 /* no weight sharing: Js[n,c, off_w + i*d_in + j] = g[c,n,i]*a[n,j]; Js[n,c, off_b + i] = g[c,n,i]
  * (off_w / off_b < 0: skip that block).  g [C, Nn, d_out], a [Nn, d_in].                      */

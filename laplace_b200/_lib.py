@@ -46,6 +46,8 @@ SIGNATURES = {
                          c_int, c_f32, c_vp, c_i64, c_int, c_vp],
     "lpb_shared_weight_contract": [c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp,
                                    c_i64, c_i64, c_i64, c_vp],
+    "lpb_kron_conv_quadform": [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_f32, c_int, c_vp,
+                               c_vp],
     "lpb_jac_linear_write": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
     "lpb_ll_jacobian_write": [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp],
     "lpb_batched_pair_dot": [c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_int, c_vp,

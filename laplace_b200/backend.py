@@ -212,6 +212,7 @@ class _B200Mixin:
         if f.ndim != 2:
             raise ValueError(f"the B200 backend supports (batch, outputs) model outputs, got shape {tuple(f.shape)}")
         self._device_check(f)
+        self._n_outputs = int(f.shape[1])
         if self.conv_engine and f.is_cuda:
             # the engine's forward uses fp16 hi/lo operands: an activation beyond +-65504 would surface here
             torch._assert_async(torch.isfinite(f).all())
@@ -613,6 +614,57 @@ class _B200Mixin:
             factors = JacobianFactors(fixed, M, ncols, sizes)
         return Z, fd, factors
 
+    # ------------------------------------------------------------------ Jacobian factors without the dense tensor
+    def _factor_blocks(self, x, cols_fn):
+        """Per-parameter-block structure of ``d f / d theta`` for a batch WITHOUT forming the dense ``(M, C, P)`` tensor
+        (447 MB per sample for ResNet-18): ``("outer", g, a)`` / ``("vec", g)`` for layers without weight sharing,
+        ``("conv", G_rows, A_rows, T)`` for convolutions / token-shared linears -- ``J_{n,c} = G_{n,c}^T A_n`` with
+        ``G_rows [(c,n,t), d_out]`` the output-gradient rows and ``A_rows [(n,t), d_in]`` the unfolded input rows
+        (SURVEY App. A).  Returns ``(f, JacobianFactors)``."""
+        self._require_supported("jacobians()")
+        f = self._forward(x)
+        fd = f.detach()
+        M, C = fd.shape
+        cols = cols_fn(fd, None)
+        ncols = cols.shape[0]
+        acts = self._acts
+        grads = self._backward(f, cols)
+        self._acts = {}
+        blocks, sizes = [], []
+        for L, g in zip(self._layers, grads):
+            a = acts[L.name]
+            a = a.float() if a.dtype != torch.float32 else a
+            shared = L.is_conv or a.dim() > 2
+            if not shared:
+                g = g.contiguous()
+                if L.has_w:
+                    blocks.append(("outer", g, a.contiguous()))
+                    sizes.append(L.d_out * L.d_in)
+                if L.has_b:
+                    blocks.append(("vec", g))
+                    sizes.append(L.d_out)
+                continue
+            if L.is_conv:
+                T = g.shape[3] * g.shape[4]
+                Grows = g.permute(0, 1, 3, 4, 2).reshape(ncols * M * T, L.d_out).contiguous()
+                gb = g.reshape(ncols, M, L.d_out, -1).sum(-1).contiguous() if L.has_b else None
+            else:
+                T = a.numel() // (M * L.d_in)
+                Grows = g.reshape(ncols * M * T, L.d_out).contiguous()
+                gb = g.reshape(ncols, M, -1, L.d_out).sum(2).contiguous() if L.has_b else None
+            if L.has_w:
+                if L.is_conv:
+                    P = K.pack_conv_rows(a, L.mod, K.F32)
+                    Arows = P.hi if P.hi.shape[1] == L.d_in else P.hi[:, :L.d_in].contiguous()   # drop the row padding
+                else:
+                    Arows = a.reshape(M * T, L.d_in).contiguous()
+                blocks.append(("conv", Grows, Arows, T))
+                sizes.append(L.d_out * L.d_in)
+            if L.has_b:
+                blocks.append(("vec", gb))
+                sizes.append(L.d_out)
+        return fd, JacobianFactors(blocks, M, ncols, sizes)
+
     def _identity_cols(self, f, y=None):
         M, C = f.shape
         return torch.eye(C, device=f.device, dtype=f.dtype).unsqueeze(1).expand(C, M, C).contiguous()
@@ -667,6 +719,12 @@ class _B200Mixin:
         return out
 
     def _jacobians_impl(self, x):
+        dtype = next(self.model.parameters()).dtype
+        if self.subnetwork_indices is None and dtype == torch.float32 and self._lazy_jacobian(x):
+            from .predictive import LazyJacobian
+
+            f, factors = self._factor_blocks(x, self._identity_cols)
+            return LazyJacobian.wrap(factors, f.device), f
         Z, f, factors = self._rows(x, self._identity_cols, n_major=True, want_factors=self.subnetwork_indices is None)
         dtype = next(self.model.parameters()).dtype
         Js = Z.to(dtype)
@@ -677,6 +735,21 @@ class _B200Mixin:
         return Js, f.to(dtype)
 
     functorch_jacobians = jacobians
+
+    # dense (B, C, P) Jacobians above this many bytes are returned as a ``LazyJacobian`` (factors only; materialised on
+    # demand by any operation that is not one of the structured predictive contractions)
+    LAZY_JACOBIAN_BYTES = 1 << 30
+
+    def _lazy_jacobian(self, x) -> bool:
+        if getattr(self, "lazy_jacobians", None) is not None:
+            return bool(self.lazy_jacobians)
+        xb = x[self.dict_key_x] if isinstance(x, MutableMapping) else x
+        M = int(xb.shape[0])
+        P = sum(p.numel() for p in self.params)
+        C = getattr(self.model, "output_size", None) or getattr(self, "_n_outputs", None)   # baselaplace.py:956-962
+        if C is None:
+            return False
+        return 4 * M * int(C) * P > self.LAZY_JACOBIAN_BYTES
 
     def last_layer_jacobians(self, x, enable_backprop: bool = False):
         """``CurvatureInterface.last_layer_jacobians`` (curvature/curvature.py:131-167)."""

@@ -58,6 +58,8 @@ int batched_pair_dot(const float*, const float*, const float*, int64_t, int, int
 int ll_ggn_expand(const float*, int, int, int, int, float*, cudaStream_t);
 int ll_sigma_gather(const float*, int, int, int, float*, cudaStream_t);
 int eigh_jacobi(const float*, int, int, float*, float*, int, cudaStream_t);
+int kron_conv_quadform(const float*, int64_t, int64_t, const float*, int64_t, int, int, int, int, int, const float*, const float*,
+                       float, int, float*, cudaStream_t);
 
 void set_gemm_pair_mode(int mode);
 int syrk_conv_patches(const void*, const void*, int64_t, int64_t, int, int, int, int, int, int, int, float, int, float*, int64_t,
@@ -280,6 +282,14 @@ int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const floa
   LPB_REQUIRE(T > 0 && ldg >= (int64_t)Nn * ncols * T && lda >= (int64_t)Nn * T, "lpb_shared_weight_contract: bad extents");
   return lpb::shared_weight_contract(mode, G, ldg, A, lda, d_out, d_in, T, Nn, ncols, scale, out, out_ld, js_stride_n,
                                      js_stride_c, ST(stream));
+}
+
+int lpb_kron_conv_quadform(const float* Gt, int64_t ldg, int64_t g_stride_c, const float* At, int64_t lda, int d_out, int d_in,
+                           int T, int Nn, int C, const float* l1, const float* l2, float delta, int damping, float* out,
+                           void* stream) {
+  LPB_REQUIRE(T > 0 && lda >= (int64_t)Nn * T && g_stride_c >= (int64_t)Nn * T && ldg >= (int64_t)(C - 1) * g_stride_c + (int64_t)Nn * T,
+              "lpb_kron_conv_quadform: bad extents");
+  return lpb::kron_conv_quadform(Gt, ldg, g_stride_c, At, lda, d_out, d_in, T, Nn, C, l1, l2, delta, damping, out, ST(stream));
 }
 
 int lpb_jac_linear_write(const float* g, const float* a, int Nn, int C, int d_out, int d_in, float* Js,

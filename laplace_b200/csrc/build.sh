@@ -7,7 +7,7 @@ mkdir -p "${OUT}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --use_fast_math=false)
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC)
-SRCS=(api.cu pack.cu gemm_simt.cu gemm_tc.cu gemm_tc2.cu gemm_tc3.cu conv_tc.cu misc.cu eigh.cu elementwise.cu)
+SRCS=(api.cu pack.cu gemm_simt.cu gemm_tc.cu gemm_tc2.cu gemm_tc3.cu conv_tc.cu misc.cu eigh.cu elementwise.cu kronquad.cu)
 OBJS=()
 pids=()
 for s in "${SRCS[@]}"; do

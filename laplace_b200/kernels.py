@@ -181,6 +181,25 @@ def shared_weight_contract(mode: int, G: Packed, A: Packed, d_out: int, d_in: in
     _bump()
 
 
+def kron_conv_quadform(Gt: torch.Tensor, At: torch.Tensor, T: int, Nn: int, C: int, l1: torch.Tensor, l2: torch.Tensor,
+                       delta: float, damping: bool, out: torch.Tensor) -> torch.Tensor:
+    """``out[n,c,k] += sum_ij w(i,j) Z_c[i,j] Z_k[i,j]`` with ``Z_c = sum_t Gt[:, (c,n,t)] At[:, (n,t)]^T`` formed tile by
+    tile in shared memory (``lpb_kron_conv_quadform``).  ``Gt [d_out, C*Nn*T]``, ``At [d_in, Nn*T]`` K-major fp32
+    (eigenbasis-rotated rows), ``l1 [d_out]``, ``l2 [d_in]`` eigenvalues, ``out [Nn, C, C]``."""
+    _check(Gt, name="Gt"), _check(At, name="At"), _check(out, name="out"), _check(l1, name="l1"), _check(l2, name="l2")
+    assert Gt.dim() == 2 and At.dim() == 2 and Gt.stride(1) == 1 and At.stride(1) == 1 and out.is_contiguous()
+    d_out, d_in = Gt.shape[0], At.shape[0]
+    assert Gt.shape[1] >= C * Nn * T and At.shape[1] >= Nn * T and out.shape == (Nn, C, C)
+    assert l1.numel() == d_out and l2.numel() == d_in and l1.is_contiguous() and l2.is_contiguous()
+    for n0 in range(0, Nn, 65535):      # gridDim.z
+        nn = min(65535, Nn - n0)
+        _lib.call("lpb_kron_conv_quadform", Gt.data_ptr() + 4 * n0 * T, Gt.stride(0), Nn * T, At.data_ptr() + 4 * n0 * T,
+                  At.stride(0), d_out, d_in, T, nn, C, _ptr(l1), _ptr(l2), float(delta), 1 if damping else 0,
+                  out.data_ptr() + 4 * n0 * C * C, _stream())
+        _bump()
+    return out
+
+
 def jac_linear_write(g: torch.Tensor, a: torch.Tensor, Js_view: torch.Tensor, stride_n: int, stride_c: int, off_w: int,
                      off_b: int) -> None:
     """``g [C, Nn, d_out]``, ``a [Nn, d_in]`` contiguous; ``Js_view`` = base pointer tensor of the Jacobian rows."""

@@ -576,6 +576,15 @@ class B200KronDecomposed(KronDecomposed):
                 gtn, at2 = proj[i]
                 m = self._gemm(at2, inv_spec)                            # [Nn, d_out]
                 K.batched_pair_dot(gtn, gtn, m, out, accumulate=True)
+            elif kind == "conv" and len(ls) == 2 and C <= 12:
+                if i not in proj:
+                    Grows, Arows, T = blk[1], blk[2], blk[3]            # [(c,n,t), d_out], [(n,t), d_in]
+                    Gt = self._gemm(self._Q32(i, 0, True), Grows)        # Q1^T G^T -> [d_out, C*Nn*T] (K-major)
+                    At = self._gemm(self._Q32(i, 1, True), Arows)        # Q2^T A^T -> [d_in, Nn*T]
+                    proj[i] = (Gt, At, T)
+                Gt, At, T = proj[i]
+                K.kron_conv_quadform(Gt, At, T, Nn, C, _as_f32(ls[0]).contiguous(), _as_f32(ls[1]).contiguous(),
+                                     float(delta), self.damping, out)
             elif kind == "vec" and len(ls) == 1:
                 if i not in proj:
                     g = blk[1]
@@ -587,6 +596,8 @@ class B200KronDecomposed(KronDecomposed):
             else:
                 if i not in proj:
                     J = blk[1] if kind == "dense" else materialize_block(blk, Nn, C)
+                    if J.dim() == 2:
+                        J = J.unsqueeze(2)
                     p = J.shape[2]
                     if len(ls) == 1:
                         proj[i] = (self._gemm(J.reshape(Nn * C, p), self._Q32(i, 0, True)).view(Nn, C, p),)
@@ -621,8 +632,19 @@ class B200KronDecomposed(KronDecomposed):
 def materialize_block(blk, Nn: int, C: int) -> torch.Tensor:
     """Dense ``[Nn, C, p]`` rows of an ``outer`` / ``vec`` block (only reached when a block's factor structure
     and the decomposed block's structure disagree)."""
+    if blk[0] == "dense":
+        return blk[1]
     if blk[0] == "vec":
         return blk[1].permute(1, 0, 2).contiguous()
+    if blk[0] == "conv":
+        # J_{n,c} = G_{n,c}^T A_n through the per-sample contraction kernel (needs K-major operands)
+        Grows, Arows, T = blk[1], blk[2], blk[3]
+        d_out, d_in = Grows.shape[1], Arows.shape[1]
+        Gk = K.Packed(Grows.t().contiguous(), None, K.F32, d_out, Grows.shape[0])
+        Ak = K.Packed(Arows.t().contiguous(), None, K.F32, d_in, Arows.shape[0])
+        J = torch.empty(Nn, C, d_out * d_in, device=Grows.device, dtype=torch.float32)
+        K.shared_weight_contract(1, Gk, Ak, d_out, d_in, T, Nn, C, J, js_stride_n=C * d_out * d_in, js_stride_c=d_out * d_in)
+        return J
     g, a = blk[1], blk[2]
     d_out, d_in = g.shape[2], a.shape[1]
     J = torch.empty(Nn, C, d_out * d_in, device=g.device, dtype=torch.float32)

@@ -80,3 +80,57 @@ class StructuredJacobian(torch.Tensor):
                     return ll_diag_variance(phi, C, has_bias, Mid).to(J1.dtype)
         with torch._C.DisableTorchFunctionSubclass():
             return func(*args, **kwargs)
+
+
+class LazyJacobian(torch.Tensor):
+    """``(B, C, P)`` Jacobian that exists only as its per-layer factors (``laplace_b200.matrix.JacobianFactors``).
+
+    ``B200GGN.jacobians`` returns it when the dense tensor would exceed ``B200GGN.LAZY_JACOBIAN_BYTES`` (ResNet-18: 447 MB per
+    sample).  ``KronLaplace.functional_variance(Js)`` = ``posterior_precision.inv_square_form(Js)`` (baselaplace.py:1834-1835)
+    reads the factors and never touches the data; shape / dtype / device queries answer from the metadata; ANY other
+    operation first materialises the dense tensor (``dense()``) and proceeds on it, so the object is always correct to
+    use -- just as memory-hungry as the reference's Jacobian when used outside the structured path."""
+
+    @staticmethod
+    def wrap(factors, device) -> "LazyJacobian":
+        P = sum(factors.sizes)
+        base = torch.zeros(1, device=device, dtype=torch.float32).expand(factors.n_batch, factors.n_out, P)   # no storage
+        t = torch.Tensor._make_subclass(LazyJacobian, base)
+        t._lpb_factors = factors
+        t._lpb_dense = None
+        return t
+
+    def dense(self) -> torch.Tensor:
+        if self._lpb_dense is None:
+            from .matrix import materialize_block
+
+            fac = self._lpb_factors
+            parts = [materialize_block(blk, fac.n_batch, fac.n_out) for blk in fac.blocks]
+            self._lpb_dense = torch.cat(parts, dim=2)
+        return self._lpb_dense
+
+    _PASSIVE = {"__get__", "size", "dim", "numel", "stride", "is_contiguous", "__repr__", "__str__", "__format__", "data_ptr",
+                "is_floating_point", "element_size", "_is_view", "untyped_storage"}
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = getattr(func, "__name__", "")
+        if name in cls._PASSIVE:
+            if name in ("__repr__", "__str__", "__format__"):
+                lz = next(a for a in args if isinstance(a, LazyJacobian))
+                return f"LazyJacobian(shape={tuple(lz.shape)}, device={lz.device}, blocks={len(lz._lpb_factors.blocks)})"
+            with torch._C.DisableTorchFunctionSubclass():
+                return func(*args, **kwargs)
+        if name == "detach" and len(args) == 1:
+            return args[0]
+
+        def unwrap(o):
+            if isinstance(o, LazyJacobian):
+                return o.dense()
+            if isinstance(o, (tuple, list)):
+                return type(o)(unwrap(v) for v in o)
+            return o
+
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*unwrap(args), **{k: unwrap(v) for k, v in kwargs.items()})

@@ -161,13 +161,28 @@ def eigh_jacobi(A, max_sweeps=30):
     return torch.nan_to_num(L.clamp(min=0)).float(), torch.nan_to_num(Q).float()
 
 
+def kron_conv_quadform(Gt, At, T, Nn, C, l1, l2, delta, damping, out):
+    d_out, d_in = Gt.shape[0], At.shape[0]
+    G = Gt[:, :C * Nn * T].reshape(d_out, C, Nn, T).double()
+    A = At[:, :Nn * T].reshape(d_in, Nn, T).double()
+    Z = torch.einsum("icnt,jnt->ncij", G, A)
+    if damping:
+        sd = float(delta) ** 0.5
+        w = 1.0 / torch.outer(l1.double() + sd, l2.double() + sd)
+    else:
+        w = 1.0 / (torch.outer(l1.double(), l2.double()) + float(delta))
+    out += torch.einsum("ncij,nkij,ij->nck", Z, Z, w).to(out.dtype)
+    return out
+
+
 def install(monkeypatch):
     """Replace the native wrappers by the emulation and lift the CUDA-only guards (tests only)."""
     from laplace_b200 import backend
 
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
-                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "diag_conv_sq", "conv_bwd_strided", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd"):
+                 "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "diag_conv_sq", "conv_bwd_strided", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd",
+                 "kron_conv_quadform"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)

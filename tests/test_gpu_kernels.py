@@ -141,6 +141,26 @@ def test_shared_weight_contract(mode, dims):
         assert rel_fro(out.cpu(), ref) < 1e-5
 
 
+@pytest.mark.parametrize("dims", [(4, 12, 4, 5, 2), (70, 100, 17, 3, 3), (64, 64, 64, 2, 10), (130, 27, 1, 6, 10), (200, 330, 5, 4, 12),
+                                  (512, 640, 1, 3, 10)])
+@pytest.mark.parametrize("damping", [False, True])
+def test_kron_conv_quadform(dims, damping):
+    """Fused eigenbasis quadratic form of a weight-sharing layer vs an fp64 einsum on the same rotated rows (ragged tile
+    edges, T below / above the 16-deep staging, C = 2..12, plain and damped spectrum)."""
+    d_out, d_in, T, Nn, C = dims
+    torch.manual_seed(8)
+    Gt, At = torch.randn(d_out, C * Nn * T), torch.randn(d_in, Nn * T)
+    l1, l2 = torch.rand(d_out) * 2, torch.rand(d_in) * 3
+    l1[:2] = 0
+    delta = 0.37
+    ref = torch.zeros(Nn, C, C, dtype=torch.float64)
+    ck.kron_conv_quadform(Gt, At, T, Nn, C, l1, l2, delta, damping, ref)
+    out = torch.full((Nn, C, C), 0.5, device=DEV)
+    K.kron_conv_quadform(Gt.to(DEV), At.to(DEV), T, Nn, C, l1.to(DEV), l2.to(DEV), delta, damping, out)
+    assert rel_fro(out.cpu().double() - 0.5, ref) < 2e-6
+    assert rel_fro(out, out.transpose(1, 2)) < 1e-7
+
+
 def test_jacobian_writers_and_pair_dot():
     torch.manual_seed(6)
     C, Nn, d_out, d_in = 3, 5, 7, 11

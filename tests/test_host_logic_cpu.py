@@ -311,3 +311,32 @@ def test_compact_and_bordered_eigendecompositions(cpu_kernels, monkeypatch):
     assert torch.allclose(Lp.double(), Lr, rtol=1e-4, atol=1e-4 * float(Lr.max()))
     assert torch.allclose(Wp.t() @ Wp, torch.eye(400), atol=1e-4)
     assert rel_fro(Wp @ torch.diag(Lp) @ Wp.t(), G) < 1e-5
+
+
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_lazy_jacobian_kron_predictive_matches_dense(golden, cpu_kernels, lik):
+    """Conv-layer Kron GLM predictive without the dense ``(B, C, P)`` Jacobian: the ``LazyJacobian`` carries
+    ``("conv", G_rows, A_rows, T)`` factors; ``inv_square_form`` rotates the ROWS into the eigenbasis and reduces per tile.
+    Same variances as the dense route and as the oracle; any other use of the tensor materialises it correctly."""
+    from laplace_b200.posterior import B200Laplace
+    from laplace_b200.predictive import LazyJacobian
+    from torch.utils.data import DataLoader, TensorDataset
+
+    model, X, y, rec = load(golden, "conv", lik, dtype=torch.float32)
+    la = B200Laplace(model, lik, "all", "kron", prior_precision=0.7).fit(DataLoader(TensorDataset(X, y), batch_size=5))
+    Jd, f = la.backend.jacobians(X)
+    assert not isinstance(Jd, LazyJacobian)
+    dense_var = la.functional_variance(Jd)
+    la.backend.lazy_jacobians = True
+    Jl, f2 = la.backend.jacobians(X)
+    assert isinstance(Jl, LazyJacobian) and Jl.shape == Jd.shape and Jl.dtype == Jd.dtype
+    assert [b[0] for b in Jl._lpb_factors.blocks] == ["conv", "vec", "outer", "vec", "outer", "vec"]
+    lazy_var = la.functional_variance(Jl)
+    assert Jl._lpb_dense is None, "the structured path must not materialise the Jacobian"
+    assert torch.allclose(lazy_var, dense_var, rtol=1e-4, atol=1e-7)
+    P = la.posterior_precision
+    P.damping = True                                    # damped spectrum through the same kernel
+    assert torch.allclose(P.inv_square_form(Jl), P.inv_square_form(Jd.clone()), rtol=1e-4, atol=1e-7)
+    # any other operation sees the dense values
+    assert torch.allclose(Jl + 0.0, Jd, atol=1e-6) and torch.allclose(Jl.sum(0), Jd.sum(0), atol=1e-5)
+    assert rel_fro(Jl.dense().double(), rec["Js"]) < 1e-6
