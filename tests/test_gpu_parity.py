@@ -124,6 +124,57 @@ def test_kron_posterior_predictive(golden, kind, lik):
     assert var_err(dense, ref) < VAR_TOL, var_err(dense, ref)
 
 
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_mc_fisher_converges_to_the_exact_ggn(golden, lik):
+    """MC functional Fisher (``_get_mc_functional_fisher``, curvature/curvature.py:341-364; KFAC with
+    ``FisherType.MC``, curvature/curvlinops.py:162-164) on the device.  The sampler's stream differs from the reference's
+    by construction, so parity is statistical: the error against the exact GGN falls like 1/sqrt(samples) and is small at
+    4000 samples -- for the Kron factors and for the dense / diagonal GGN (reference test: tests/
+    test_curv_backends_curvlinops.py:158-176)."""
+    model, X, y, rec = load(golden, "mlp", lik)
+    _, exact = co.kfac_factors(model, lik, X, y, N=len(X))
+    model, X, y = _to(model, X, y, torch.float32)
+    be = B200GGN(model, lik, stochastic=True)
+    torch.manual_seed(0)
+    errs = []
+    for s in (10, 4000):
+        _, k = be.kron(X, y, N=len(X), mc_samples=s)
+        errs.append(max(rel_fro(h.cpu(), ho) for F, Fo in zip(k.kfacs, exact) for h, ho in zip(F, Fo)))
+    assert errs[1] < 0.08 and errs[1] < 0.5 * errs[0], errs
+    be_full = B200GGN(model, lik, stochastic=True, num_samples=4000)
+    _, H = be_full.full(X, y)
+    _, d = be_full.diag(X, y)
+    assert rel_fro(H.cpu(), rec["ggn_full"]) < 0.08 and rel_fro(d.cpu(), rec["ggn_diag"]) < 0.08
+
+
+@pytest.mark.parametrize("kind", ["mlp", "conv", "wide_conv"])
+@pytest.mark.parametrize("lazy", [False, True])
+def test_gp_kernels_vs_reference_einsums(golden, kind, lazy):
+    """SURVEY 8(f)3 on the device: ``K = J J^T`` between batches (``FunctionalLaplace._kernel_batch / _kernel_star /
+    _kernel_batch_star``, baselaplace.py:3026-3122) from the Jacobian factors vs the reference einsums in fp64."""
+    from laplace_b200 import gp
+
+    if kind == "wide_conv":
+        torch.manual_seed(9)
+        model = torch.nn.Sequential(torch.nn.Conv2d(8, 16, 3, 1, 1), torch.nn.Tanh(), torch.nn.Conv2d(16, 12, 3, 1, 1), torch.nn.Tanh(),
+                                    torch.nn.Flatten(), torch.nn.Linear(48, 3)).double()
+        X = torch.randn(7, 8, 2, 2, dtype=torch.float64)
+    else:
+        model, X, _, _ = load(golden, kind, "classification")
+    J, _ = co.jacobians(model, X)
+    P, na = J.shape[-1], len(X) // 2
+    be = B200GGN(model.float().to(DEV), "classification")
+    be.lazy_jacobians = lazy
+    J1, _ = be.jacobians(X[:na].float().to(DEV))
+    J2, _ = be.jacobians(X[na:].float().to(DEV))
+    Ja, Jb = J[:na], J[na:]
+    assert rel_fro(gp.kernel_batch(J1, J2).cpu(), torch.einsum("ap,bp->ab", Ja.reshape(-1, P), Jb.reshape(-1, P))) < 1e-5
+    assert rel_fro(gp.kernel_star(J1).cpu(), torch.einsum("bcp,bep->bce", Ja, Ja)) < 1e-5
+    assert rel_fro(gp.kernel_batch_star(J1, J2).cpu(), torch.einsum("bcp,dep->bdce", Ja, Jb)) < 1e-5
+    indep = torch.stack([torch.einsum("bp,ep->be", Ja[:, c], Jb[:, c]) for c in range(J.shape[1])], -1)
+    assert rel_fro(gp.kernel_batch(J1, J2, independent_outputs=True).cpu(), indep) < 1e-5
+
+
 def test_conv_kron_predictive_without_dense_jacobian():
     """all-weights Kron GLM predictive of a (reduced-width) ResNet-18 through the ``LazyJacobian``
     route -- per-layer ``G_{n,c}^T A_n`` formed tile by tile in the Kron eigenbasis, never as a ``(B, C, P)`` tensor --

@@ -340,3 +340,40 @@ def test_lazy_jacobian_kron_predictive_matches_dense(golden, cpu_kernels, lik):
     # any other operation sees the dense values
     assert torch.allclose(Jl + 0.0, Jd, atol=1e-6) and torch.allclose(Jl.sum(0), Jd.sum(0), atol=1e-5)
     assert rel_fro(Jl.dense().double(), rec["Js"]) < 1e-6
+
+
+def _gp_case(kind, golden):
+    if kind == "wide_conv":       # small maps, wide channels: the structured sum over (t, t') is the cheaper route
+        torch.manual_seed(9)
+        model = torch.nn.Sequential(torch.nn.Conv2d(8, 16, 3, 1, 1), torch.nn.Tanh(), torch.nn.Conv2d(16, 12, 3, 1, 1), torch.nn.Tanh(),
+                                    torch.nn.Flatten(), torch.nn.Linear(48, 3)).double()
+        return model, torch.randn(7, 8, 2, 2, dtype=torch.float64)
+    model, X, _, _ = load(golden, kind, "classification")
+    return model, X
+
+
+@pytest.mark.parametrize("kind", ["mlp", "conv", "wide_conv"])
+@pytest.mark.parametrize("lazy", [False, True])
+def test_gp_kernels_match_reference_einsums(golden, cpu_kernels, kind, lazy):
+    """the three kernel tensors of ``FunctionalLaplace`` (baselaplace.py:3026-3122) from the backend's
+    Jacobian factors, against the reference's einsums on the oracle's dense Jacobians."""
+    from laplace_b200 import gp
+
+    model, X = _gp_case(kind, golden)
+    J, _ = co.jacobians(model, X)
+    P = J.shape[-1]
+    na = len(X) // 2
+    be = B200GGN(model.float(), "classification")
+    be.lazy_jacobians = lazy
+    J1, _ = be.jacobians(X[:na].float())
+    J2, _ = be.jacobians(X[na:].float())
+    Ja, Jb = J[:na], J[na:]
+    assert rel_fro(gp.kernel_batch(J1, J2), torch.einsum("ap,bp->ab", Ja.reshape(-1, P), Jb.reshape(-1, P))) < 1e-5
+    assert rel_fro(gp.kernel_batch(J1), torch.einsum("ap,bp->ab", Ja.reshape(-1, P), Ja.reshape(-1, P))) < 1e-5
+    assert rel_fro(gp.kernel_star(J1), torch.einsum("bcp,bep->bce", Ja, Ja)) < 1e-5
+    assert rel_fro(gp.kernel_star(J1, joint=True), torch.einsum("acp,bep->abce", Ja, Ja)) < 1e-5
+    assert rel_fro(gp.kernel_batch_star(J1, J2), torch.einsum("bcp,dep->bdce", Ja, Jb)) < 1e-5
+    indep = torch.stack([torch.einsum("bp,ep->be", Ja[:, c], Jb[:, c]) for c in range(J.shape[1])], -1)
+    assert rel_fro(gp.kernel_batch(J1, J2, independent_outputs=True), indep) < 1e-5
+    assert rel_fro(gp.kernel_star(J1, independent_outputs=True), (Ja ** 2).sum(-1)) < 1e-5
+    model.double()
