@@ -487,6 +487,10 @@ class _B200Mixin:
             if side is not None:
                 main.wait_stream(side)
 
+        if self.conv_engine and self.precision == "auto":
+            from . import conv_engine as _ce0
+
+            _ce0.LEAN_BWD_MIN_ROWS = A_SINGLE_PRODUCT_MIN_ROWS     # reset in the ``finally`` below
         try:
             try:
                 grads = self._backward(f, cols)
@@ -508,6 +512,10 @@ class _B200Mixin:
                 grads = self._backward(f, cols)
         finally:
             join()
+            if self.conv_engine:
+                from . import conv_engine as _ce1
+
+                _ce1.LEAN_BWD_MIN_ROWS = 0
         self._acts = {}
         stash = {}
         if (self.conv_engine and not reduce and self.precision in ("auto", "bf16x3")

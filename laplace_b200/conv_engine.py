@@ -34,6 +34,12 @@ KIND = K.BF16X3       # reverse pass: gradients span many orders of magnitude ->
 KIND_FWD = K.F16X3    # forward pass: activations / weights sit inside fp16 range -> fp16 hi/lo (22 bits); the
                       # ~2e-7 forward error keeps ReLU masks identical to an fp32 forward (a 1e-5 error flips a
                       # few masks per 10^5 units, each flip is a 100 % error on that unit's gradient)
+# > 0: backward-data convolutions over at least this many gradient rows use the bf16 hi half of the gradient alone
+# against the exact (hi + lo) weights -- two tensor-core products instead of three.  The gradient is then rounded to 8
+# bits INDEPENDENTLY per sample row (relative 2^-9, unbiased), which averages out in the factor sums over the rows; the
+# weights, shared by all rows, stay exact.  Set by the backend around the reverse pass of ``kron()`` under
+# precision="auto" (backend.A_SINGLE_PRODUCT_MIN_ROWS); 0 elsewhere (Jacobians / dense / diagonal curvature).
+LEAN_BWD_MIN_ROWS = 0
 USE_IMPLICIT = os.environ.get("LPB_NO_IMPLICIT") != "1"
 USE_STRIDED = os.environ.get("LPB_NO_STRIDED") != "1"     # strided reverse passes as per-parity implicit GEMMs
 
@@ -178,11 +184,12 @@ def _backward_from_rows(G: K.Packed, Q: int, T: int, mod: nn.Conv2d, in_shape, n
     st["G"], st["G_pass"] = G, PASS_ID[0]
     if not need_dx:
         return None
+    Gd = K.hi_only(G) if (0 < LEAN_BWD_MIN_ROWS <= G.rows and G.kind == K.BF16X3) else G
     if implicit_ok(mod, in_shape[2], in_shape[3]):
-        return _implicit_rows(G, Q, in_shape[2], in_shape[3], mod, "bwd_taps", mod.in_channels, -1)
+        return _implicit_rows(Gd, Q, in_shape[2], in_shape[3], mod, "bwd_taps", mod.in_channels, -1)
     if strided_ok(mod, in_shape[2], in_shape[3]):
         OH, OW = K.conv_out_hw(in_shape, mod)
-        return K.conv_bwd_strided(G, Q, OH, OW, _CACHE.get(mod, "bwd_taps"), mod, (Q,) + tuple(in_shape[1:]))
+        return K.conv_bwd_strided(Gd, Q, OH, OW, _CACHE.get(mod, "bwd_taps"), mod, (Q,) + tuple(in_shape[1:]))
     Wt = _CACHE.get(mod, "bwd_taps")                         # [(kh,kw,ci), Co]
     Dc = torch.empty(Q * T, Wt.rows, device=G.hi.device, dtype=torch.float32)
     K.gemm_nt(G, Wt, Dc, 1.0, accumulate=False)              # [(q,t), (kh,kw,ci)]

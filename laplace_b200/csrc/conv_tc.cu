@@ -160,9 +160,11 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
                                const __grid_constant__ ConvTaps taps, const __grid_constant__ ConvOutMap om, int kchunks,
                                int num_stages, int fp16_operands, int bn, int tiles_n, int num_items, int tiles_per_img,
                                int rows_per_tile) {
+  // NPROD 1: A_hi*B_hi; 2: + A_hi*B_lo (rounded activations / gradients, exact weights); 3: + A_lo*B_hi
   const int B_BYTES = bn * BK * 2;
-  const int STAGE_BYTES = (NPROD == 3 ? 2 : 1) * (TILE_BYTES + B_BYTES);
-  const int OFF_B_HI = TILE_BYTES, OFF_A_LO = TILE_BYTES + B_BYTES, OFF_B_LO = 2 * TILE_BYTES + B_BYTES;
+  const int STAGE_BYTES = NPROD == 3 ? 2 * (TILE_BYTES + B_BYTES) : (NPROD == 2 ? TILE_BYTES + 2 * B_BYTES : TILE_BYTES + B_BYTES);
+  const int OFF_B_HI = TILE_BYTES, OFF_A_LO = TILE_BYTES + B_BYTES;
+  const int OFF_B_LO = NPROD == 2 ? TILE_BYTES + B_BYTES : 2 * TILE_BYTES + B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
@@ -207,10 +209,8 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
           const int ch = h0 + taps.dh[ti], cw = taps.dw[ti], wrow = taps.w[ti] * N + tn * bn;
           tma_load_4d(&tmX_hi, &full_bar[stage], st, kc * BK, cw, ch, q0);
           tma_load_2d(&tmW_hi, &full_bar[stage], st + OFF_B_HI, kc * BK, wrow);
-          if (NPROD == 3) {
-            tma_load_4d(&tmX_lo, &full_bar[stage], st + OFF_A_LO, kc * BK, cw, ch, q0);
-            tma_load_2d(&tmW_lo, &full_bar[stage], st + OFF_B_LO, kc * BK, wrow);
-          }
+          if (NPROD == 3) tma_load_4d(&tmX_lo, &full_bar[stage], st + OFF_A_LO, kc * BK, cw, ch, q0);
+          if (NPROD >= 2) tma_load_2d(&tmW_lo, &full_bar[stage], st + OFF_B_LO, kc * BK, wrow);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -237,9 +237,12 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
               const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
               umma_f16(tacc, a_hi + koff, b_hi + koff, idesc, acc);
               acc = 1;
-              if (NPROD == 3) {
-                const uint64_t a_lo = make_smem_desc(sbase + OFF_A_LO), b_lo = make_smem_desc(sbase + OFF_B_LO);
+              if (NPROD >= 2) {
+                const uint64_t b_lo = make_smem_desc(sbase + OFF_B_LO);
                 umma_f16(tacc, a_hi + koff, b_lo + koff, idesc, 1);
+              }
+              if (NPROD == 3) {
+                const uint64_t a_lo = make_smem_desc(sbase + OFF_A_LO);
                 umma_f16(tacc, a_lo + koff, b_hi + koff, idesc, 1);
               }
             }
@@ -345,38 +348,43 @@ static int conv_nhwc_core(const void* X_hi, const void* X_lo, int64_t Q, int H, 
   LPB_REQUIRE(big ? (128 % W == 0 && H % (128 / W) == 0) : (128 % (H * W) == 0),
               "conv_nhwc_bf16: %dx%d images do not tile 128-row blocks", H, W);
   LPB_REQUIRE((ldx % 8) == 0 && (ldw % 8) == 0 && ldx >= Kc && ldw >= Kc, "conv_nhwc_bf16: bad leading dimensions");
-  LPB_REQUIRE((X_lo == nullptr) == (W_lo == nullptr), "conv_nhwc_bf16: lo operands must both be given or both NULL");
+  LPB_REQUIRE(X_lo == nullptr || W_lo != nullptr, "conv_nhwc_bf16: an operand lo half needs the weight lo half");
   LPB_REQUIRE(ldd >= N, "conv_nhwc_bf16: ldd too small");
   const bool x3 = X_lo != nullptr;
+  const bool x2 = !x3 && W_lo != nullptr;   // rounded operand rows (hi only) against exact (hi + lo) weights: two products
   const int q_per_tile = big ? 1 : 128 / (H * W);
   const int rows_per_tile = big ? 128 / W : H, tiles_per_img = big ? H / rows_per_tile : 0;
   CUtensorMap tX_hi, tX_lo, tW_hi, tW_lo;
   const int bn = N <= 64 ? 64 : 128;
   if (make_tmap_nhwc(&tX_hi, X_hi, Q, H, W, Kc, ldx, q_per_tile, rows_per_tile)) return 1;
   if (make_tmap_2d(&tW_hi, W_hi, w_rows, Kc, ldw, bn)) return 1;
-  if (x3) {
-    if (make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile, rows_per_tile)) return 1;
-    if (make_tmap_2d(&tW_lo, W_lo, w_rows, Kc, ldw, bn)) return 1;
-  } else {
-    tX_lo = tX_hi; tW_lo = tW_hi;
-  }
+  tX_lo = tX_hi; tW_lo = tW_hi;
+  if (x3 && make_tmap_nhwc(&tX_lo, X_lo, Q, H, W, Kc, ldx, q_per_tile, rows_per_tile)) return 1;
+  if ((x3 || x2) && make_tmap_2d(&tW_lo, W_lo, w_rows, Kc, ldw, bn)) return 1;
   const int64_t Mrows = Q * H * W;
   const int64_t tiles_m = big ? Q * tiles_per_img : ceil_div(Q, q_per_tile);
   const int tiles_n = (int)ceil_div(N, bn);
   const int kchunks = (int)ceil_div(Kc, tc::BK);
-  const int stage_bytes = (x3 ? 2 : 1) * (tc::TILE_BYTES + bn * tc::BK * 2);
+  const int b_bytes = bn * tc::BK * 2;
+  const int stage_bytes = x3 ? 2 * (tc::TILE_BYTES + b_bytes) : (x2 ? tc::TILE_BYTES + 2 * b_bytes : tc::TILE_BYTES + b_bytes);
   const int64_t items = tiles_m * tiles_n;
   LPB_REQUIRE(items <= 2147483647LL, "conv_nhwc_bf16: too many tiles");
   const int pstages = (int)imin(8, (196 * 1024) / stage_bytes);
   const size_t psmem = (size_t)pstages * stage_bytes + (2 * pstages + 4) * sizeof(uint64_t) + 16 + 1024;
-  static bool pattr1 = false, pattr3 = false;
+  static bool pattr1 = false, pattr2 = false, pattr3 = false;
+  if (x2 && !pattr2) {
+    if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024), "conv_nhwc_bf16 attr"))
+      return 1;
+    pattr2 = true;
+  }
   if (x3 && !pattr3) {
     if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         227 * 1024), "conv_nhwc_bf16 attr"))
       return 1;
     pattr3 = true;
   }
-  if (!x3 && !pattr1) {
+  if (!x3 && !x2 && !pattr1) {
     if (check_cuda(cudaFuncSetAttribute(tc::conv_nhwc_tc_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         227 * 1024), "conv_nhwc_bf16 attr"))
       return 1;
@@ -385,6 +393,10 @@ static int conv_nhwc_core(const void* X_hi, const void* X_lo, int64_t Q, int H, 
   const unsigned pgrid = (unsigned)imin(items, sm_count());
   if (x3)
     tc::conv_nhwc_tc_persistent_kernel<3><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
+        tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, taps, om, kchunks, pstages, fp16_operands, bn, tiles_n,
+        (int)items, tiles_per_img, rows_per_tile);
+  else if (x2)
+    tc::conv_nhwc_tc_persistent_kernel<2><<<pgrid, tc::NUM_THREADS, psmem, st>>>(
         tX_hi, tX_lo, tW_hi, tW_lo, Mrows, N, alpha, D, ldd, q_per_tile, taps, om, kchunks, pstages, fp16_operands, bn, tiles_n,
         (int)items, tiles_per_img, rows_per_tile);
   else

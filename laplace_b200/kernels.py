@@ -372,10 +372,13 @@ def conv_nhwc(X: Packed, Q: int, H: int, W: int, Wt: Packed, N: int, KH: int, KW
     """Implicit-GEMM stride-1 convolution on NHWC bf16(hi/lo) rows ``X [(q,h,w), Kc]`` with tap-major weights
     ``Wt [(tap, n), Kc]``; ``out [(q,h,w), N]`` fp32 is overwritten."""
     _check(out, name="out")
-    assert X.kind in (BF16, BF16X3, F16X3) and X.kind == Wt.kind and X.rows == Q * H * W and Wt.rows == KH * KW * N and X.K == Wt.K
+    # operand rows may be given as their hi half alone against hi/lo weights: two products instead of three
+    lean = X.lo is None and Wt.lo is not None and (X.kind, Wt.kind) in ((BF16, BF16X3), (F16, F16X3))
+    assert X.kind in (BF16, BF16X3, F16X3, F16) and (X.kind == Wt.kind or lean)
+    assert X.rows == Q * H * W and Wt.rows == KH * KW * N and X.K == Wt.K
     assert out.shape == (Q * H * W, N) and out.stride(1) == 1
     _lib.call("lpb_conv_nhwc_tc", _ptr(X.hi), _ptr(X.lo), Q, H, W, X.K, X.ldk, _ptr(Wt.hi), _ptr(Wt.lo), Wt.ldk, N, KH, KW,
-              base_h, base_w, sgn, alpha, _ptr(out), out.stride(0), 1 if X.kind == F16X3 else 0, _stream())
+              base_h, base_w, sgn, alpha, _ptr(out), out.stride(0), 1 if X.kind in FP16_KINDS else 0, _stream())
     _bump()
     return out
 
@@ -386,7 +389,8 @@ def conv_bwd_strided(G: Packed, Q: int, OH: int, OW: int, Wt: Packed, mod, in_sh
     (returned as a channels-last view ``[Q, C_in, H, W]``)."""
     _, Ci, H, W = in_shape
     kh, kw = mod.kernel_size
-    assert G.kind in (BF16, BF16X3) and G.kind == Wt.kind and G.rows == Q * OH * OW and Wt.rows == kh * kw * Ci and G.K == Wt.K
+    lean = G.lo is None and Wt.lo is not None and (G.kind, Wt.kind) == (BF16, BF16X3)
+    assert G.kind in (BF16, BF16X3) and (G.kind == Wt.kind or lean) and G.rows == Q * OH * OW and Wt.rows == kh * kw * Ci and G.K == Wt.K
     out = torch.empty(Q, H, W, Ci, device=G.hi.device, dtype=torch.float32)
     _lib.call("lpb_conv_bwd_strided_tc", _ptr(G.hi), _ptr(G.lo), Q, OH, OW, G.K, G.ldk, _ptr(Wt.hi), _ptr(Wt.lo), Wt.ldk, Ci,
               kh, kw, mod.stride[0], mod.stride[1], mod.padding[0], mod.padding[1], H, W, _ptr(out), out.stride(2), _stream())

@@ -77,6 +77,35 @@ def test_conv_forward_backward_vs_fp64(geom):
     assert rel_fro(gin_cl, gref) < 2e-5
 
 
+@pytest.mark.parametrize("geom", [(64, 64, 3, 1, 1, 1, 8), (128, 64, 3, 1, 1, 1, 4), (64, 128, 3, 2, 1, 1, 16), (256, 256, 3, 1, 1, 1, 2)])
+def test_two_product_backward_data(geom):
+    """``LEAN_BWD_MIN_ROWS`` route (kron() under precision="auto"): the gradient rows enter the backward-data convolution
+    as their bf16 hi half only, the weights stay hi + lo.  The result equals the exact convolution of the ROUNDED gradient
+    (5e-6: weights are not rounded) and deviates from the unrounded one by the bf16 rounding of the rows (~2^-9, unbiased:
+    the mean signed deviation is two orders of magnitude smaller)."""
+    cin, cout, k, s, p, d, hw = geom
+    torch.manual_seed(2)
+    mod = torch.nn.Conv2d(cin, cout, k, s, p, dilation=d, bias=False).to(DEV)
+    oh = (hw + 2 * p - k) // s + 1
+    g = torch.randn(130, cout, oh, oh, device=DEV)
+    shape = (130, cin, hw, hw)
+    gref = torch.nn.grad.conv2d_input(shape, mod.weight.double(), g.double(), s, p, d)
+    ground = torch.nn.grad.conv2d_input(shape, mod.weight.double(), g.bfloat16().double(), s, p, d)
+    keep = conv_engine.LEAN_BWD_MIN_ROWS
+    conv_engine.LEAN_BWD_MIN_ROWS = 1
+    try:
+        conv_engine.PASS_ID[0] += 1
+        gin = conv_engine.conv_backward_data(g, mod, shape)
+    finally:
+        conv_engine.LEAN_BWD_MIN_ROWS = keep
+    assert rel_fro(gin, ground) < 5e-6
+    assert 1e-4 < rel_fro(gin, gref) < 4e-3
+    assert abs(float((gin.double() - gref).mean() / gref.abs().mean())) < 5e-5
+    conv_engine.PASS_ID[0] += 1
+    full = conv_engine.conv_backward_data(g, mod, shape)
+    assert rel_fro(full, gref) < 2e-5
+
+
 def test_store_mode_gemm_nonsymmetric():
     torch.manual_seed(2)
     A, B = torch.randn(576, 64), torch.randn(40000, 64)

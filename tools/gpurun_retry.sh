@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
-# usage: tools/gpurun_retry.sh <timeout> <script> [--gpus N]   -- retries while the pod answers "busy" (exit code 3)
-T=$1; S=$2; shift 2
-for i in $(seq 1 20); do
-  /usr/local/graft/bin/gpurun "$@" --timeout "$T" -- "bash $S"
+# usage: tools/gpurun_retry.sh <log> <timeout> <command...>   -- retries while the pod answers "busy" (exit code 3)
+log="$1"; shift; to="$1"; shift
+for i in $(seq 1 12); do
+  /usr/local/graft/bin/gpurun --timeout "$to" -- "$@" > "$log" 2>&1
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 150
