@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "bf16x3"])
     ap.add_argument("--model", default="resnet18")
+    ap.add_argument("--structure", default="kron", choices=["kron", "diag_ef"],
+                    help="kron: KFAC-GGN (the headline metric, BASELINE configs[1]); diag_ef: diagonal empirical Fisher with a "
+                         "vector all-reduce (BASELINE configs[3], e.g. --model wrn28_10)")
     ap.add_argument("--cpu-samples", type=int, default=256, help="samples of the bounded CPU-baseline run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predictive", action="store_true", help="skip the GLM-predictive legs")
@@ -55,7 +58,8 @@ def parse():
 
 
 def workload_name(args):
-    return f"{args.model} (torchvision topology, random init, frozen norm), 32x32x3 synthetic, C=10, KFAC-GGN all weights"
+    what = "KFAC-GGN all weights" if args.structure == "kron" else "diagonal empirical Fisher all weights"
+    return f"{args.model} (random init, frozen norm), {'x'.join(map(str, input_shape(args.model)[::-1]))} synthetic, C=10, {what}"
 
 
 def make_model(name):
@@ -276,14 +280,15 @@ def run_ours(args):
         return decompose_sharded(H) if world > 1 else H.decompose()
 
     t0 = time.perf_counter()
-    ms_cold, _ = timed(decompose_once)
+    ms_cold, Hd = timed(decompose_once)
+    del Hd
     ms_dec, Hd = timed(decompose_once)
     extras["decompose_ms_first_call_cold"] = round(ms_cold, 1)
     extras["decompose_ms_once_per_fit"] = round(ms_dec, 1)
     extras["decompose_how"] = (f"factors sharded over {world} ranks (greedy n^3 balance), local eigh, one all-gather of Q/lambda"
                                if world > 1 else "single process") + \
         f"; n<=128 hand-written Jacobi kernel, larger: library syevd on {matrix.N_EIGH_THREADS} host threads, dead-coordinate " \
-        f"compaction {'on' if matrix.COMPACT_DEAD_COORDINATES else 'off'}, 385..512 padded to 513 {'on' if matrix.PAD_EIGH else 'off'}"
+        f"compaction {'on' if matrix.COMPACT_DEAD_COORDINATES else 'off'}, {matrix.PAD_EIGH_RANGE[0]}..{matrix.PAD_EIGH_RANGE[1]} padded to 513 (syevd) {'on' if matrix.PAD_EIGH else 'off'}"
     fit_s = N_total / value + ms_dec / 1e3
     extras["fit_50k_samples_per_sec_incl_decompose"] = round(N_total / fit_s, 1)
     del Hd
@@ -415,7 +420,7 @@ def measure_small_batch(be, dev, shape, N_total, B=512, steps=10):
     return {"ms_per_step": round(ms, 3), "samples_per_sec": round(B / (ms / 1e3), 1)}
 
 
-def measure_roofline(be, K, Xs, ys, N_total, args, dev):
+def measure_roofline(be, K, Xs, ys, N_total, args, dev, step_fn=None):
     """Times every native kernel family of two steps with CUDA events on the launching stream and reports the
     roofline of the DOMINANT one (largest share of device time), plus a per-family table under `families`.
 
@@ -463,11 +468,17 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev):
         "relu_bwd": lambda r, a, kw: ("bytes", 8.0 * r.numel() + 4.0 * a[1].numel(), False),
         "maxpool2d_bwd": lambda r, a, kw: ("bytes", 4.0 * (r.numel() + a[0].numel()) + 8.0 * a[1].numel(), False),
         "col2im": lambda r, a, kw: ("bytes", 4.0 * (a[0].shape[0] * a[0].shape[1] + r.numel()), False),
+        # tensor-core diagonal of a convolution weight: per (sample, column) one T-deep [C_out x 9 C_in] product
+        "diag_conv_sq": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[0].K * a[1].K * a[5].kernel_size[0] * a[5].kernel_size[1], True),
+        "shared_weight_contract": lambda r, a, kw: ("flops", 2.0 * a[3] * a[4] * a[5] * a[6] * a[7], False),
     }
     origs = {n: wrap(n, w) for n, w in works.items()}
     try:
         for i in range(2):
-            be.kron(Xs[i % len(Xs)], ys[i % len(ys)], N=N_total)
+            if step_fn is not None:
+                step_fn(i)
+            else:
+                be.kron(Xs[i % len(Xs)], ys[i % len(ys)], N=N_total)
         torch.cuda.synchronize()
     finally:
         for n, o in origs.items():
@@ -625,9 +636,84 @@ def measure_predictive(model, dev, world, timed, args):
     return out
 
 
+def run_diag_ef(args):
+    """BASELINE configs[3]: diagonal empirical Fisher over all weights (e.g. ``--model wrn28_10``), one vector all-reduce at
+    the end.  Same timing contract as the headline run; ``value`` = samples/s of ``B200EF.diag`` steps."""
+    import torch.distributed as dist
+
+    from laplace_b200 import B200EF
+    from laplace_b200 import kernels as K
+
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, Ksteps, W = args.batch, args.steps, max(3, args.warmup)
+    N_total = 50000
+    model = make_model(args.model).to(dev)
+    be = B200EF(model, "classification", precision=args.precision, model_tf32=args.model_tf32)
+    shape = input_shape(args.model)
+    torch.manual_seed(1 + rank)
+    nb = min(4, W + Ksteps)
+    Xs = [torch.randn(B, *shape, device=dev) for _ in range(nb)]
+    ys = [torch.randint(10, (B,), device=dev) for _ in range(nb)]
+    state = {"H": None}
+
+    def step(i):
+        _, d = be.diag(Xs[i % nb], ys[i % nb], N=N_total)
+        state["H"] = d if state["H"] is None else state["H"].add_(d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    for i in range(W):
+        step(i)
+    if world > 1:
+        scratch = torch.zeros_like(state["H"])
+        for _ in range(2):
+            dist.all_reduce(scratch)
+    barrier()
+    l0 = K.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ksteps):
+        step(W + i)
+    if world > 1:
+        dist.all_reduce(state["H"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = K.LAUNCHES - l0
+    clk = clocks.stop() if rank == 0 else None
+    roof = measure_roofline(be, K, Xs, ys, N_total, args, dev, step_fn=step)
+    if rank == 0:
+        P = int(state["H"].numel())
+        print(json.dumps({
+            "metric": "diag_ef_fit_samples_per_sec", "value": world * Ksteps * B / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": Ksteps, "warmup": W, "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 hi/lo split operands, fp32 accumulate", "data": "synthetic",
+            "config": {"workload": workload_name(args), "batch_per_gpu": B, "parallelism": f"dp{world}", "parameters": P,
+                       "exchange": f"one all-reduce of the {4 * P / 1e6:.0f} MB diagonal after the K steps, inside the timed region"},
+            "clocks": clk, "gpu_launches": launches, "roofline": roof}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.structure == "diag_ef":
+        run_diag_ef(a)
     else:
         run_ours(a)

@@ -723,6 +723,9 @@ class _B200Mixin:
                 return cache[key]
         out = self._jacobians_impl(x)
         if key is not None and len(cache) < self._jac_cache_max:
+            fac = getattr(out[0], "_lpb_factors", None)
+            if fac is not None:
+                fac.keep_projections = True
             cache[key] = out
         return out
 

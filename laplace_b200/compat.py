@@ -76,11 +76,17 @@ def _torchmetrics_placeholder() -> types.ModuleType:
 
         def add_state(self, name, default, dist_reduce_fx=None):
             self._lpb_defaults[name] = default
-            setattr(self, name, default.clone() if torch.is_tensor(default) else list(default))
+            if torch.is_tensor(default):
+                self.register_buffer(name, default.clone(), persistent=False)   # follows ``.to(device)`` like the real states
+            else:
+                setattr(self, name, list(default))
 
         def reset(self):
             for name, default in self._lpb_defaults.items():
-                setattr(self, name, default.clone() if torch.is_tensor(default) else list(default))
+                if torch.is_tensor(default):
+                    getattr(self, name).copy_(default)
+                else:
+                    setattr(self, name, list(default))
 
         def forward(self, *a, **k):
             self.update(*a, **k)
@@ -93,8 +99,8 @@ def _torchmetrics_placeholder() -> types.ModuleType:
             self.add_state("total", torch.tensor(0.0))
 
         def update(self, preds, target):
-            self.sum_squared_error = self.sum_squared_error.to(preds.device) + ((preds - target) ** 2).sum(0)
-            self.total = self.total.to(preds.device) + target.shape[0]
+            self.sum_squared_error += ((preds - target) ** 2).sum(0)
+            self.total += target.shape[0]
 
         def compute(self):
             return self.sum_squared_error / self.total

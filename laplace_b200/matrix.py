@@ -271,6 +271,14 @@ def _symeig_threaded(items, one, eigvals, eigvecs):
     q = queue.SimpleQueue()
     for k, it in enumerate(items):          # largest first: `items` is sorted by size
         q.put((k, it))
+    sizes = [int(it[2].shape[0]) for it in items]
+    dt = items[0][2].dtype
+    Qflat = torch.empty(sum(n * n for n in sizes), device=dev, dtype=dt)
+    Lflat = torch.empty(sum(sizes), device=dev, dtype=dt)
+    out, qo, lo = [], 0, 0
+    for n in sizes:
+        out.append((Lflat[lo:lo + n], Qflat[qo:qo + n * n].view(n, n)))
+        qo, lo = qo + n * n, lo + n
     errors = []
 
     def work(stream):
@@ -284,10 +292,14 @@ def _symeig_threaded(items, one, eigvals, eigvecs):
                     except queue.Empty:
                         break
                     L, W = one(k, H)
-                    for t in (L, W):
-                        t.record_stream(cur)     # allocated on the worker's stream, consumed on the caller's
+                    # results land in buffers the CALLER's stream allocated (``out``): the worker's own pool then only
+                    # ever holds one factor's temporaries, so repeated decompositions do not grow it with synchronising
+                    # cudaMallocs (429 vs 220 ms for ResNet-18 when the previous result was still alive)
+                    Lo, Wo = out[k]
+                    Lo.copy_(L), Wo.copy_(W)
                     H.record_stream(stream)
-                    eigvals[i][j], eigvecs[i][j] = L, W
+                    eigvals[i][j], eigvecs[i][j] = Lo, Wo
+                    del L, W
         except BaseException as e:  # noqa: BLE001 -- re-raised in the caller's thread
             errors.append(e)
 
@@ -395,6 +407,9 @@ class JacobianFactors:
     def __init__(self, blocks, n_batch: int, n_out: int, sizes):
         self.blocks, self.n_batch, self.n_out, self.sizes = blocks, n_batch, n_out, sizes
         self._proj = (None, {})
+        # rotated rows of weight-sharing layers double the memory of a batch: cached only when a sweep over prior precisions
+        # will reuse them (``backend.cached_jacobians()``, ``laplace_b200.tuning``)
+        self.keep_projections = False
 
     def projections(self, basis_key) -> dict:
         """Per-block eigenbasis projections of these Jacobians for ONE decomposition (identified by the rotation cache all
@@ -577,12 +592,14 @@ class B200KronDecomposed(KronDecomposed):
                 m = self._gemm(at2, inv_spec)                            # [Nn, d_out]
                 K.batched_pair_dot(gtn, gtn, m, out, accumulate=True)
             elif kind == "conv" and len(ls) == 2 and C <= 12:
-                if i not in proj:
+                if i in proj:
+                    Gt, At, T = proj[i]
+                else:
                     Grows, Arows, T = blk[1], blk[2], blk[3]            # [(c,n,t), d_out], [(n,t), d_in]
                     Gt = self._gemm(self._Q32(i, 0, True), Grows)        # Q1^T G^T -> [d_out, C*Nn*T] (K-major)
                     At = self._gemm(self._Q32(i, 1, True), Arows)        # Q2^T A^T -> [d_in, Nn*T]
-                    proj[i] = (Gt, At, T)
-                Gt, At, T = proj[i]
+                    if fac.keep_projections:   # as large as the rows themselves: kept only for sweeps over deltas
+                        proj[i] = (Gt, At, T)
                 K.kron_conv_quadform(Gt, At, T, Nn, C, _as_f32(ls[0]).contiguous(), _as_f32(ls[1]).contiguous(),
                                      float(delta), self.damping, out)
             elif kind == "vec" and len(ls) == 1:

@@ -52,6 +52,9 @@ def gridsearch_prior_precision(la, val_loader, interval: torch.Tensor | None = N
         X, y = X.to(dev), y.to(dev)
         with torch.enable_grad():
             Js, f_mu = la.backend.last_layer_jacobians(X) if last_layer else la.backend.jacobians(X)
+        fac = getattr(Js, "_lpb_factors", None)
+        if fac is not None:
+            fac.keep_projections = True
         batches.append((Js, f_mu.detach(), y))
     keep = la.prior_precision
     losses = []

@@ -10,9 +10,14 @@ import torch
 
 
 def symeig(M: torch.Tensor):
-    """``laplace.utils.utils.symeig`` (utils/utils.py:193-228): ``eigh(UPLO='U')``,
-    eigenvalues clamped at 0, NaNs zeroed."""
-    L, W = torch.linalg.eigh(M, UPLO="U")
+    """``laplace.utils.utils.symeig`` (utils/utils.py:193-228): ``eigh(UPLO='U')``, on failure once more on ``M + I``
+    with the jitter removed from the eigenvalues (:209-216; LAPACK's divide-and-conquer does give up on some rank-deficient
+    factors, e.g. a 576x576 input factor with 46 live coordinates), eigenvalues clamped at 0, NaNs zeroed."""
+    try:
+        L, W = torch.linalg.eigh(M, UPLO="U")
+    except RuntimeError:
+        L, W = torch.linalg.eigh(M + torch.eye(M.shape[0], dtype=M.dtype, device=M.device), UPLO="U")
+        L = L - 1.0
     return torch.nan_to_num(L.clamp(min=0.0)), torch.nan_to_num(W)
 
 
