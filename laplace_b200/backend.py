@@ -34,13 +34,18 @@ from .matrix import B200Kron, JacobianFactors
 
 SUPPORTED = (nn.Linear, nn.Conv2d)
 PRECISIONS = ("auto", "fp32", "bf16", "bf16x3")
-# precision="auto": input (A) factors over at least this many sample rows use ONE fp16 product instead of three.
-# fp16 rounds every activation by at most 2^-12 relative, independently across the sample rows that are summed, so the
-# factor's relative error is ~ 2^-12 * sqrt(2) / sqrt(rows) <= 2.7e-6 at 16 384 rows (measured against the fp64 oracle
-# in tests/test_gpu_zz_scale.py) -- far inside the 1e-4 gate -- for a third of the tensor-core work.  Output-gradient
-# (B) factors keep three products: gradient rows are heavy-tailed (few confident samples carry the sum), so the
-# effective number of averaged rows can be far below the row count.
+# precision="auto": input (A) factors use ONE fp16 product instead of three when they are summed over at least
+# max(A_SINGLE_PRODUCT_MIN_ROWS, A_SINGLE_PRODUCT_ROWS_PER_DIM * d_in) sample rows.  fp16 rounds every activation by at most
+# 2^-12 relative, independently across rows; for a factor over K rows of d features the relative Frobenius error is at most
+# ~ 3.4e-4 * sqrt(d / K) (white inputs: measured 2.1e-5 on the 147-feature stem at K = 16 384, predicted 3.2e-5) and an order
+# of magnitude less on post-ReLU activations, whose factors are dominated by the mean (measured <= 1e-5 on every such layer
+# of ResNet-18).  128 rows per feature bounds the white-input case by 3e-5, inside the 1e-4 gate next to the 2.5e-5 of the
+# reverse pass.  Output-gradient (B) factors and the reverse pass itself keep three products: a two-product backward-data
+# convolution (gradient rows rounded to bf16, exact weights: conv_engine.LEAN_BWD_MIN_ROWS) was measured at 1.1e-4 .. 1.8e-4
+# on the B factors -- the rounding of a gradient element does not average out inside its own dot product -- and stays off.
 A_SINGLE_PRODUCT_MIN_ROWS = 16384
+A_SINGLE_PRODUCT_ROWS_PER_DIM = 128
+LEAN_BACKWARD_MIN_ROWS = 0     # > 0: two-product backward-data convolutions in kron() from this many gradient rows (off)
 
 
 class _Layer:
@@ -447,7 +452,8 @@ class _B200Mixin:
                 Prows, Xs = rows.get("P"), rows.get("X")
 
                 def lean(P):   # see A_SINGLE_PRODUCT_MIN_ROWS (fp16 operands only: a bf16 half keeps 8 bits, not 11)
-                    ok = self.precision == "auto" and P.kind == K.F16X3 and P.rows >= A_SINGLE_PRODUCT_MIN_ROWS
+                    ok = (self.precision == "auto" and P.kind == K.F16X3
+                          and P.rows >= max(A_SINGLE_PRODUCT_MIN_ROWS, A_SINGLE_PRODUCT_ROWS_PER_DIM * L.d_in))
                     return K.hi_only(P) if ok else P
 
                 if (Xs is not None and Xs[1] == M and K.conv_patches_ok(Xs[0].K, Xs[2], Xs[3], *L.mod.kernel_size)):
@@ -487,10 +493,10 @@ class _B200Mixin:
             if side is not None:
                 main.wait_stream(side)
 
-        if self.conv_engine and self.precision == "auto":
+        if self.conv_engine and self.precision == "auto" and LEAN_BACKWARD_MIN_ROWS > 0:
             from . import conv_engine as _ce0
 
-            _ce0.LEAN_BWD_MIN_ROWS = A_SINGLE_PRODUCT_MIN_ROWS     # reset in the ``finally`` below
+            _ce0.LEAN_BWD_MIN_ROWS = LEAN_BACKWARD_MIN_ROWS     # opt-in experiment, reset in the ``finally`` below
         try:
             try:
                 grads = self._backward(f, cols)

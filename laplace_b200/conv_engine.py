@@ -35,10 +35,10 @@ KIND_FWD = K.F16X3    # forward pass: activations / weights sit inside fp16 rang
                       # ~2e-7 forward error keeps ReLU masks identical to an fp32 forward (a 1e-5 error flips a
                       # few masks per 10^5 units, each flip is a 100 % error on that unit's gradient)
 # > 0: backward-data convolutions over at least this many gradient rows use the bf16 hi half of the gradient alone
-# against the exact (hi + lo) weights -- two tensor-core products instead of three.  The gradient is then rounded to 8
-# bits INDEPENDENTLY per sample row (relative 2^-9, unbiased), which averages out in the factor sums over the rows; the
-# weights, shared by all rows, stay exact.  Set by the backend around the reverse pass of ``kron()`` under
-# precision="auto" (backend.A_SINGLE_PRODUCT_MIN_ROWS); 0 elsewhere (Jacobians / dense / diagonal curvature).
+# against the exact (hi + lo) weights -- two tensor-core products instead of three.  OFF by default: each gradient element
+# then carries ~2e-3 of relative noise (the 2^-9 rounding of the rows does not average out inside one dot product), which
+# costs 1.1e-4 .. 1.8e-4 rel-fro on the KFAC B factors at batch 64 .. 256 (tools/gpu_lean_diag.py).  Kept as a measured
+# option (backend.LEAN_BACKWARD_MIN_ROWS) for batches where rows / d_out >= ~2e5.
 LEAN_BWD_MIN_ROWS = 0
 USE_IMPLICIT = os.environ.get("LPB_NO_IMPLICIT") != "1"
 USE_STRIDED = os.environ.get("LPB_NO_STRIDED") != "1"     # strided reverse passes as per-parity implicit GEMMs

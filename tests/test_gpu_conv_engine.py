@@ -79,7 +79,7 @@ def test_conv_forward_backward_vs_fp64(geom):
 
 @pytest.mark.parametrize("geom", [(64, 64, 3, 1, 1, 1, 8), (128, 64, 3, 1, 1, 1, 4), (64, 128, 3, 2, 1, 1, 16), (256, 256, 3, 1, 1, 1, 2)])
 def test_two_product_backward_data(geom):
-    """``LEAN_BWD_MIN_ROWS`` route (kron() under precision="auto"): the gradient rows enter the backward-data convolution
+    """``LEAN_BWD_MIN_ROWS`` route (opt-in, off by default -- see conv_engine.py): the gradient rows enter the backward-data convolution
     as their bf16 hi half only, the weights stay hi + lo.  The result equals the exact convolution of the ROUNDED gradient
     (5e-6: weights are not rounded) and deviates from the unrounded one by the bf16 rounding of the rows (~2^-9, unbiased:
     the mean signed deviation is two orders of magnitude smaller)."""
