@@ -6,7 +6,7 @@ curvature at the end.  Every curvature structure of the path is a 
 curvature/curvlinops.py:46-53, baselaplace.py:964) -- ``ShardedLoader`` keeps ``len(loader.dataset)`` global.
 
 Exchange (SURVEY 8(e) "v2"): all-reduce of the flat factor buffer, then every rank eigendecomposes only the factors it
-owns (greedy balance on ``n^3``) and the eigenvectors / eigenvalues are replicated with ONE all-gather of equally sized
+owns (greedy balance on the measured cost of the live block) and the eigenvectors / eigenvalues are replicated with ONE all-gather of equally sized
 per-rank slabs -- each byte of ``Q`` crosses NVLink once (the round-1 version all-reduced a zero-padded buffer: world
 times the traffic, and the reduction arithmetic on top).
 """
@@ -91,15 +91,20 @@ def allreduce_curvature(H, loss=None, group=None):
     return H, loss
 
 
-def factor_owners(sizes, world: int):
-    """Greedy balance of the eigendecomposition cost (``n^3``) over ``world`` ranks, largest first.  Deterministic: every
-    rank computes the same table."""
-    order = sorted(range(len(sizes)), key=lambda k: (-sizes[k], k))
+def factor_owners(sizes, world: int, cost=None):
+    """Greedy balance of the eigendecomposition cost over ``world`` ranks, most expensive first (``cost(n)``: measured
+    milliseconds by size, ``matrix.eigh_cost_ms``; ``sizes`` are the LIVE sizes -- a 4608-row input factor of a 3x3
+    convolution on a 1x1 map costs what its 460 live coordinates cost).  Deterministic: every rank computes the same table."""
+    from .matrix import eigh_cost_ms
+
+    cost = cost or eigh_cost_ms
+    w = [float(cost(int(n))) for n in sizes]
+    order = sorted(range(len(sizes)), key=lambda k: (-w[k], k))
     load, owner = [0.0] * world, [0] * len(sizes)
     for k in order:
         r = min(range(world), key=lambda q: (load[q], q))
         owner[k] = r
-        load[r] += float(sizes[k]) ** 3
+        load[r] += w[k]
     return owner
 
 
@@ -114,8 +119,10 @@ def decompose_sharded(kron, damping: bool = False, group=None):
         return kron.decompose(damping=damping)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     mats = [(i, j, H) for i, F in enumerate(kron.kfacs) for j, H in enumerate(F)]
+    from .matrix import live_sizes
+
     sizes = [int(m[2].shape[0]) for m in mats]
-    owner = factor_owners(sizes, world)
+    owner = factor_owners(live_sizes([m[2] for m in mats]), world)    # all ranks hold identical (all-reduced) factors
     owned = [[k for k in range(len(mats)) if owner[k] == r] for r in range(world)]
     slab = max(sum(sizes[k] * (sizes[k] + 1) for k in ks) for ks in owned)     # n*n eigenvectors + n eigenvalues each
     dev, dt = mats[0][2].device, mats[0][2].dtype

@@ -222,6 +222,10 @@ def _symeig_concurrent(items, eigvals, eigvecs):
     if COMPACT_DEAD_COORDINATES:
         # one host read for all factors: how many coordinates carry any mass (PSD: zero diagonal <=> zero row/column)
         live = torch.stack([(H.diagonal() != 0).sum() for _, _, H in items]).tolist()
+    if BATCHED_MID_SIZES and items[0][2].is_cuda and items[0][2].dtype == torch.float32:
+        items, live = _symeig_mid_batched(items, live, eigvals, eigvecs)
+        if not items:
+            return
     serial = not items[0][2].is_cuda or len(items) == 1 or N_EIGH_STREAMS <= 1
 
     def one(k, H):
@@ -251,6 +255,88 @@ def _symeig_concurrent(items, eigvals, eigvecs):
             H.record_stream(streams[k % len(streams)])
     for s_ in streams:
         cur.wait_stream(s_)
+
+
+# Factors whose live block has at most this many rows go through ONE batched library call per size class (256 / 513 rows,
+# bordered like ``_eigh_padded``) instead of one call each: 17 factors of <= 513 rows 96 -> 30 ms, 6 of 256 rows 32 -> 3.8 ms.
+BATCHED_MID_SIZES = True
+BATCHED_MID_CLASSES = (256, 513)
+
+
+def _symeig_mid_batched(items, live, eigvals, eigvecs):
+    """Handles every factor whose live block fits ``BATCHED_MID_CLASSES`` with ``cusolverDnXsyevBatched``; returns the
+    remaining ``(items, live)`` for the one-by-one route.  Compaction (dead coordinates dropped) and bordering (negative
+    diagonal block that decouples exactly and sorts first) are the same as in ``_symeig_compact`` / ``_eigh_padded``."""
+    from . import _cusolver
+
+    if not _cusolver.available():
+        return items, live
+    groups: dict[int, list] = {}
+    rest, rest_live = [], []
+    for k, it in enumerate(items):
+        n = it[2].shape[0]
+        lv = live[k] if (live is not None and live[k] <= COMPACT_MAX_LIVE_FRACTION * n) else n
+        cls = next((c for c in BATCHED_MID_CLASSES if lv <= c), None)
+        if cls is None or lv == 0:
+            rest.append(it)
+            rest_live.append(live[k] if live is not None else None)
+        else:
+            groups.setdefault(cls, []).append((it, lv))
+    for cls, grp in groups.items():
+        if len(grp) < 2:       # a single factor gains nothing from the batched entry point
+            for it, lv in grp:
+                rest.append(it)
+                rest_live.append(lv if live is not None else None)
+            continue
+        dev = grp[0][0][2].device
+        batch = torch.zeros(len(grp), cls, cls, device=dev, dtype=torch.float32)
+        meta = []
+        for b, ((i, j, H), lv) in enumerate(grp):
+            n = H.shape[0]
+            if lv < n:
+                alive = H.diagonal() != 0
+                idx, dead = torch.nonzero(alive).squeeze(1), torch.nonzero(~alive).squeeze(1)
+                Hs = H.index_select(0, idx).index_select(1, idx)
+            else:
+                idx = dead = None
+                Hs = H
+            k_ = Hs.shape[0]
+            batch[b, :k_, :k_] = torch.triu(Hs) + torch.triu(Hs, 1).t()          # UPLO = 'U' (utils/utils.py:207)
+            if k_ < cls:
+                border = -(Hs.diagonal().abs().max() + 1.0)
+                batch[b, k_:, k_:] = torch.diag_embed(border.expand(cls - k_))
+            meta.append((i, j, n, k_, idx, dead))
+        try:
+            W, Q, info = _cusolver.syev_batched(batch)
+        except RuntimeError as e:
+            import warnings
+
+            warnings.warn(f"laplace_b200: batched eigensolver unavailable ({e}); using one call per factor")
+            for it, lv in grp:
+                rest.append(it)
+                rest_live.append(lv if live is not None else None)
+            continue
+        bad = info.ne(0).tolist()          # one host read per size class (the reference's symeig retries on failure too)
+        for b, (i, j, n, k_, idx, dead) in enumerate(meta):
+            if bad[b]:
+                rest.append(grp[b][0])
+                rest_live.append(grp[b][1] if live is not None else None)
+                continue
+            p = cls - k_
+            Ls = torch.nan_to_num(W[b, p:].clamp(min=0.0))
+            Ws = torch.nan_to_num(Q[b, :k_, p:])
+            if idx is None:
+                eigvals[i][j], eigvecs[i][j] = Ls, Ws.contiguous()
+            else:
+                L = torch.cat([torch.zeros(n - k_, dtype=Ls.dtype, device=dev), Ls])
+                Wf = torch.zeros(n, n, dtype=Ws.dtype, device=dev)
+                Wf[dead, torch.arange(n - k_, device=dev)] = 1
+                Wf[idx.unsqueeze(1), (n - k_) + torch.arange(k_, device=dev).unsqueeze(0)] = Ws
+                eigvals[i][j], eigvecs[i][j] = L, Wf
+    if live is None:
+        rest_live = None
+    order = sorted(range(len(rest)), key=lambda q: -rest[q][2].shape[0])
+    return [rest[q] for q in order], (None if rest_live is None else [rest_live[q] for q in order])
 
 
 # The library eigensolver synchronises with the host between its phases, so factors issued from ONE thread run strictly
@@ -312,6 +398,28 @@ def _symeig_threaded(items, one, eigvals, eigvecs):
         cur.wait_stream(s_)
     if errors:
         raise errors[0]
+
+
+def live_sizes(mats):
+    """Number of coordinates of each PSD factor that carry any mass (zero diagonal <=> zero row / column) -- ONE host
+    read for all factors.  ``decompose`` works on the live block only (``_symeig_compact``), so this is the size that
+    determines a factor's cost."""
+    if not COMPACT_DEAD_COORDINATES or not mats:
+        return [int(H.shape[0]) for H in mats]
+    live = torch.stack([(H.diagonal() != 0).sum() if H.ndim == 2 else torch.as_tensor(H.numel(), device=H.device)
+                        for H in mats]).tolist()
+    return [int(l) if l <= COMPACT_MAX_LIVE_FRACTION * H.shape[0] else int(H.shape[0]) for l, H in zip(live, mats)]
+
+
+# measured on B200 (profiles/r02_eigh.md): milliseconds of one decomposition by (live) size, fp32
+_EIGH_MS = ((1, 0.2), (64, 0.3), (128, 1.2), (129, 5.6), (513, 5.6), (576, 6.2), (1024, 11.3), (1152, 13.3), (2304, 30.5), (4608, 85.5))
+
+
+def eigh_cost_ms(n: int) -> float:
+    for (n0, t0), (n1, t1) in zip(_EIGH_MS, _EIGH_MS[1:]):
+        if n <= n1:
+            return t0 + (t1 - t0) * (max(n, n0) - n0) / max(1, n1 - n0)
+    return _EIGH_MS[-1][1] * (n / _EIGH_MS[-1][0]) ** 3
 
 
 COMPACT_DEAD_COORDINATES = True

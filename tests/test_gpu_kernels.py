@@ -223,6 +223,42 @@ def test_eigh_jacobi(n):
     assert torch.allclose(ev2.cpu().double(), ev, atol=1e-6)
 
 
+@pytest.mark.parametrize("batched,threads", [(True, 4), (False, 4), (False, 1)])
+def test_decompose_routes_agree_with_fp64(batched, threads):
+    """``B200Kron.decompose`` over a mix of factor sizes -- hand-written Jacobi (<= 128), the batched mid-size route
+    (bordered to 256 / 513 rows, dead coordinates compacted), one library call per factor beyond, host threads -- against an
+    fp64 eigendecomposition: eigenvalues, reconstruction, orthogonality, ``UPLO='U'`` semantics of ``symeig``
+    (utils/utils.py:193-228)."""
+    from laplace_b200 import B200Kron, matrix
+
+    torch.manual_seed(12)
+
+    def psd(n, dead=0):
+        Z = torch.randn(n, 2 * n)
+        A = Z @ Z.T / (2 * n)
+        if dead:
+            A[:dead] = 0
+            A[:, :dead] = 0
+        return A
+
+    facs = [psd(64), psd(130), psd(200), psd(256), psd(300), psd(513), psd(600, dead=400), psd(700), psd(1200, dead=900), psd(40), psd(147)]
+    kron = B200Kron([[f.to(DEV)] for f in facs])
+    keep = (matrix.BATCHED_MID_SIZES, matrix.N_EIGH_THREADS)
+    matrix.BATCHED_MID_SIZES, matrix.N_EIGH_THREADS = batched, threads
+    try:
+        kd = kron.decompose()
+    finally:
+        matrix.BATCHED_MID_SIZES, matrix.N_EIGH_THREADS = keep
+    for f, Q, L in zip(facs, kd.eigenvectors, kd.eigenvalues):
+        n = f.shape[0]
+        Q, L = Q[0].cpu().double(), L[0].cpu().double()
+        assert Q.shape == (n, n) and L.shape == (n,) and (L[1:] >= L[:-1]).all() and float(L.min()) >= 0
+        ref = torch.linalg.eigvalsh(f.double()).clamp(min=0)
+        assert torch.allclose(L, ref, rtol=1e-4, atol=2e-6 * float(ref.max())), n
+        assert rel_fro((Q * L) @ Q.T, f) < 1e-5, n
+        assert float((Q.T @ Q - torch.eye(n, dtype=torch.float64)).abs().max()) < 2e-5, n
+
+
 @pytest.mark.parametrize("Kr,M,N", [(64, 128, 128), (512, 64, 64), (1000, 200, 96), (4096, 128, 128), (5000, 513, 257), (40000, 300, 300), (33, 10, 10)])
 @pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 1e-5)])
 def test_gemm_tn_rows_operands(Kr, M, N, kind, tol):
