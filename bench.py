@@ -505,13 +505,14 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev, step_fn=None):
     # DRAM bytes per launch of the dominant family from the committed ncu launch list of the same workload (a number
     # taken under a profiler is never a bench value; it only annotates the roofline entry)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic_run26.json")
-    if args.model == "resnet18" and args.batch == 4096 and args.precision == "bf16x3" and os.path.exists(tpath):
+    tfile = {"auto": "r02_ncu_traffic.json", "bf16x3": "r01_ncu_traffic_run26.json"}.get(args.precision, "")
+    tpath = os.path.join(ROOT, "profiles", tfile)
+    if args.model == "resnet18" and args.batch == 4096 and tfile and os.path.exists(tpath) and step_fn is None:
         traffic = json.load(open(tpath))["families"].get(dom, {}).get("dram_bytes_per_launch")
     return {"bound": "tensor" if tensor else "hbm", "kernel": names.get(dom, "lpb::" + dom + "_kernel"),
             "achieved": d["achieved"], "peak": peak, "unit": d["unit"], "frac": d["achieved"] / peak, "traffic": traffic,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu launch list of the same command "
-                            "(profiles/r01_ncu_traffic_run26.json)" if traffic else "",
+            "traffic_note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu launch list of the same workload "
+                            f"(profiles/{tfile}, profiles/r02_launches_b4096_auto.md)" if traffic else "",
             "peak_source": pk["source"] + (", bf16 sustained" if tensor else ", copy bandwidth"),
             "note": "algorithmic FLOPs (one product per MAC) over CUDA-event time; precision bf16x3 issues 3 tensor-core "
                     "products per algorithmic MAC, so the tensor pipe does 3x the counted work" if tensor and args.precision == "bf16x3" else "",
