@@ -92,25 +92,39 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const ItemGeom it = decode_item(item, num_tiles, symmetric, tiles_m, tiles_n, total_kchunks, kchunks_per_split);
+        // implicit-patch operands: the (tap, channel block) of the tile's four 64-feature blocks is fixed over the K loop --
+        // decode it ONCE per item, and step the sample coordinates (image, first image row) instead of dividing per chunk.
+        // (r02: with the decode inside the loop -- ~6 integer divisions per chunk in the single producer thread -- the
+        // loader, not the tensor pipe or the L2 fill, bound the kernel: 17 % tensor-pipe activity in the one-product mode.)
+        int p_ci[4] = {0, 0, 0, 0}, p_dw[4] = {0, 0, 0, 0}, p_dh[4] = {0, 0, 0, 0};
+        int n0 = 0, h0 = 0;
+        if (LOADER == 2 || LOADER == 3) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int fb = (b < 2 ? it.tm : it.tn) * 2 + (b & 1);
+            const int live = fb / pg.blocks_per_tap;
+            const int tap = pg.tap_of[live < pg.num_taps ? live : 0];
+            const int kh = tap / pg.KW, kw = tap - kh * pg.KW;
+            // feature blocks past the last tap read channel coordinate Ci: entirely out of bounds = zeros
+            p_ci[b] = live < pg.num_taps ? (fb - live * pg.blocks_per_tap) * 64 : pg.Ci;
+            p_dw[b] = kw - pg.PW;
+            p_dh[b] = kh - pg.PH;
+          }
+          if (pg.chunks_per_img > 0) { n0 = it.kc_begin / pg.chunks_per_img; h0 = (it.kc_begin - n0 * pg.chunks_per_img) * pg.rows_per_chunk; }
+          else { n0 = it.kc_begin * pg.imgs_per_chunk; h0 = 0; }
+          if (LOADER == 3 && pg.n_images > 0) n0 %= pg.n_images;
+        }
+        const int img_rows = pg.chunks_per_img * pg.rows_per_chunk;   // image height when an image spans several chunks
         for (int kc = it.kc_begin; kc < it.kc_end; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], it.diag ? STAGE_BYTES / 2 : STAGE_BYTES);
           auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, int tile, bool is_b) {
             if (LOADER == 2 || (LOADER == 3 && is_b)) {
-              int n0, h0;
-              if (pg.chunks_per_img > 0) { n0 = kc / pg.chunks_per_img; h0 = (kc - n0 * pg.chunks_per_img) * pg.rows_per_chunk; }
-              else { n0 = kc * pg.imgs_per_chunk; h0 = 0; }
-              if (LOADER == 3 && pg.n_images > 0) n0 %= pg.n_images;
 #pragma unroll
               for (int b = 0; b < 2; ++b) {
-                const int fb = tile * 2 + b;
-                const int live = fb / pg.blocks_per_tap;
-                const int tap = pg.tap_of[live < pg.num_taps ? live : 0];
-                const int kh = tap / pg.KW, kw = tap - kh * pg.KW;
-                // feature blocks past the last tap read channel coordinate Ci: entirely out of bounds = zeros
-                const int ci0 = live < pg.num_taps ? (fb - live * pg.blocks_per_tap) * 64 : pg.Ci;
-                tma_load_4d(map, &full_bar[stage], dst + b * (TILE_BYTES / 2), ci0, kw - pg.PW, h0 + kh - pg.PH, n0);
+                const int q = (is_b ? 2 : 0) + b;
+                tma_load_4d(map, &full_bar[stage], dst + b * (TILE_BYTES / 2), p_ci[q], p_dw[q], h0 + p_dh[q], n0);
               }
             } else if (MN) {
               tma_load_2d(map, &full_bar[stage], dst, tile * BM, kc * BK);
@@ -124,6 +138,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gr
           if (NPROD == 3) {
             load_tile(&tmA_lo, st + 2 * TILE_BYTES, it.tm, false);
             if (!it.diag) load_tile(&tmB_lo, st + 3 * TILE_BYTES, it.tn, true);
+          }
+          if (LOADER == 2 || LOADER == 3) {   // next chunk's sample coordinates
+            if (pg.chunks_per_img > 0) {
+              h0 += pg.rows_per_chunk;
+              if (h0 >= img_rows) { h0 = 0; ++n0; }
+            } else {
+              n0 += pg.imgs_per_chunk;
+            }
+            if (LOADER == 3 && pg.n_images > 0 && n0 >= pg.n_images) n0 -= pg.n_images;
           }
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
