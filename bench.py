@@ -363,8 +363,9 @@ def run_ours(args):
     pred = {}
     if not args.no_predictive:
         leg("predictive", lambda: pred.update(measure_predictive(model, dev, world, timed, args)))
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.model == "resnet18":
         leg("b512", lambda: extras.__setitem__("batch_512", measure_small_batch(be, dev, shape, N_total)))
+    if rank == 0 and world == 1:
         leg("jtj_syrk_kernel", lambda: extras.__setitem__("jtj_syrk_kernel", measure_syrk_probe(K, dev)))
 
     if rank == 0:
