@@ -182,6 +182,22 @@ int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const floa
                                int T, int Nn, int ncols, float scale, float* out, int64_t out_ld, int64_t js_stride_n,
                                int64_t js_stride_c, void* stream);
 
+/* ---- layer-level KFAC entry points (compositions of the kernels above) ------------------------------------
+ * For a caller that holds plain fp32 tensors and wants ONE call per Kronecker factor of CurvlinopsInterface.kron
+ * (curvature/curvlinops.py:77-108).  `workspace`: device scratch of at least lpb_workspace_bytes(rows, d) bytes, owned by
+ * the caller.  `out` [d, d] fp32 is ACCUMULATED into (the caller zeroes it once per fit).
+ *   lpb_kfac_accum_rows   out += alpha * X^T X for fp32 rows X [rows, d]: the input factor A of an nn.Linear (rows = the
+ *                         (n, t) layer inputs, alpha = sqrt(factor)/(N*T), fp16_operands = 1) or the output-gradient factor
+ *                         B of any layer (rows = the (col, n, t) gradient rows, alpha = sqrt(factor), fp16_operands = 0: bf16
+ *                         hi/lo keeps the gradients' dynamic range).  Three tensor-core products, fp32 accumulation.
+ *   lpb_kfac_accum_conv_input out += alpha * P^T P for the unfolded patches P [(n,oh,ow), C*KH*KW] of an NCHW fp32 input
+ *                         (curvlinops' unfold + einsum): workspace rows = N*OH*OW, d = C*KH*KW.                        */
+int64_t lpb_workspace_bytes(int64_t rows, int64_t d);
+int lpb_kfac_accum_rows(const float* X, int64_t rows, int64_t d, int64_t ldx, float alpha, int fp16_operands, void* workspace,
+                        int64_t workspace_bytes, float* out, int64_t ldo, void* stream);
+int lpb_kfac_accum_conv_input(const float* x, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int DH,
+                          int DW, float alpha, void* workspace, int64_t workspace_bytes, float* out, int64_t ldo, void* stream);
+
 /* Kron GLM-predictive quadratic form of a weight-sharing layer without the dense Jacobian (replaces the per-(n,c) dense
  * rotations of KronDecomposed._bmm / inv_square_form, utils/matrix.py:406-461, for convolution / token-shared layers):
  *   out[n,c,k] += sum_ij w(i,j) Z_c[i,j] Z_k[i,j],  Z_c[i,j] = sum_t Gt[i, c*g_stride_c + n*T + t] * At[j, n*T + t],

@@ -46,6 +46,8 @@ SIGNATURES = {
                          c_int, c_f32, c_vp, c_i64, c_int, c_vp],
     "lpb_shared_weight_contract": [c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp,
                                    c_i64, c_i64, c_i64, c_vp],
+    "lpb_kfac_accum_rows": [c_vp, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_vp, c_i64, c_vp],
+    "lpb_kfac_accum_conv_input": [c_vp] + [c_int] * 12 + [c_f32, c_vp, c_i64, c_vp, c_i64, c_vp],
     "lpb_kron_conv_quadform": [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_f32, c_int, c_vp,
                                c_vp],
     "lpb_jac_linear_write": [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp],
@@ -56,7 +58,7 @@ SIGNATURES = {
     "lpb_ll_sigma_gather": [c_vp, c_int, c_int, c_int, c_vp, c_vp],
     "lpb_eigh_jacobi": [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp],
 }
-EXPORTS = ["lpb_version", "lpb_last_error"] + list(SIGNATURES)
+EXPORTS = ["lpb_version", "lpb_last_error", "lpb_workspace_bytes"] + list(SIGNATURES)
 
 _lib = None
 
@@ -81,6 +83,8 @@ def load() -> C.CDLL:
     lib.lpb_version.argtypes = []
     lib.lpb_last_error.restype = C.c_char_p
     lib.lpb_last_error.argtypes = []
+    lib.lpb_workspace_bytes.restype = c_i64
+    lib.lpb_workspace_bytes.argtypes = [c_i64, c_i64]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

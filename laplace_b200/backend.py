@@ -429,6 +429,10 @@ class _B200Mixin:
             if L.has_b:
                 dims.append([L.d_out])
         kron = B200Kron.zeros(dims, fd.device, torch.float32)
+        if fd.is_cuda:
+            from .matrix import prewarm_eigensolver
+
+            prewarm_eigensolver(fd.device)     # library start-up overlaps the data pass (once per process)
         sq = math.sqrt(self.factor)
         slots, idx = {}, 0   # layer name -> index of its first Kron block
         for L in self._layers:

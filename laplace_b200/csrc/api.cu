@@ -292,6 +292,49 @@ int lpb_kron_conv_quadform(const float* Gt, int64_t ldg, int64_t g_stride_c, con
   return lpb::kron_conv_quadform(Gt, ldg, g_stride_c, At, lda, d_out, d_in, T, Nn, C, l1, l2, delta, damping, out, ST(stream));
 }
 
+// ---- layer-level KFAC entry points (lpb_kfac_accum_A / _B, lpb_workspace_bytes) -------------------------
+// Compositions of the kernels above for a caller that holds plain fp32 activations / gradients and wants one call per
+// factor: operand split into 16-bit hi/lo rows in the caller's workspace, then the MN-major tcgen05 SYRK.
+static int64_t ld_round8(int64_t k) { return (k + 7) / 8 * 8 < 8 ? 8 : (k + 7) / 8 * 8; }
+
+int64_t lpb_workspace_bytes(int64_t rows, int64_t d) {
+  if (rows < 0 || d <= 0) return -1;
+  return 2 * rows * ld_round8(d) * 2 + 512;   // hi + lo 16-bit rows, 256-byte aligned halves
+}
+
+static int split_workspace(void* ws, int64_t ws_bytes, int64_t rows, int64_t d, void** hi, void** lo, int64_t* ld) {
+  LPB_REQUIRE(ws != nullptr && ws_bytes >= lpb_workspace_bytes(rows, d), "workspace too small: need %lld bytes",
+              (long long)lpb_workspace_bytes(rows, d));
+  *ld = ld_round8(d);
+  uintptr_t base = ((uintptr_t)ws + 255) & ~(uintptr_t)255;
+  *hi = (void*)base;
+  *lo = (void*)((base + (uintptr_t)(rows * *ld * 2) + 255) & ~(uintptr_t)255);
+  return 0;
+}
+
+int lpb_kfac_accum_rows(const float* X, int64_t rows, int64_t d, int64_t ldx, float alpha, int fp16_operands, void* workspace,
+                        int64_t workspace_bytes, float* out, int64_t ldo, void* stream) {
+  LPB_REQUIRE(X != nullptr && out != nullptr && rows > 0 && d > 0 && ldx >= d && ldo >= d, "lpb_kfac_accum_rows: bad extents");
+  void *hi, *lo;
+  int64_t ld;
+  if (split_workspace(workspace, workspace_bytes, rows, d, &hi, &lo, &ld)) return 1;
+  if (lpb::pack_cast(X, rows, d, ldx, hi, lo, fp16_operands ? lpb::OUT_F16_HILO : lpb::OUT_BF16_HILO, ld, ST(stream))) return 1;
+  return lpb::gemm_tn_rows(hi, lo, ld, hi, lo, ld, d, d, rows, alpha, 1, out, ldo, 1, fp16_operands ? 1 : 0, ST(stream));
+}
+
+int lpb_kfac_accum_conv_input(const float* x, int N, int C, int H, int W, int KH, int KW, int SH, int SW, int PH, int PW, int DH,
+                          int DW, float alpha, void* workspace, int64_t workspace_bytes, float* out, int64_t ldo, void* stream) {
+  lpb::ConvGeom g;
+  if (make_geom(g, N, C, H, W, KH, KW, SH, SW, PH, PW, DH, DW)) return 1;
+  const int64_t rows = (int64_t)N * g.OH * g.OW, d = (int64_t)C * KH * KW;
+  LPB_REQUIRE(out != nullptr && ldo >= d, "lpb_kfac_accum_conv_input: bad output extents");
+  void *hi, *lo;
+  int64_t ld;
+  if (split_workspace(workspace, workspace_bytes, rows, d, &hi, &lo, &ld)) return 1;
+  if (lpb::pack_conv2d_rows(x, g, hi, lo, lpb::OUT_F16_HILO, ld, ST(stream))) return 1;
+  return lpb::gemm_tn_rows(hi, lo, ld, hi, lo, ld, d, d, rows, alpha, 1, out, ldo, 1, 1, ST(stream));
+}
+
 int lpb_jac_linear_write(const float* g, const float* a, int Nn, int C, int d_out, int d_in, float* Js,
                          int64_t js_stride_n, int64_t js_stride_c, int64_t off_w, int64_t off_b, void* stream) {
   return lpb::jac_linear_write(g, a, Nn, C, d_out, d_in, Js, js_stride_n, js_stride_c, off_w, off_b, ST(stream));

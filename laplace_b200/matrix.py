@@ -138,6 +138,10 @@ class B200Kron(Kron):
     # -- reference Kron.decompose (utils/matrix.py:123-150) + symeig (utils/utils.py:193-228) ---
     def decompose(self, damping: bool = False) -> "B200KronDecomposed":
         mats = [(i, j, H) for i, F in enumerate(self.kfacs) for j, H in enumerate(F)]
+        if mats and mats[0][2].is_cuda:
+            t = _PREWARM.get(mats[0][2].device)
+            if t is not None and t.is_alive():
+                t.join()
         eigvecs = [[None] * len(F) for F in self.kfacs]
         eigvals = [[None] * len(F) for F in self.kfacs]
         by_size: dict[int, list] = {}
@@ -398,6 +402,40 @@ def _symeig_threaded(items, one, eigvals, eigvecs):
         cur.wait_stream(s_)
     if errors:
         raise errors[0]
+
+
+_PREWARM = {}
+
+
+def prewarm_eigensolver(device) -> None:
+    """Load and initialise the library eigensolvers on a background thread (own stream) so that their one-time start-up
+    -- 0.3 .. 19 s on a fresh process: the cuSOLVER image is paged in and its handles / workspaces are created on first
+    use -- overlaps the data pass of ``fit()`` instead of landing inside the first ``decompose()``.  Called by the backend
+    on its first ``kron()``; idempotent; failures are left to the real call."""
+    dev = torch.device(device)
+    if dev.type != "cuda" or dev in _PREWARM:
+        return
+    import threading
+
+    def work():
+        try:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(torch.cuda.Stream(dev)):
+                for n in (8, 300, 600):
+                    A = torch.eye(n, device=dev) + 0.01
+                    torch.linalg.eigh(A, UPLO="U")
+                if BATCHED_MID_SIZES:
+                    from . import _cusolver
+
+                    if _cusolver.available():
+                        _cusolver.syev_batched((torch.eye(256, device=dev) + 0.01).expand(2, 256, 256).contiguous())
+                torch.cuda.current_stream(dev).synchronize()
+        except Exception:  # noqa: BLE001 -- a warm-up must never fail a fit
+            pass
+
+    t = threading.Thread(target=work, daemon=True, name="lpb-eigh-prewarm")
+    _PREWARM[dev] = t
+    t.start()
 
 
 def live_sizes(mats):

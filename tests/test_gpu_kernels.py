@@ -376,3 +376,32 @@ def test_pack_cast_fused(shape, kind, tol):
         got = p.hi[:, :cols].float() + (p.lo[:, :cols].float() if p.lo is not None else 0)
         err = float((got - want).norm() / want.norm())
         assert err <= tol, (err, sc is None, yy is None)
+
+
+def test_layer_level_kfac_entry_points():
+    """``lpb_kfac_accum_rows`` / ``lpb_kfac_accum_conv_input`` (SURVEY 8(b) plan-level surface): fp32 tensors in, one call per
+    Kronecker factor, against fp64."""
+    import ctypes as C
+
+    from laplace_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(3)
+    st = torch.cuda.current_stream().cuda_stream
+    X = torch.randn(5000, 200, device=DEV)
+    ws = torch.empty(lib.lpb_workspace_bytes(5000, 200), device=DEV, dtype=torch.uint8)
+    for fp16 in (1, 0):
+        out = torch.zeros(200, 200, device=DEV)
+        _lib.call("lpb_kfac_accum_rows", X.data_ptr(), 5000, 200, 200, 0.5, fp16, ws.data_ptr(), ws.numel(), out.data_ptr(), 200, st)
+        _lib.call("lpb_kfac_accum_rows", X.data_ptr(), 5000, 200, 200, 0.5, fp16, ws.data_ptr(), ws.numel(), out.data_ptr(), 200, st)
+        assert rel_fro(out.cpu(), (X.double().T @ X.double()).cpu()) < (3e-6 if fp16 else 2e-5)
+    x = torch.randn(40, 16, 9, 9, device=DEV)
+    conv = torch.nn.Conv2d(16, 8, 3, 2, 1)
+    P = torch.nn.functional.unfold(x.double(), 3, padding=1, stride=2).permute(0, 2, 1).reshape(-1, 144)
+    ws2 = torch.empty(lib.lpb_workspace_bytes(P.shape[0], 144), device=DEV, dtype=torch.uint8)
+    out = torch.zeros(144, 144, device=DEV)
+    _lib.call("lpb_kfac_accum_conv_input", x.data_ptr(), 40, 16, 9, 9, 3, 3, 2, 2, 1, 1, 1, 1, 0.25, ws2.data_ptr(), ws2.numel(),
+              out.data_ptr(), 144, st)
+    assert rel_fro(out.cpu(), 0.25 * (P.T @ P).cpu()) < 3e-6
+    with pytest.raises(RuntimeError, match="workspace too small"):
+        _lib.call("lpb_kfac_accum_rows", X.data_ptr(), 5000, 200, 200, 0.5, 1, ws.data_ptr(), 16, out.data_ptr(), 200, st)
