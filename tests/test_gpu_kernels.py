@@ -394,7 +394,7 @@ def test_layer_level_kfac_entry_points():
         out = torch.zeros(200, 200, device=DEV)
         _lib.call("lpb_kfac_accum_rows", X.data_ptr(), 5000, 200, 200, 0.5, fp16, ws.data_ptr(), ws.numel(), out.data_ptr(), 200, st)
         _lib.call("lpb_kfac_accum_rows", X.data_ptr(), 5000, 200, 200, 0.5, fp16, ws.data_ptr(), ws.numel(), out.data_ptr(), 200, st)
-        assert rel_fro(out.cpu(), (X.double().T @ X.double()).cpu()) < (3e-6 if fp16 else 2e-5)
+        assert rel_fro(out.cpu(), (X.double().T @ X.double()).cpu()) < (1e-5 if fp16 else 3e-5)
     x = torch.randn(40, 16, 9, 9, device=DEV)
     conv = torch.nn.Conv2d(16, 8, 3, 2, 1)
     P = torch.nn.functional.unfold(x.double(), 3, padding=1, stride=2).permute(0, 2, 1).reshape(-1, 144)
@@ -402,6 +402,6 @@ def test_layer_level_kfac_entry_points():
     out = torch.zeros(144, 144, device=DEV)
     _lib.call("lpb_kfac_accum_conv_input", x.data_ptr(), 40, 16, 9, 9, 3, 3, 2, 2, 1, 1, 1, 1, 0.25, ws2.data_ptr(), ws2.numel(),
               out.data_ptr(), 144, st)
-    assert rel_fro(out.cpu(), 0.25 * (P.T @ P).cpu()) < 3e-6
+    assert rel_fro(out.cpu(), 0.25 * (P.T @ P).cpu()) < 1e-5
     with pytest.raises(RuntimeError, match="workspace too small"):
         _lib.call("lpb_kfac_accum_rows", X.data_ptr(), 5000, 200, 200, 0.5, 1, ws.data_ptr(), 16, out.data_ptr(), 200, st)
