@@ -470,6 +470,8 @@ def measure_roofline(be, K, Xs, ys, N_total, args, dev, step_fn=None):
         "relu_bwd": lambda r, a, kw: ("bytes", 8.0 * r.numel() + 4.0 * a[1].numel(), False),
         "maxpool2d_bwd": lambda r, a, kw: ("bytes", 4.0 * (r.numel() + a[0].numel()) + 8.0 * a[1].numel(), False),
         "col2im": lambda r, a, kw: ("bytes", 4.0 * (a[0].shape[0] * a[0].shape[1] + r.numel()), False),
+        "maxpool2d_bwd_pack": lambda r, a, kw: ("bytes", bytes_packed(r) - 4.0 * r.rows * r.K + 4.0 * a[0].numel() + 8.0 * a[1].numel()
+                                                + (4.0 * a[7].numel() if a[7] is not None else 0.0), False),
         # tensor-core diagonal of a convolution weight: per (sample, column) one T-deep [C_out x 9 C_in] product
         "diag_conv_sq": lambda r, a, kw: ("flops", 2.0 * a[0].rows * a[0].K * a[1].K * a[5].kernel_size[0] * a[5].kernel_size[1], True),
         "shared_weight_contract": lambda r, a, kw: ("flops", 2.0 * a[3] * a[4] * a[5] * a[6] * a[7], False),

@@ -182,6 +182,13 @@ int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const floa
                                int T, int Nn, int ncols, float scale, float* out, int64_t out_ld, int64_t js_stride_n,
                                int64_t js_stride_c, void* stream);
 
+/* max-pool reverse map FUSED with the operand split of the convolution chain in front of the pool (conv -> frozen BN -> ReLU
+ * -> max-pool, the ResNet stem): rows [(col, n, h, w), C] bf16 hi/lo = split( unpool(g) * scale[c] * (y > 0) ); g, idx, y
+ * channels-last (y = the pool's input, NULL: no mask; scale NULL: 1).  Replaces lpb_maxpool2d_bwd_nhwc + lpb_pack_cast_fused
+ * for that chain: the fp32 un-pooled gradient is never written.                                                      */
+int lpb_maxpool2d_bwd_pack_nhwc(const float* g, const int64_t* idx, const float* scale, const float* y, void* dst_hi, void* dst_lo,
+                                int64_t ld, int64_t Q, int Nb, int C, int H, int W, int OH, int OW, int k, int s, int p, void* stream);
+
 /* ---- layer-level KFAC entry points (compositions of the kernels above) ------------------------------------
  * For a caller that holds plain fp32 tensors and wants ONE call per Kronecker factor of CurvlinopsInterface.kron
  * (curvature/curvlinops.py:77-108).  `workspace`: device scratch of at least lpb_workspace_bytes(rows, d) bytes, owned by

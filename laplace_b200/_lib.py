@@ -39,6 +39,7 @@ SIGNATURES = {
     "lpb_scale_channels": [c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_vp],
     "lpb_relu_bwd": [c_vp, c_vp, c_vp, c_i64, c_int, c_vp],
     "lpb_maxpool2d_bwd": [c_vp, c_vp, c_vp, c_i64] + [c_int] * 9 + [c_vp],
+    "lpb_maxpool2d_bwd_pack_nhwc": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64] + [c_int] * 9 + [c_vp],
     "lpb_maxpool2d_bwd_nhwc": [c_vp, c_vp, c_vp, c_i64] + [c_int] * 9 + [c_vp],
     "lpb_gemm_tn_tc": [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp, c_i64, c_int, c_int,
                        c_vp],

@@ -40,6 +40,7 @@ KIND_FWD = K.F16X3    # forward pass: activations / weights sit inside fp16 rang
 # costs 1.1e-4 .. 1.8e-4 rel-fro on the KFAC B factors at batch 64 .. 256 (tools/gpu_lean_diag.py).  Kept as a measured
 # option (backend.LEAN_BACKWARD_MIN_ROWS) for batches where rows / d_out >= ~2e5.
 LEAN_BWD_MIN_ROWS = 0
+FUSE_POOL = os.environ.get("LPB_NO_POOL_FUSION") != "1"   # max-pool reverse map fused with the stem chain's operand split
 USE_IMPLICIT = os.environ.get("LPB_NO_IMPLICIT") != "1"
 USE_STRIDED = os.environ.get("LPB_NO_STRIDED") != "1"     # strided reverse passes as per-parity implicit GEMMs
 
@@ -218,6 +219,16 @@ def conv_backward_fused(g: torch.Tensor, mod: nn.Conv2d, in_shape, need_dx: bool
     convolution.  The fp32 gradients between the three modules are never materialised."""
     Q, Co = g.shape[0], g.shape[1]
     T = g.shape[2] * g.shape[3]
+    pre = STASH.get(id(mod), {}).pop("G_pre", None)
+    if pre is not None:
+        # the producer of this gradient (a fused max-pool reverse map) already emitted the masked / scaled operand rows and
+        # handed autograd a storage-less placeholder.  If anything else contributed to the gradient, autograd has summed it
+        # into a NEW tensor -- the placeholder is gone and the pre-packed rows would miss that contribution.
+        G, pass_id, ptr = pre
+        if pass_id == PASS_ID[0] and g.data_ptr() == ptr and all(st == 0 for st in g.stride()) and G.rows == Q * T:
+            return _backward_from_rows(G, Q, T, mod, in_shape, need_dx)
+        raise FusionConflict("convolution engine: the output of a fused conv/BN/ReLU chain feeds a fused max-pool AND another "
+                             "operation; use fuse_elementwise=False")
     if _is_nhwc(g) and (y is None or _is_nhwc(y)):
         y2 = None if y is None else y.permute(0, 2, 3, 1).reshape(-1, Co)
         G = K.pack_cast_fused(g.permute(0, 2, 3, 1).reshape(Q * T, Co), KIND, scale, y2)
@@ -497,9 +508,23 @@ class _Relu(torch.autograd.Function):
 
 
 class _MaxPoolBwd(torch.autograd.Function):
+    """``chain`` = ``None`` or ``(conv module, BN scale or None, pool input y)`` when the pool's input is the output of a
+    fused conv -> BN -> ReLU chain: the un-pooled gradient is then emitted as that chain's packed operand rows
+    (``maxpool2d_bwd_pack``) and autograd only carries a storage-less placeholder (see ``conv_backward_fused``)."""
+
     @staticmethod
-    def forward(g, idx, in_shape, k, s, p):
-        return K.maxpool2d_bwd(g if g.dtype == torch.float32 else g.float(), idx, in_shape, k, s, p)
+    def forward(g, idx, in_shape, k, s, p, chain):
+        g = g if g.dtype == torch.float32 else g.float()
+        cl = torch.channels_last
+        if (chain is not None and g.shape[1] % 8 == 0 and g.is_contiguous(memory_format=cl) and not g.is_contiguous()
+                and idx.is_contiguous(memory_format=cl) and chain[2].is_contiguous(memory_format=cl)
+                and idx.shape[0] * in_shape[1] * in_shape[2] * in_shape[3] < (1 << 31)):
+            cm, scale, y = chain
+            G = K.maxpool2d_bwd_pack(g, idx, in_shape, k, s, p, scale, y)
+            dummy = g.new_zeros(1).expand(g.shape[0], g.shape[1], in_shape[2], in_shape[3])
+            STASH.setdefault(id(cm), {})["G_pre"] = (G, PASS_ID[0], dummy.data_ptr())
+            return dummy
+        return K.maxpool2d_bwd(g, idx, in_shape, k, s, p)
 
     @staticmethod
     def setup_context(ctx, inputs, output):
@@ -510,29 +535,31 @@ class _MaxPoolBwd(torch.autograd.Function):
         raise NotImplementedError
 
     @staticmethod
-    def vmap(info, in_dims, g, idx, in_shape, k, s, p):
+    def vmap(info, in_dims, g, idx, in_shape, k, s, p, chain):
         g2, nb, B = _fold(g, in_dims[0])
-        out = _MaxPoolBwd.apply(g2, idx, in_shape, k, s, p)
+        out = _MaxPoolBwd.apply(g2, idx, in_shape, k, s, p, chain)
         return out.view(nb, B, *out.shape[1:]), 0
 
 
 class _MaxPool(torch.autograd.Function):
     @staticmethod
-    def forward(x, k, s, p):
+    def forward(x, k, s, p, chain):
         out, idx = torch.nn.functional.max_pool2d(x, k, s, p, return_indices=True)
         return out, idx
 
     @staticmethod
     def setup_context(ctx, inputs, output):
-        x, k, s, p = inputs
+        x, k, s, p, chain = inputs
         ctx.save_for_backward(output[1])
         ctx.mark_non_differentiable(output[1])
         ctx.geom = (tuple(x.shape), k, s, p)
+        # the chain's ReLU mask is the sign of THIS input: keep it (detached) for the fused reverse map
+        ctx.chain = None if chain is None else (chain[0], chain[1], x.detach())
 
     @staticmethod
     def backward(ctx, g, _gidx):
         in_shape, k, s, p = ctx.geom
-        return _MaxPoolBwd.apply(g, ctx.saved_tensors[0], in_shape, k, s, p), None, None, None
+        return _MaxPoolBwd.apply(g, ctx.saved_tensors[0], in_shape, k, s, p, ctx.chain), None, None, None, None
 
 
 def _pool_geom(m: nn.Module):
@@ -646,17 +673,20 @@ class patched_convs:
                 if not (usable(x) and _device_bound(x)):
                     return nn.ReLU.forward(m, x)
                 tag = getattr(x, "_lpb_tag", None)
-                if self.fuse and tag is not None and x.dim() == 4:
+                if self.fuse and tag is not None and tag[0] in ("conv", "conv_affine") and x.dim() == 4:
                     cm, xin = tag[1], tag[2]
                     STASH.setdefault(id(cm), {})["fused"] = True
-                    return _ConvAffineRelu.apply(xin, cm.weight, cm, x.detach(), tag[3] if tag[0] == "conv_affine" else None)
+                    sc = tag[3] if tag[0] == "conv_affine" else None
+                    return _tag(_ConvAffineRelu.apply(xin, cm.weight, cm, x.detach(), sc), ("chain_out", cm, sc))
                 return _Relu.apply(x)
             m.forward = relu_fwd
         for m, geom in self.pools:
             def pool_fwd(x, m=m, geom=geom):
                 if x.dim() != 4 or not usable(x) or not _device_bound(x) or x.shape[2] * x.shape[3] > 1024:
                     return nn.MaxPool2d.forward(m, x)
-                return _MaxPool.apply(x, *geom)[0]
+                tag = getattr(x, "_lpb_tag", None)
+                chain = (tag[1], tag[2]) if (self.fuse and FUSE_POOL and tag is not None and tag[0] == "chain_out") else None
+                return _MaxPool.apply(x, *geom, chain)[0]
             m.forward = pool_fwd
         return self
 

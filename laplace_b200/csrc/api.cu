@@ -44,6 +44,8 @@ int gemm_nt_bf16(const void*, const void*, int64_t, const void*, const void*, in
 int scale_channels(const float*, const float*, float*, int64_t, int, int64_t, cudaStream_t);
 int relu_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
 int maxpool2d_bwd(const float*, const int64_t*, float*, int64_t, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int maxpool2d_bwd_pack_nhwc(const float*, const int64_t*, const float*, const float*, void*, void*, int64_t, int64_t, int, int, int,
+                            int, int, int, int, int, int, cudaStream_t);
 int gemm_tn_rows(const void*, const void*, int64_t, const void*, const void*, int64_t, int64_t, int64_t, int64_t, float,
                  int, float*, int64_t, int, int, cudaStream_t);
 int conv_nhwc_bf16(const void*, const void*, int64_t, int, int, int64_t, int64_t, const void*, const void*, int64_t, int, int,
@@ -282,6 +284,12 @@ int lpb_shared_weight_contract(int mode, const float* G, int64_t ldg, const floa
   LPB_REQUIRE(T > 0 && ldg >= (int64_t)Nn * ncols * T && lda >= (int64_t)Nn * T, "lpb_shared_weight_contract: bad extents");
   return lpb::shared_weight_contract(mode, G, ldg, A, lda, d_out, d_in, T, Nn, ncols, scale, out, out_ld, js_stride_n,
                                      js_stride_c, ST(stream));
+}
+
+int lpb_maxpool2d_bwd_pack_nhwc(const float* g, const int64_t* idx, const float* scale, const float* y, void* dst_hi, void* dst_lo,
+                                int64_t ld, int64_t Q, int Nb, int C, int H, int W, int OH, int OW, int k, int s, int p, void* stream) {
+  LPB_REQUIRE(g != nullptr && idx != nullptr && dst_hi != nullptr && dst_lo != nullptr, "lpb_maxpool2d_bwd_pack_nhwc: null operand");
+  return lpb::maxpool2d_bwd_pack_nhwc(g, idx, scale, y, dst_hi, dst_lo, ld, Q, Nb, C, H, W, OH, OW, k, s, p, ST(stream));
 }
 
 int lpb_kron_conv_quadform(const float* Gt, int64_t ldg, int64_t g_stride_c, const float* At, int64_t lda, int d_out, int d_in,

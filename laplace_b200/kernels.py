@@ -515,3 +515,26 @@ def maxpool2d_bwd(g: torch.Tensor, idx: torch.Tensor, in_shape, k: int, s: int, 
     _lib.call("lpb_maxpool2d_bwd", _ptr(g), _ptr(idx), _ptr(out), Q, idx.shape[0], C, H, W, OH, OW, k, s, p, _stream())
     _bump()
     return out
+
+
+def maxpool2d_bwd_pack(g: torch.Tensor, idx: torch.Tensor, in_shape, k: int, s: int, p: int, scale: torch.Tensor | None,
+                       y: torch.Tensor | None) -> Packed:
+    """Un-pooled gradient of a max-pool times the ReLU mask ``y > 0`` and the channel ``scale``, emitted directly as bf16
+    hi/lo operand rows ``[(q, h, w), C]`` (``lpb_maxpool2d_bwd_pack_nhwc``).  ``g [Q, C, OH, OW]``, ``idx [Nb, C, OH, OW]`` and
+    ``y [Nb, C, H, W]`` channels-last."""
+    _check(g, name="g")
+    Q, C, OH, OW = g.shape
+    H, W = in_shape[-2:]
+    cl = torch.channels_last
+    assert g.is_contiguous(memory_format=cl) and idx.is_contiguous(memory_format=cl) and C % 8 == 0
+    if y is not None:
+        _check(y, name="y")
+        assert y.is_contiguous(memory_format=cl) and tuple(y.shape) == (idx.shape[0], C, H, W)
+    if scale is not None:
+        _check(scale, name="scale")
+        scale = scale.contiguous()
+    out = alloc_rows(Q * H * W, C, BF16X3, g.device)
+    _lib.call("lpb_maxpool2d_bwd_pack_nhwc", _ptr(g), _ptr(idx), _ptr(scale), _ptr(y), _ptr(out.hi), _ptr(out.lo), out.ldk, Q,
+              idx.shape[0], C, H, W, OH, OW, k, s, p, _stream())
+    _bump()
+    return out

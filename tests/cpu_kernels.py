@@ -161,6 +161,18 @@ def eigh_jacobi(A, max_sweeps=30):
     return torch.nan_to_num(L.clamp(min=0)).float(), torch.nan_to_num(Q).float()
 
 
+def maxpool2d_bwd_pack(g, idx, in_shape, k, s, p, scale, y):
+    Q, C, OH, OW = g.shape
+    H, W = in_shape[-2:]
+    Nb = idx.shape[0]
+    un = maxpool2d_bwd(g.contiguous(), idx, in_shape, k, s, p)
+    if scale is not None:
+        un = un * scale.view(1, -1, 1, 1)
+    if y is not None:
+        un = (un.reshape(Q // Nb, Nb, C, H, W) * (y > 0)).reshape(Q, C, H, W)
+    return pack_cast(un.permute(0, 2, 3, 1).reshape(Q * H * W, C).contiguous(), K.BF16X3)
+
+
 def kron_conv_quadform(Gt, At, T, Nn, C, l1, l2, delta, damping, out):
     d_out, d_in = Gt.shape[0], At.shape[0]
     G = Gt[:, :C * Nn * T].reshape(d_out, C, Nn, T).double()
@@ -182,7 +194,7 @@ def install(monkeypatch):
     for name in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "shared_weight_contract", "jac_linear_write",
                  "ll_jacobian_write", "batched_pair_dot", "ll_ggn_expand", "ll_sigma_gather", "eigh_jacobi",
                  "pack_conv_rows", "pack_nchw_rows", "pack_cast", "pack_cast_fused", "col2im", "col2im_nhwc", "syrk_conv_patches", "diag_conv_sq", "conv_bwd_strided", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd",
-                 "kron_conv_quadform"):
+                 "kron_conv_quadform", "maxpool2d_bwd_pack"):
         monkeypatch.setattr(K, name, globals()[name])
     monkeypatch.setattr(K, "alloc_packed", _alloc)
     monkeypatch.setattr(K, "alloc_rows", _alloc)

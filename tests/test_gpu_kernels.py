@@ -317,6 +317,30 @@ def test_maxpool_backward_kernel(geom):
     assert gotc.is_contiguous(memory_format=cl) and torch.allclose(gotc, ref, atol=1e-6)
 
 
+@pytest.mark.parametrize("geom", [(3, 2, 1, 16, 64), (2, 2, 0, 8, 8), (3, 1, 1, 7, 16), (3, 2, 1, 9, 24)])
+@pytest.mark.parametrize("with_scale,with_mask", [(True, True), (False, True), (True, False)])
+def test_maxpool_backward_fused_with_operand_split(geom, with_scale, with_mask):
+    """``maxpool2d_bwd_pack``: un-pool + ReLU mask + BN scale + bf16 hi/lo split in one pass == the three separate kernels."""
+    k, s, p, hw, C = geom
+    torch.manual_seed(13)
+    cl = torch.channels_last
+    x = torch.randn(4, C, hw, hw, device=DEV).contiguous(memory_format=cl)
+    out, idx = torch.nn.functional.max_pool2d(x, k, s, p, return_indices=True)
+    g = torch.randn(3 * 4, C, *out.shape[2:], device=DEV).contiguous(memory_format=cl)
+    scale = (torch.rand(C, device=DEV) + 0.5) if with_scale else None
+    y = torch.relu(x) if with_mask else None
+    P = K.maxpool2d_bwd_pack(g, idx.contiguous(memory_format=cl), x.shape, k, s, p, scale, y)
+    un = K.maxpool2d_bwd(g, idx.contiguous(memory_format=cl), x.shape, k, s, p)
+    if scale is not None:
+        un = un * scale.view(1, -1, 1, 1)
+    if y is not None:
+        un = (un.reshape(3, 4, C, hw, hw) * (y > 0)).reshape(12, C, hw, hw)
+    ref = un.permute(0, 2, 3, 1).reshape(-1, C)
+    got = P.hi[:, :C].float() + P.lo[:, :C].float()
+    assert P.kind == K.BF16X3 and P.rows == 12 * hw * hw
+    assert rel_fro(got, ref) < 2e-5 and torch.equal(P.hi[:, :C], ref.bfloat16())
+
+
 @pytest.mark.parametrize("M,N,Kc", [(256, 256, 64), (256, 256, 4096), (513, 257, 2048), (300, 300, 40000), (1000, 1000, 512),
                                     (1152, 1152, 3000), (640, 2000, 130), (64, 64, 300000)])
 @pytest.mark.parametrize("kind,tol", [(K.BF16, 6e-3), (K.BF16X3, 3e-5), (K.F16X3, 1e-5)])

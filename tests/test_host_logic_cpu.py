@@ -134,13 +134,20 @@ def test_convolution_engine_paths_on_model_zoo(cpu_kernels, monkeypatch, name, k
     passes, functorch-batched columns, factor SYRKs from the stashed rows) == oracle, on reduced model shapes."""
     from laplace_b200 import conv_engine, models
 
+    from laplace_b200 import kernels as K
+
     monkeypatch.setattr(conv_engine, "ELEMENTWISE_MIN_BATCH", 0)
+    pool_packs = []
+    orig_pack = K.maxpool2d_bwd_pack
+    monkeypatch.setattr(K, "maxpool2d_bwd_pack", lambda *a, **k: (pool_packs.append(1), orig_pack(*a, **k))[1])
     model = models.make(name, **kw)
     torch.manual_seed(0)
     X, y = torch.randn(4, 3, 32, 32), torch.randint(10, (4,))
     be = B200GGN(model, "classification")
     _, kron = be.kron(X, y, N=4)
     assert be.last_backward_mode == "batched"
+    # torchvision stem (conv -> BN -> ReLU -> max-pool): the pool's reverse map emits the chain's operand rows directly
+    assert bool(pool_packs) == (name == "resnet18" and not kw.get("cifar_stem"))
     # conv -> frozen BN -> ReLU chains run as one fused reverse node; the reduced WideResNet adds the raw stem output
     # to a residual (a second consumer of a fused intermediate): detected, repeated unfused, and remembered
     assert be.fuse_elementwise == (name != "wrn28_10")
@@ -377,3 +384,41 @@ def test_gp_kernels_match_reference_einsums(golden, cpu_kernels, kind, lazy):
     assert rel_fro(gp.kernel_batch(J1, J2, independent_outputs=True), indep) < 1e-5
     assert rel_fro(gp.kernel_star(J1, independent_outputs=True), (Ja ** 2).sum(-1)) < 1e-5
     model.double()
+
+
+def test_fused_pool_conflict_falls_back(cpu_kernels, monkeypatch):
+    """A fused conv -> BN -> ReLU chain whose output feeds a fused max-pool AND a second operation: the pool's pre-packed
+    rows would miss the second contribution -- detected (the placeholder gradient was replaced by a sum), the batch is
+    repeated unfused, the factors match the oracle."""
+    from laplace_b200 import conv_engine
+
+    monkeypatch.setattr(conv_engine, "ELEMENTWISE_MIN_BATCH", 0)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 8, 3, 1, 1, bias=False)
+            self.bn = torch.nn.BatchNorm2d(8)
+            self.relu = torch.nn.ReLU()
+            self.pool = torch.nn.MaxPool2d(3, 2, 1)
+            self.conv2 = torch.nn.Conv2d(8, 8, 3, 1, 1)
+            self.fc = torch.nn.Linear(8, 3)
+
+        def forward(self, x):
+            h = self.relu(self.bn(self.conv(x)))
+            z = self.pool(h) + torch.nn.functional.avg_pool2d(h, 2)      # second consumer of the chain output
+            return self.fc(torch.tanh(self.conv2(z)).mean((2, 3)))
+
+    torch.manual_seed(4)
+    net = Net().eval()
+    net.bn.running_mean.normal_(0, 0.1), net.bn.running_var.uniform_(0.5, 1.5)
+    for p_ in net.bn.parameters():
+        p_.requires_grad_(False)
+    X, y = torch.randn(6, 3, 8, 8), torch.randint(3, (6,))
+    be = B200GGN(net, "classification")
+    _, kron = be.kron(X, y, N=6)
+    assert be.fuse_elementwise is False and not be._fused
+    _, kf = co.kfac_factors(net.double(), "classification", X.double(), y, N=6)
+    net.float()
+    worst = max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo))
+    assert worst < 1e-5, worst
