@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-samples", type=int, default=256, help="samples of the bounded CPU-baseline run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predictive", action="store_true", help="skip the GLM-predictive legs")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="run every kron() step eagerly (default: the step is captured "
+                    "into a CUDA graph after two eager calls and replayed, backend_kwargs={'cuda_graph': True})")
     ap.add_argument("--model-tf32", action="store_true", help="let cuDNN/cuBLAS use TF32 in the model's own passes")
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0 = min(cores, 16), the measured optimum)")
     return ap.parse_args()
@@ -200,7 +202,7 @@ def run_ours(args):
     B, Ksteps, W = args.batch, args.steps, max(3, args.warmup)
     N_total = 50000
     model = make_model(args.model).to(dev)
-    be_kwargs = {"precision": args.precision, "model_tf32": args.model_tf32}
+    be_kwargs = {"precision": args.precision, "model_tf32": args.model_tf32, "cuda_graph": not args.no_cuda_graph}
     be = B200GGN(model, "classification", **be_kwargs)
     shape = input_shape(args.model)
     torch.manual_seed(1 + rank)
@@ -236,10 +238,11 @@ def run_ours(args):
     def step(i):
         nonlocal H
         _, kr = be.kron(Xs[i % n_batches], ys[i % n_batches], N=N_total)
-        if H is None:
-            H = kr
-        else:
-            H += kr
+        if H is None:        # own accumulator: with cuda_graph the returned factors are the graph's static output buffers
+            from laplace_b200 import B200Kron
+
+            H = B200Kron.zeros(kr.dims(), dev, torch.float32)
+        H += kr
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -351,7 +354,8 @@ def run_ours(args):
     del Hd
 
     # ---------------- roofline of the dominant kernel (separate short pass, CUDA events around each launch) -----
-    roof = measure_roofline(be, K, Xs, ys, N_total, args, dev)
+    # per-launch CUDA events need eager launches: same backend settings without the graph replay
+    roof = measure_roofline(B200GGN(model, "classification", **{**be_kwargs, "cuda_graph": False}), K, Xs, ys, N_total, args, dev)
 
     # The legs below annotate the line (predictive, small-batch line, the contraction kernel alone); a failure in one of
     # them must not lose the headline measurement, so each is recorded as an error string instead.
@@ -365,7 +369,13 @@ def run_ours(args):
     if not args.no_predictive:
         leg("predictive", lambda: pred.update(measure_predictive(model, dev, world, timed, args)))
     if rank == 0 and world == 1 and args.model == "resnet18":
-        leg("b512", lambda: extras.__setitem__("batch_512", measure_small_batch(be, dev, shape, N_total)))
+        def b512():
+            res = {"cuda_graph" if be.cuda_graph else "eager": measure_small_batch(be, dev, shape, N_total)}
+            other = B200GGN(model, "classification", **{**be_kwargs, "cuda_graph": not be.cuda_graph})
+            res["cuda_graph" if other.cuda_graph else "eager"] = measure_small_batch(other, dev, shape, N_total)
+            extras["batch_512"] = res
+
+        leg("b512", b512)
     if rank == 0 and world == 1:
         leg("jtj_syrk_kernel", lambda: extras.__setitem__("jtj_syrk_kernel", measure_syrk_probe(K, dev)))
 
@@ -385,6 +395,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "batch_per_gpu": B, "global_batch": B * world, "N_dataset": N_total,
                        "parallelism": f"dp{world}", "precision": args.precision,
+                       "cuda_graph": "kron() step captured after 2 eager calls and replayed (backend_kwargs cuda_graph=True)"
+                       if not args.no_cuda_graph else "off (eager launches)",
                        "model_passes": "tf32 (PyTorch default)" if args.model_tf32 else "fp32 (TF32 disabled in cuDNN/cuBLAS)",
                        "l2": "distinct batch every step; per-step working set (factor buffers 376 MB + staging) exceeds the 126 MB L2",
                        "exchange": exchange, "e2e_api": api, **extras},
@@ -406,10 +418,14 @@ def measure_small_batch(be, dev, shape, N_total, B=512, steps=10):
     torch.manual_seed(11)
     Xs = [torch.randn(B, *shape, device=dev) for _ in range(4)]
     ys = [torch.randint(10, (B,), device=dev) for _ in range(4)]
+    from laplace_b200 import B200Kron
+
     H = None
-    for i in range(3):
+    for i in range(4):
         _, k = be.kron(Xs[i % 4], ys[i % 4], N=N_total)
-        H = k if H is None else H.__iadd__(k)
+        if H is None:
+            H = B200Kron.zeros(k.dims(), dev, torch.float32)
+        H += k
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()

@@ -82,7 +82,7 @@ class _B200Mixin:
     """Shared machinery of the GGN and EF flavours."""
 
     def _b200_init(self, precision: str = "auto", batched_backward: bool = True, model_tf32: bool = False,
-                   conv_engine: bool = True, fuse_elementwise: bool = True):
+                   conv_engine: bool = True, fuse_elementwise: bool = True, cuda_graph: bool = False):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.precision = precision
@@ -92,6 +92,10 @@ class _B200Mixin:
         # KFAC path only: reverse pass of conv -> frozen BN -> ReLU chains as one node per convolution (conv_engine.py)
         self.fuse_elementwise = fuse_elementwise
         self._fused = False
+        # kron(): replay a captured CUDA graph of the whole step once the same (shapes, N, kwargs, parameter versions) has
+        # run eagerly twice (opt-in: a model whose forward branches on data would be frozen on the captured branch)
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs: dict = {}
         # KFAC path: input (A) factors on a side stream, concurrent with the reverse pass
         import os
 
@@ -405,6 +409,60 @@ class _B200Mixin:
         if reduce and rows.shape[1] > 1:
             rows = rows.sum(1, keepdim=True)
         return K.pack_rows(rows.reshape(-1, g.shape[-1]).contiguous(), kind)
+
+    # ------------------------------------------------------------------ KFAC through a captured CUDA graph
+    GRAPH_WARMUP_CALLS = 2
+
+    def _state_key(self):
+        """Versions of everything the captured step reads through cached host-side state (packed weights, folded BN
+        affines): an optimiser step between two ``kron()`` calls (``marglik_training``) must trigger a fresh capture."""
+        return tuple((t.data_ptr(), t._version) for t in list(self.model.parameters()) + list(self.model.buffers()))
+
+    def _kron_graphed(self, x, y, N, cols_fn, weight, kfac_approx):
+        """One ``kron()`` step at B <= 1024 is bound by the host (~1500 kernel launches plus the functorch dispatch of the
+        custom autograd Functions: 13 ms at B = 512 against 4 ms of device time).  The step has static shapes and no host
+        synchronisation, so after ``GRAPH_WARMUP_CALLS`` eager calls with the same key it is captured once (forward, column-
+        batched reverse pass, packs, SYRKs, side stream included) and replayed: inputs are copied into the graph's static
+        buffers, the returned loss / ``B200Kron`` ARE the graph's static outputs -- consume them (``la.H += H_batch``,
+        baselaplace.py:985) before the next call.  Any failure to capture falls back to eager for good."""
+        if not (self.cuda_graph and torch.is_tensor(x) and x.is_cuda and torch.is_tensor(y)):
+            return self._kron_impl(x, y, N, cols_fn, weight, kfac_approx)
+        key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, float(N), kfac_approx, float(weight), self.precision,
+               self.fuse_elementwise, self._state_key())
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) > 8:
+                self._graphs.clear()       # parameter versions moved on (training): drop stale captures
+            ent = self._graphs[key] = {"calls": 0, "graph": None}
+        if ent["graph"] is False:
+            return self._kron_impl(x, y, N, cols_fn, weight, kfac_approx)
+        if ent["graph"] is None:
+            ent["calls"] += 1
+            if ent["calls"] <= self.GRAPH_WARMUP_CALLS:
+                return self._kron_impl(x, y, N, cols_fn, weight, kfac_approx)
+            try:
+                sx, sy = torch.empty_like(x), torch.empty_like(y.to(x.device))
+                sx.copy_(x), sy.copy_(y)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = K.LAUNCHES
+                with torch.cuda.graph(g):
+                    out = self._kron_impl(sx, sy, N, cols_fn, weight, kfac_approx)
+                ent.update(graph=g, x=sx, y=sy, out=out, launches=K.LAUNCHES - n0)
+                K._bump(-ent["launches"])       # capturing launched nothing; every replay launches them all
+            except Exception as e:  # noqa: BLE001 -- capture is an optimisation; say why it is off and carry on eagerly
+                import warnings
+
+                torch.cuda.synchronize()
+                ent["graph"] = False
+                warnings.warn(f"laplace_b200: CUDA-graph capture of kron() failed ({type(e).__name__}: {str(e)[:200]}); "
+                              "running eagerly")
+                return self._kron_impl(x, y, N, cols_fn, weight, kfac_approx)
+        ent["x"].copy_(x, non_blocking=True)
+        ent["y"].copy_(y, non_blocking=True)
+        ent["graph"].replay()
+        K._bump(ent["launches"])                # the graph's kernel nodes (bench.py reports launches of native kernels)
+        return ent["out"]
 
     # ------------------------------------------------------------------ KFAC
     def _kron_impl(self, x, y, N, cols_fn, weight: float, kfac_approx: str = "expand"):
@@ -875,10 +933,10 @@ class B200GGN(_B200Mixin, GGNInterface):
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
                  dict_key_y="labels", stochastic=False, num_samples=1, precision="auto", batched_backward=True,
-                 model_tf32=False, conv_engine=True, fuse_elementwise=True):
+                 model_tf32=False, conv_engine=True, fuse_elementwise=True, cuda_graph=False):
         GGNInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y,
                               stochastic, num_samples)
-        self._b200_init(precision, batched_backward, model_tf32, conv_engine, fuse_elementwise)
+        self._b200_init(precision, batched_backward, model_tf32, conv_engine, fuse_elementwise, cuda_graph)
 
     def _ggn_cols(self, f, y=None):
         return self._mc_cols(f, self.num_samples) if self.stochastic else self._hessian_sqrt_cols(f)
@@ -901,7 +959,7 @@ class B200GGN(_B200Mixin, GGNInterface):
             sq2 = 2.0 if self.likelihood == "regression" else 1.0   # MSE-sum Hessian is 2 I
             return self._kron_impl(x, y, N, lambda f, yy: self._mc_cols(f, S) * math.sqrt(S * sq2), 1.0 / S, approx)
         sq2 = math.sqrt(2.0) if self.likelihood == "regression" else 1.0
-        return self._kron_impl(x, y, N, lambda f, yy: self._hessian_sqrt_cols(f) * sq2, 1.0, approx)
+        return self._kron_graphed(x, y, N, lambda f, yy: self._hessian_sqrt_cols(f) * sq2, 1.0, approx)
 
     def full(self, x, y, **kwargs: Any):
         """``GGNInterface.full`` (curvature/curvature.py:375-411): ``H = sum_n J_n^T L_n J_n``; loss = factor * loss;
@@ -975,13 +1033,13 @@ class B200EF(_B200Mixin, EFInterface):
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None, dict_key_x="input_ids",
                  dict_key_y="labels", precision="auto", batched_backward=True, model_tf32=False, conv_engine=True,
-                 fuse_elementwise=True):
+                 fuse_elementwise=True, cuda_graph=False):
         EFInterface.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y)
-        self._b200_init(precision, batched_backward, model_tf32, conv_engine, fuse_elementwise)
+        self._b200_init(precision, batched_backward, model_tf32, conv_engine, fuse_elementwise, cuda_graph)
 
     def kron(self, x, y, N, **kwargs: Any):
         """``CurvlinopsInterface.kron`` with ``FisherType.EMPIRICAL`` (curvature/curvlinops.py:174-176)."""
-        return self._kron_impl(x, y, N, self._loss_grad_cols, 1.0, kwargs.get("kfac_approx", "expand"))
+        return self._kron_graphed(x, y, N, self._loss_grad_cols, 1.0, kwargs.get("kfac_approx", "expand"))
 
     def full(self, x, y, **kwargs: Any):
         """``EFInterface.full`` (curvature/curvature.py:467-493): ``factor * sum_n g_n g_n^T``."""

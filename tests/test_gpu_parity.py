@@ -310,3 +310,39 @@ def test_config1_mlp_parity_anchor():
     err_e2e = float((f_var.cpu().double() - ref).abs().max() / ref.abs().max())
     assert err_e2e < VAR_TOL, f"end-to-end predictive variance error {err_e2e:.2e}"
     assert torch.allclose(f_mu.cpu().double(), f, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,kw,B,shape", [("mlp", {}, 64, (784,)), ("resnet18", {"width": 16}, 32, (3, 32, 32))])
+def test_kron_cuda_graph_replay_matches_eager(name, kw, B, shape):
+    """``cuda_graph=True``: after two eager calls the whole ``kron()`` step (forward, column-batched reverse pass, packs,
+    SYRKs, side stream) is captured once and replayed -- same factors as the eager backend on NEW batches, a fresh capture
+    after the parameters change (``marglik_training`` updates them between fits), EF flavour included."""
+    from laplace_b200 import conv_engine
+
+    model = models.make(name, **kw).to(DEV)
+    torch.manual_seed(6)
+    Xs = [torch.randn(B, *shape, device=DEV) for _ in range(5)]
+    ys = [torch.randint(10, (B,), device=DEV) for _ in range(5)]
+    keep = conv_engine.ELEMENTWISE_MIN_BATCH
+    conv_engine.ELEMENTWISE_MIN_BATCH = 0          # fused chains / custom reverse maps inside the captured step
+    try:
+        for cls in (B200GGN, B200EF):
+            eager, graphed = cls(model, "classification"), cls(model, "classification", cuda_graph=True)
+            for i, (X, y) in enumerate(zip(Xs, ys)):
+                le, ke = eager.kron(X, y, N=500)
+                lg, kg = graphed.kron(X, y, N=500)
+                assert torch.allclose(lg, le, rtol=1e-6)
+                worst = max(rel_fro(a, b) for Fa, Fb in zip(kg.kfacs, ke.kfacs) for a, b in zip(Fa, Fb))
+                assert worst < 2e-6, (i, worst)
+            ent = list(graphed._graphs.values())
+            assert len(ent) == 1 and ent[0]["graph"] not in (None, False), "the step was not captured"
+            with torch.no_grad():                      # an optimiser step between two fits
+                for p in model.parameters():
+                    if p.requires_grad:
+                        p.mul_(1.01)
+            le, ke = eager.kron(Xs[0], ys[0], N=500)
+            lg, kg = graphed.kron(Xs[0], ys[0], N=500)
+            assert len(graphed._graphs) == 2            # new parameter versions -> new key (eager again, then re-captured)
+            assert max(rel_fro(a, b) for Fa, Fb in zip(kg.kfacs, ke.kfacs) for a, b in zip(Fa, Fb)) < 2e-6
+    finally:
+        conv_engine.ELEMENTWISE_MIN_BATCH = keep
