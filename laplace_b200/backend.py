@@ -151,8 +151,13 @@ class _B200Mixin:
             )
 
     def _make_hook(self, name):
+        import weakref
+
+        ref = weakref.ref(self)     # the module must not keep the backend (and its captured graphs / buffers) alive
+
         def hook(mod, inp, out):
-            if self._capturing:
+            self = ref()
+            if self is not None and self._capturing:
                 if name in self._outs:
                     # the reference's hook-based KFAC sums the contributions of every call; this backend captures one
                     # (input, output) pair per module, so say so instead of silently keeping the last call only
@@ -162,6 +167,13 @@ class _B200Mixin:
                 self._outs[name] = out
                 self._out_state[name] = (out._version, out.grad_fn)
         return hook
+
+    def __del__(self):
+        for h in getattr(self, "_hooks", ()):
+            try:
+                h.remove()
+            except Exception:  # noqa: BLE001 -- interpreter shutdown
+                pass
 
     # in-place ops that leave d(result)/d(tensor) = identity: the gradient w.r.t. the modified tensor IS the gradient
     # w.r.t. the layer output (e.g. torchvision's ``out += identity``)
@@ -424,7 +436,11 @@ class _B200Mixin:
         synchronisation, so after ``GRAPH_WARMUP_CALLS`` eager calls with the same key it is captured once (forward, column-
         batched reverse pass, packs, SYRKs, side stream included) and replayed: inputs are copied into the graph's static
         buffers, the returned loss / ``B200Kron`` ARE the graph's static outputs -- consume them (``la.H += H_batch``,
-        baselaplace.py:985) before the next call.  Any failure to capture falls back to eager for good."""
+        baselaplace.py:985) before the next call.  Any failure to capture falls back to eager for good (and restores torch's
+        CUDA generator, which an aborted capture leaves in capture mode).  Known case (r02, tools/gpu_graph_diag.py): a second,
+        eager, fusing backend on the SAME model instance called in strict alternation with this one invalidates the capture
+        (cudaErrorStreamCaptureInvalidated; cause not identified) -- any other interleaving, separate model instances, or
+        one backend per model (what ``Laplace(...)`` does) capture fine."""
         if not (self.cuda_graph and torch.is_tensor(x) and x.is_cuda and torch.is_tensor(y)):
             return self._kron_impl(x, y, N, cols_fn, weight, kfac_approx)
         key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, float(N), kfac_approx, float(weight), self.precision,
@@ -441,12 +457,24 @@ class _B200Mixin:
             if ent["calls"] <= self.GRAPH_WARMUP_CALLS:
                 return self._kron_impl(x, y, N, cols_fn, weight, kfac_approx)
             try:
+                from .matrix import wait_prewarm
+
+                wait_prewarm(x.device)     # library start-up on another thread (cudaMalloc ...) would invalidate the capture
+                if self.conv_engine:
+                    from . import conv_engine as _ceq
+
+                    _ceq.STASH.clear()     # operands another backend's step left behind are released OUTSIDE the capture
+                import gc
+
+                gc.collect()
+                rng_state = torch.cuda.get_rng_state(x.device)
                 sx, sy = torch.empty_like(x), torch.empty_like(y.to(x.device))
                 sx.copy_(x), sy.copy_(y)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 n0 = K.LAUNCHES
-                with torch.cuda.graph(g):
+                # thread_local: loader / prefetch threads of the host program may keep calling CUDA while we capture
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     out = self._kron_impl(sx, sy, N, cols_fn, weight, kfac_approx)
                 ent.update(graph=g, x=sx, y=sy, out=out, launches=K.LAUNCHES - n0)
                 K._bump(-ent["launches"])       # capturing launched nothing; every replay launches them all
@@ -455,6 +483,11 @@ class _B200Mixin:
 
                 torch.cuda.synchronize()
                 ent["graph"] = False
+                try:    # an aborted capture leaves torch's CUDA generator in capture mode ("Offset increment outside graph
+                    torch.cuda.manual_seed(0)                      # capture"): re-seeding clears it, then the state is restored
+                    torch.cuda.set_rng_state(rng_state, x.device)
+                except Exception:  # noqa: BLE001
+                    pass
                 warnings.warn(f"laplace_b200: CUDA-graph capture of kron() failed ({type(e).__name__}: {str(e)[:200]}); "
                               "running eagerly")
                 return self._kron_impl(x, y, N, cols_fn, weight, kfac_approx)

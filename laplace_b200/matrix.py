@@ -139,9 +139,7 @@ class B200Kron(Kron):
     def decompose(self, damping: bool = False) -> "B200KronDecomposed":
         mats = [(i, j, H) for i, F in enumerate(self.kfacs) for j, H in enumerate(F)]
         if mats and mats[0][2].is_cuda:
-            t = _PREWARM.get(mats[0][2].device)
-            if t is not None and t.is_alive():
-                t.join()
+            wait_prewarm(mats[0][2].device)
         eigvecs = [[None] * len(F) for F in self.kfacs]
         eigvals = [[None] * len(F) for F in self.kfacs]
         by_size: dict[int, list] = {}
@@ -436,6 +434,12 @@ def prewarm_eigensolver(device) -> None:
     t = threading.Thread(target=work, daemon=True, name="lpb-eigh-prewarm")
     _PREWARM[dev] = t
     t.start()
+
+
+def wait_prewarm(device) -> None:
+    t = _PREWARM.get(torch.device(device))
+    if t is not None and t.is_alive():
+        t.join()
 
 
 def live_sizes(mats):

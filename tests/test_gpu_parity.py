@@ -319,7 +319,10 @@ def test_kron_cuda_graph_replay_matches_eager(name, kw, B, shape):
     after the parameters change (``marglik_training`` updates them between fits), EF flavour included."""
     from laplace_b200 import conv_engine
 
+    import copy
+
     model = models.make(name, **kw).to(DEV)
+    model_e = copy.deepcopy(model)                 # the eager reference runs on its own instance (see _kron_graphed's note)
     torch.manual_seed(6)
     Xs = [torch.randn(B, *shape, device=DEV) for _ in range(5)]
     ys = [torch.randint(10, (B,), device=DEV) for _ in range(5)]
@@ -327,7 +330,7 @@ def test_kron_cuda_graph_replay_matches_eager(name, kw, B, shape):
     conv_engine.ELEMENTWISE_MIN_BATCH = 0          # fused chains / custom reverse maps inside the captured step
     try:
         for cls in (B200GGN, B200EF):
-            eager, graphed = cls(model, "classification"), cls(model, "classification", cuda_graph=True)
+            eager, graphed = cls(model_e, "classification"), cls(model, "classification", cuda_graph=True)
             for i, (X, y) in enumerate(zip(Xs, ys)):
                 le, ke = eager.kron(X, y, N=500)
                 lg, kg = graphed.kron(X, y, N=500)
@@ -337,9 +340,10 @@ def test_kron_cuda_graph_replay_matches_eager(name, kw, B, shape):
             ent = list(graphed._graphs.values())
             assert len(ent) == 1 and ent[0]["graph"] not in (None, False), "the step was not captured"
             with torch.no_grad():                      # an optimiser step between two fits
-                for p in model.parameters():
-                    if p.requires_grad:
-                        p.mul_(1.01)
+                for mm in (model, model_e):
+                    for p in mm.parameters():
+                        if p.requires_grad:
+                            p.mul_(1.01)
             le, ke = eager.kron(Xs[0], ys[0], N=500)
             lg, kg = graphed.kron(Xs[0], ys[0], N=500)
             assert len(graphed._graphs) == 2            # new parameter versions -> new key (eager again, then re-captured)
