@@ -37,7 +37,7 @@ KIND_FWD = K.F16X3    # forward pass: activations / weights sit inside fp16 rang
 # > 0: backward-data convolutions over at least this many gradient rows use the bf16 hi half of the gradient alone
 # against the exact (hi + lo) weights -- two tensor-core products instead of three.  OFF by default: each gradient element
 # then carries ~2e-3 of relative noise (the 2^-9 rounding of the rows does not average out inside one dot product), which
-# costs 1.1e-4 .. 1.8e-4 rel-fro on the KFAC B factors at batch 64 .. 256 (tools/gpu_lean_diag.py).  Kept as a measured
+# costs 1.1e-4 .. 1.8e-4 rel-fro on the KFAC B factors at batch 64 .. 256 (tests/diagnostics/gpu_lean_diag.py).  Kept as a measured
 # option (backend.LEAN_BACKWARD_MIN_ROWS) for batches where rows / d_out >= ~2e5.
 LEAN_BWD_MIN_ROWS = 0
 FUSE_POOL = os.environ.get("LPB_NO_POOL_FUSION") != "1"   # max-pool reverse map fused with the stem chain's operand split

@@ -4,7 +4,7 @@ import os, sys, time
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from laplace_b200 import B200GGN, kernels as K, models  # noqa: E402
 from oracle import curvature_oracle as co  # noqa: E402  (tools/ is test infrastructure)
 

@@ -3,7 +3,7 @@ import os, sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from laplace_b200 import B200GGN, backend as bk, conv_engine, models  # noqa: E402
 from oracle import curvature_oracle as co  # noqa: E402
 

@@ -5,7 +5,7 @@ import os, sys
 import torch
 from torch.utils.data import DataLoader, TensorDataset
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from laplace_b200 import B200GGN, matrix, models  # noqa: E402
 from laplace_b200.posterior import B200Laplace  # noqa: E402
 from oracle import curvature_oracle as co  # noqa: E402
