@@ -63,3 +63,49 @@ def test_sharded_fit_equals_single_process(tmp_path, cpu_kernels):
         assert torch.allclose(res[hs][1], torch.as_tensor(la.loss), rtol=1e-5)
         if hs == "kron":
             assert torch.allclose(res["kron_rec"], H, rtol=1e-4, atol=1e-6)
+
+
+def _worker_edge(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from laplace_b200.distributed import ShardedLoader, check_same_order, fit_distributed
+    from laplace_b200.posterior import B200Laplace
+    from tests import cpu_kernels as ck
+
+    ck.install(_Patch())
+    torch.manual_seed(711)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    X, y = torch.randn(4, 6), torch.randint(2, (4,))
+    res = {}
+    # ONE batch for two ranks: rank 1's shard is empty and must contribute zeros instead of hanging the all-reduce
+    la = fit_distributed(B200Laplace(model, "classification", "all", "kron"), DataLoader(TensorDataset(X, y), batch_size=4))
+    res["H"] = la.H_facs.to_matrix().clone()
+    # ranks that iterate DIFFERENT batch sequences (unsynchronised shuffle) are detected
+    g = torch.Generator().manual_seed(rank)
+    Xs = torch.randn(16, 6)
+    shuffled = DataLoader(TensorDataset(Xs, torch.zeros(16, dtype=torch.long)), batch_size=4, shuffle=True, generator=g)
+    sh = ShardedLoader(shuffled, rank, world)
+    for _ in sh:
+        pass
+    try:
+        check_same_order(sh, "cpu")
+        res["order"] = "not detected"
+    except RuntimeError as e:
+        res["order"] = str(e)
+    if rank == 0:
+        torch.save(res, out_path)
+    dist.destroy_process_group()
+
+
+def test_empty_shard_and_unsynchronised_shuffle(tmp_path, cpu_kernels):
+    out = str(tmp_path / "edge.pt")
+    mp.spawn(_worker_edge, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    from laplace_b200.posterior import B200Laplace
+
+    torch.manual_seed(711)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    X, y = torch.randn(4, 6), torch.randint(2, (4,))
+    la = B200Laplace(model, "classification", "all", "kron").fit(DataLoader(TensorDataset(X, y), batch_size=4))
+    assert torch.allclose(res["H"], la.H_facs.to_matrix(), rtol=1e-5, atol=1e-7)
+    assert "different batch sequence" in res["order"]
