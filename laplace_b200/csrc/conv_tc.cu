@@ -201,17 +201,23 @@ conv_nhwc_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmX_hi, const
         // small images: a tile is q_per_tile whole images; large images: rows_per_tile image rows of one image
         int q0 = tm * q_per_tile, h0 = 0;
         if (tiles_per_img > 0) { q0 = tm / tiles_per_img; h0 = (tm - q0 * tiles_per_img) * rows_per_tile; }
+        // (tap, channel chunk) stepped, not divided out of `it`: the producer thread's per-iteration arithmetic is on the
+        // critical path of the ring (cf. the implicit-patch SYRK loader, gemm_tc3.cu)
+        int ti = 0, kc = 0;
+        int ch = h0 + taps.dh[0], cw = taps.dw[0], wrow = taps.w[0] * N + tn * bn;
         for (int it = 0; it < total; ++it) {
-          const int ti = it / kchunks, kc = it - ti * kchunks;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          const int ch = h0 + taps.dh[ti], cw = taps.dw[ti], wrow = taps.w[ti] * N + tn * bn;
           tma_load_4d(&tmX_hi, &full_bar[stage], st, kc * BK, cw, ch, q0);
           tma_load_2d(&tmW_hi, &full_bar[stage], st + OFF_B_HI, kc * BK, wrow);
           if (NPROD == 3) tma_load_4d(&tmX_lo, &full_bar[stage], st + OFF_A_LO, kc * BK, cw, ch, q0);
           if (NPROD >= 2) tma_load_2d(&tmW_lo, &full_bar[stage], st + OFF_B_LO, kc * BK, wrow);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          if (++kc == kchunks) {
+            kc = 0;
+            if (++ti < taps.n) { ch = h0 + taps.dh[ti]; cw = taps.dw[ti]; wrow = taps.w[ti] * N + tn * bn; }
+          }
         }
       }
     }
