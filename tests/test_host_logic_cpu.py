@@ -422,3 +422,33 @@ def test_fused_pool_conflict_falls_back(cpu_kernels, monkeypatch):
     net.float()
     worst = max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo))
     assert worst < 1e-5, worst
+
+
+def test_token_shared_linear_lazy_predictive_and_gp(cpu_kernels):
+    """A transformer's ``nn.Linear`` applied to every token is a weight shared over ``T`` positions, the same structure as a
+    convolution (curvlinops KFAC-expand): its ``LazyJacobian`` blocks are ``("conv", G_rows, A_rows, T)``, the Kron
+    predictive and the GP kernels run on them without the dense Jacobian and agree with the dense route and the oracle."""
+    from laplace_b200 import gp, models
+    from laplace_b200.posterior import B200Laplace
+    from laplace_b200.predictive import LazyJacobian
+    from torch.utils.data import DataLoader, TensorDataset
+
+    model = models.make("vit_b16", image=16, patch=8, dim=16, depth=1, heads=2, mlp_dim=32)
+    torch.manual_seed(0)
+    X, y = torch.randn(6, 3, 16, 16), torch.randint(10, (6,))
+    la = B200Laplace(model, "classification", "all", "kron", prior_precision=0.5).fit(DataLoader(TensorDataset(X, y), batch_size=3))
+    Jd, _ = la.backend.jacobians(X[:3])
+    dense_var = la.functional_variance(Jd)
+    la.backend.lazy_jacobians = True
+    Jl, _ = la.backend.jacobians(X[:3])
+    assert isinstance(Jl, LazyJacobian)
+    kinds = [b[0] for b in Jl._lpb_factors.blocks]
+    assert kinds.count("conv") >= 4 and "outer" in kinds          # per-token linears / the classification head
+    assert torch.allclose(la.functional_variance(Jl), dense_var, rtol=1e-4, atol=1e-7)
+    assert Jl._lpb_dense is None
+    Jo, _ = co.jacobians(model.double(), X[:3].double())
+    model.float()
+    flat = Jo.reshape(-1, Jo.shape[-1])
+    assert rel_fro(gp.kernel_batch(Jl), flat @ flat.t()) < 1e-5
+    assert rel_fro(gp.kernel_star(Jl), torch.einsum("bcp,bep->bce", Jo, Jo)) < 1e-5
+    assert rel_fro(Jl.dense().double(), Jo) < 1e-5
