@@ -19,6 +19,7 @@ on its own.
 from __future__ import annotations
 
 import math
+from collections.abc import MutableMapping
 
 import torch
 
@@ -34,10 +35,11 @@ def _predict(la, Js, f_mu, likelihood: str):
 @torch.no_grad()
 def gridsearch_prior_precision(la, val_loader, interval: torch.Tensor | None = None, log_prior_prec_min: float = -4,
                                log_prior_prec_max: float = 4, grid_size: int = 100, running_metric: bool = False,
-                               set_result: bool = True):
+                               set_result: bool = True, dict_key_y: str = "labels"):
     """Returns ``(best_prior_precision, losses [grid_size])``; NLL for classification (probit GLM predictive), summed MSE
     of the predictive mean for regression (the reference's default metrics).  Sets ``la.prior_precision`` to the winner
-    unless ``set_result=False``."""
+    unless ``set_result=False``.  Mapping batches (Hugging Face style) are passed to the model whole and their targets
+    read from ``dict_key_y``, as ``utils.validate`` does (utils/utils.py:60-65)."""
     likelihood = str(getattr(la.likelihood, "value", la.likelihood))
     if likelihood == "reward_modeling":
         likelihood = "classification"
@@ -48,8 +50,12 @@ def gridsearch_prior_precision(la, val_loader, interval: torch.Tensor | None = N
     batches = []
     la.model.eval()
     for data in val_loader:
-        X, y = data
-        X, y = X.to(dev), y.to(dev)
+        if isinstance(data, MutableMapping):
+            X, y = data, data[dict_key_y]
+        else:
+            X, y = data
+            X = X.to(dev)
+        y = y.to(dev)
         with torch.enable_grad():
             Js, f_mu = la.backend.last_layer_jacobians(X) if last_layer else la.backend.jacobians(X)
         fac = getattr(Js, "_lpb_factors", None)

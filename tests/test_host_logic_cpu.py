@@ -452,3 +452,54 @@ def test_token_shared_linear_lazy_predictive_and_gp(cpu_kernels):
     assert rel_fro(gp.kernel_batch(Jl), flat @ flat.t()) < 1e-5
     assert rel_fro(gp.kernel_star(Jl), torch.einsum("bcp,bep->bce", Jo, Jo)) < 1e-5
     assert rel_fro(Jl.dense().double(), Jo) < 1e-5
+
+
+@pytest.mark.parametrize("structure", ["kron", "full", "diag"])
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_gridsearch_structures_likelihoods_and_mapping_batches(golden, cpu_kernels, structure, lik):
+    """``tuning.gridsearch_prior_precision`` on the stand-alone posterior for every structure and both likelihoods: same
+    loss curve as a loop that re-derives Jacobians and variances for every grid value (what ``utils.validate`` does,
+    utils/utils.py:39-101), tuple batches and mapping batches (targets under ``dict_key_y``) alike."""
+    import math
+
+    from laplace_b200.posterior import B200Laplace
+    from laplace_b200.tuning import gridsearch_prior_precision
+    from torch.utils.data import DataLoader, TensorDataset
+
+    model, X, y, _ = load(golden, "mlp", lik, dtype=torch.float32)
+    la = B200Laplace(model, lik, "all", structure).fit(DataLoader(TensorDataset(X, y), batch_size=5))
+    vl = [(X[:6], y[:6]), (X[6:], y[6:])]
+    grid = torch.logspace(-2, 2, 7)
+    best, losses = gridsearch_prior_precision(la, vl, interval=grid, set_result=False)
+    brute = []
+    for pp in grid:
+        la.prior_precision = pp
+        tot = 0.0
+        for Xb, yb in vl:
+            Js, f = la.backend.jacobians(Xb)
+            var = la.functional_variance(Js)
+            if lik == "regression":
+                tot += float(((f - yb) ** 2).sum())
+            else:
+                kappa = 1.0 / torch.sqrt(1.0 + math.pi / 8.0 * torch.diagonal(var, dim1=1, dim2=2))
+                tot += float(torch.nn.functional.nll_loss(torch.softmax(kappa * f, -1).log(), yb, reduction="sum"))
+        brute.append(tot / len(X))
+    assert torch.allclose(losses, torch.tensor(brute, dtype=torch.float64), rtol=1e-5, atol=1e-7)
+    assert float(best) == float(grid[int(torch.tensor(brute).argmin())])
+
+    class DictModel(torch.nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+
+        def forward(self, batch):
+            return self.net(batch["input_ids"])
+
+    la_d = B200Laplace(DictModel(model), lik, "all", structure)
+
+    class Batches(list):
+        dataset = range(len(X))
+
+    la_d.fit(Batches({"input_ids": X[i:i + 5], "labels": y[i:i + 5]} for i in (0, 5)))
+    _, losses_d = gridsearch_prior_precision(la_d, [{"input_ids": Xb, "labels": yb} for Xb, yb in vl], interval=grid)
+    assert torch.allclose(losses_d, losses, rtol=1e-5, atol=1e-7)
