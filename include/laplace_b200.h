@@ -42,6 +42,10 @@ int lpb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * 1 256 x 256 CTA-pair tiles (tcgen05 cta_group::2) whenever M, N >= 256, 2 persistent CTAs with double-buffered
  * TMEM accumulators.  Results agree to fp32 rounding. */
 int lpb_set_gemm_tile_mode(int mode);
+/* lpb_pack_cast_fused / lpb_relu_bwd read their ReLU mask y once per mask element and walk the gradient rows that share
+ * it ("mask-major") when the mask has at least this many elements (default 4 Mi: larger masks do not survive in L2 between
+ * the folded curvature columns); smaller masks keep the row-major kernels.  < 0: always row-major.  Bit-identical results. */
+int lpb_set_mask_major_min(int64_t min_mask_elems);
 
 /* ---- pack: layer inputs / output gradients -> K-major staging ----------------------------
  * Front end of the KFAC factor contractions that curvlinops performs as einsum("b i,b j->i j")

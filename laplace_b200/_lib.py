@@ -18,6 +18,7 @@ c_i64, c_int, c_f32, c_vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 SIGNATURES = {
     "lpb_device_info": [C.POINTER(c_int)] * 3,
     "lpb_set_gemm_tile_mode": [c_int],
+    "lpb_set_mask_major_min": [c_i64],
     "lpb_pack_rows_t": [c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_f32, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
     "lpb_pack_conv2d_t": [c_vp] + [c_int] * 12 + [c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],
     "lpb_pack_nchw_t": [c_vp, c_i64, c_int, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_int, c_i64, c_i64, c_vp],

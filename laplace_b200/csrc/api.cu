@@ -43,6 +43,7 @@ int gemm_nt_bf16(const void*, const void*, int64_t, const void*, const void*, in
                  int, float*, int64_t, int, int, cudaStream_t);
 int scale_channels(const float*, const float*, float*, int64_t, int, int64_t, cudaStream_t);
 int relu_bwd(const float*, const float*, float*, int64_t, int, cudaStream_t);
+void set_mask_major_min(int64_t);
 int maxpool2d_bwd(const float*, const int64_t*, float*, int64_t, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int maxpool2d_bwd_pack_nhwc(const float*, const int64_t*, const float*, const float*, void*, void*, int64_t, int64_t, int, int, int,
                             int, int, int, int, int, int, cudaStream_t);
@@ -90,6 +91,11 @@ const char* lpb_last_error(void) { return lpb::get_error(); }
 
 int lpb_set_gemm_tile_mode(int mode) {
   lpb::set_gemm_pair_mode(mode);
+  return 0;
+}
+
+int lpb_set_mask_major_min(int64_t min_mask_elems) {
+  lpb::set_mask_major_min(min_mask_elems);
   return 0;
 }
 

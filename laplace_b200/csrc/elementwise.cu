@@ -65,11 +65,34 @@ __global__ void __launch_bounds__(256) relu_bwd_scalar_kernel(const float* __res
     out[e] = y[e % n] > 0.f ? g[e] : 0.f;
 }
 
+// Mask-major variant (see pack_cast_fused_maskmajor_kernel, pack.cu): a thread keeps its 4 mask values and walks the reps
+// gradient blocks that share them, so a mask larger than L2 is read once instead of once per folded column.
+__global__ void __launch_bounds__(256) relu_bwd_maskmajor_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                                  float* __restrict__ out, int64_t n4, int reps) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(y) + e);
+#pragma unroll 4
+    for (int r = 0; r < reps; ++r) {
+      const float4 v = reinterpret_cast<const float4*>(g)[(int64_t)r * n4 + e];
+      reinterpret_cast<float4*>(out)[(int64_t)r * n4 + e] =
+          make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
+    }
+  }
+}
+
+int64_t mask_major_min();   // pack.cu
+
 int relu_bwd(const float* g, const float* y, float* out, int64_t n, int reps, cudaStream_t st) {
   if (n == 0 || reps == 0) return 0;
   const int64_t total = n * reps;
   const int blocks_cap = sm_count() * 16;
-  if (n % 4 == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)out % 16) == 0)
+  const bool vec = n % 4 == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)out % 16) == 0;
+  if (vec && reps > 1 && mask_major_min() >= 0 && n >= mask_major_min()) {
+    relu_bwd_maskmajor_kernel<<<(int)imin(ceil_div(n / 4, 256), sm_count() * 32), 256, 0, st>>>(g, y, out, n / 4, reps);
+    LPB_CHECK_LAUNCH("relu_bwd");
+    return 0;
+  }
+  if (vec)
     relu_bwd_kernel<<<(int)imin(ceil_div(total / 4, 256), blocks_cap), 256, 0, st>>>(g, y, out, n / 4, total / 4);
   else
     relu_bwd_scalar_kernel<<<(int)imin(ceil_div(total, 256), blocks_cap), 256, 0, st>>>(g, y, out, n, total);

@@ -445,6 +445,63 @@ __global__ void __launch_bounds__(256) pack_cast_fused_kernel(const float* __res
   }
 }
 
+// Same map, mask-major: one thread owns an 8-wide piece of a MASK row and walks the rows / rows_y gradient rows that share it
+// (the folded curvature columns), so y is read once instead of once per column.  The row-major kernel above streams the
+// columns one after the other; with a mask larger than a fraction of L2 (the stem of a ResNet-18 at B = 4096: 268 MB) every
+// column re-reads it from DRAM -- r02 ncu: 594 MB read / 362 MB written per launch, i.e. y cost 0.64 of the gradient's own
+// bytes instead of 0.1.  Arithmetic and rounding are those of the row-major kernel, element by element.
+template <int KIND>
+__global__ void __launch_bounds__(256) pack_cast_fused_maskmajor_kernel(const float* __restrict__ src, int64_t rows_y, int64_t colsv,
+                                                                         int reps, int64_t ld_src, const float* __restrict__ scale,
+                                                                         const float* __restrict__ y, int64_t ld_y, void* hi, void* lo,
+                                                                         int64_t ld) {
+  const int64_t total = rows_y * colsv;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ry = e / colsv, c = (e - ry * colsv) * 8;
+    float mul[8];
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(y + ry * ld_y + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(y + ry * ld_y + c + 4));
+      const float m[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mul[i] = m[i] > 0.f ? 1.f : 0.f;
+    }
+    float sc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = scale ? __ldg(scale + c + i) : 1.f;
+#pragma unroll 4
+    for (int rep = 0; rep < reps; ++rep) {
+      const int64_t r = (int64_t)rep * rows_y + ry;
+      const float4 a = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+      const float4 b = *reinterpret_cast<const float4*>(src + r * ld_src + c + 4);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      alignas(16) unsigned short h[8], l[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (scale) v[i] *= sc[i];                      // same operation order as the row-major kernel: scale, then mask
+        v[i] = mul[i] != 0.f ? v[i] : 0.f;
+        if constexpr (KIND == OUT_F16_HILO) {
+          const __half hh = __float2half_rn(v[i]);
+          h[i] = __half_as_ushort(hh);
+          l[i] = __half_as_ushort(__float2half_rn(v[i] - __half2float(hh)));
+        } else {
+          const __nv_bfloat16 hh = __float2bfloat16_rn(v[i]);
+          h[i] = __bfloat16_as_ushort(hh);
+          l[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v[i] - __bfloat162float(hh)));
+        }
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(hi) + r * ld + c) = *reinterpret_cast<const uint4*>(h);
+      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(lo) + r * ld + c) = *reinterpret_cast<const uint4*>(l);
+    }
+  }
+}
+
+// Mask size (elements) from which the mask-major kernels take over: below it the mask survives in L2 between the columns
+// (a pass streams 3x its size past it) and the row-major kernels expose more parallelism.  <0: never (tests, A/B timing).
+static int64_t g_mask_major_min = 4 << 20;
+void set_mask_major_min(int64_t n) { g_mask_major_min = n; }
+int64_t mask_major_min() { return g_mask_major_min; }
+
 int pack_cast_fused(const float* src, int64_t rows, int64_t cols, int64_t ld_src, const float* scale, const float* y,
                     int64_t rows_y, int64_t ld_y, void* hi, void* lo, int kind, int64_t ld, cudaStream_t st) {
   if (rows == 0 || cols == 0) return 0;
@@ -455,7 +512,15 @@ int pack_cast_fused(const float* src, int64_t rows, int64_t cols, int64_t ld_src
   const bool vec = (kind == OUT_BF16_HILO || kind == OUT_F16_HILO) && cols % 8 == 0 && ld_src % 4 == 0 && ld % 8 == 0 &&
                    ((uintptr_t)src % 16) == 0 && ((uintptr_t)hi % 16) == 0 && ((uintptr_t)lo % 16) == 0 &&
                    (y == nullptr || (ld_y % 4 == 0 && ((uintptr_t)y % 16) == 0));
-  if (vec) {
+  if (vec && y != nullptr && rows / rows_y > 1 && g_mask_major_min >= 0 && rows_y * cols >= g_mask_major_min) {
+    const int64_t total = rows_y * (cols / 8);
+    const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
+    const int reps = (int)(rows / rows_y);
+    if (kind == OUT_F16_HILO)
+      pack_cast_fused_maskmajor_kernel<OUT_F16_HILO><<<blocks, 256, 0, st>>>(src, rows_y, cols / 8, reps, ld_src, scale, y, ld_y, hi, lo, ld);
+    else
+      pack_cast_fused_maskmajor_kernel<OUT_BF16_HILO><<<blocks, 256, 0, st>>>(src, rows_y, cols / 8, reps, ld_src, scale, y, ld_y, hi, lo, ld);
+  } else if (vec) {
     const int64_t total = rows * (cols / 8);
     const int blocks = (int)imin(ceil_div(total, 256), (int64_t)sm_count() * 32);
     if (kind == OUT_F16_HILO)

@@ -91,6 +91,12 @@ def set_gemm_tile_mode(mode: int) -> None:
     _lib.call("lpb_set_gemm_tile_mode", int(mode))
 
 
+def set_mask_major_min(min_mask_elems: int) -> None:
+    """Mask size from which ``pack_cast_fused`` / ``relu_bwd`` switch to their mask-major kernels (``lpb_set_mask_major_min``;
+    default 4 Mi elements, negative: never).  Same results bit for bit; for tests and A/B timing."""
+    _lib.call("lpb_set_mask_major_min", int(min_mask_elems))
+
+
 # ------------------------------------------------------------------------------ pack
 def pack_rows(src: torch.Tensor, kind: int, out: Packed | None = None, k0: int = 0, scale: float = 1.0,
               square: bool = False, row_scale: torch.Tensor | None = None, nrep: int = 1, total_K: int | None = None) -> Packed:

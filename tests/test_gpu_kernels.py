@@ -402,6 +402,41 @@ def test_pack_cast_fused(shape, kind, tol):
         assert err <= tol, (err, sc is None, yy is None)
 
 
+@pytest.mark.parametrize("rows_y,cols,reps", [(96, 64, 10), (1000, 24, 3), (33, 512, 7), (1 << 14, 256, 3)])
+def test_mask_major_kernels_bit_identical(rows_y, cols, reps):
+    """``pack_cast_fused`` / ``relu_bwd`` with the mask read once per element (mask-major: what runs for masks >= 4 Mi elements,
+    the last shape here by default) against the row-major kernels: the same bits, and both equal to the separate maps."""
+    torch.manual_seed(rows_y + reps)
+    g = torch.randn(reps * rows_y, cols, device=DEV)
+    y = torch.randn(rows_y, cols, device=DEV).clamp_min(0)
+    scale = torch.rand(cols, device=DEV) + 0.5
+    want = (g.view(reps, rows_y, cols) * scale * (y > 0)).view(-1, cols)
+    try:
+        if rows_y * cols < (4 << 20):
+            K.set_mask_major_min(0)
+        outs = {}
+        for mode in ("mask-major", "row-major"):
+            if mode == "row-major":
+                K.set_mask_major_min(-1)
+            for kind in (K.BF16X3, K.F16X3):
+                for sc in (scale, None):
+                    p = K.pack_cast_fused(g, kind, sc, y)
+                    outs[mode, kind, sc is None] = (p.hi[:, :cols].clone(), p.lo[:, :cols].clone())
+            outs[mode, "relu"] = K.relu_bwd(g, y, reps)
+        for key, val in outs.items():
+            if key[0] != "mask-major":
+                continue
+            other = outs[("row-major",) + key[1:]]
+            if key[1] == "relu":
+                assert torch.equal(val, other) and torch.equal(val, (g.view(reps, rows_y, cols) * (y > 0)).view(-1, cols))
+            else:
+                assert torch.equal(val[0], other[0]) and torch.equal(val[1], other[1]), key
+        hi, lo = outs["mask-major", K.F16X3, False]
+        assert float((hi.float() + lo.float() - want).norm() / want.norm()) < 5e-7
+    finally:
+        K.set_mask_major_min(4 << 20)
+
+
 def test_layer_level_kfac_entry_points():
     """``lpb_kfac_accum_rows`` / ``lpb_kfac_accum_conv_input`` (SURVEY 8(b) plan-level surface): fp32 tensors in, one call per
     Kronecker factor, against fp64."""
