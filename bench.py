@@ -333,6 +333,18 @@ def run_ours(args):
     ms_e2e, _ = timed(e2e_steps)
     e2e_value = world * Ksteps * B / (ms_e2e / 1e3)
     h2d = Xh[0].numel() * 4 + yh[0].numel() * 8
+    # what this box's host link delivers for exactly these copies (the e2e leg is copy-bound when a step's input takes longer
+    # to arrive than to process: 50 MB per 20 ms step needs 2.5 GB/s)
+    xdst = torch.empty_like(Xs[0])
+
+    def h2d_copies():
+        for j in range(8):
+            xdst.copy_(Xh[j % n_batches], non_blocking=True)
+
+    h2d_copies()
+    ms_h2d, _ = timed(h2d_copies)
+    h2d_gbps = 8 * Xh[0].numel() * 4 / (ms_h2d / 1e3) / 1e9
+    del xdst
 
     # ---------------- once-per-fit eigendecomposition (inside KronLaplace.fit, baselaplace.py:1809), sharded over ranks ----
     def decompose_once():
@@ -402,7 +414,8 @@ def run_ours(args):
                        "exchange": exchange, "e2e_api": api, **extras},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / Ksteps, "loss": state.get("loss")},
+                    "ms_per_step": ms_e2e / Ksteps, "loss": state.get("loss"),
+                    "h2d_GBps_measured": round(h2d_gbps, 1)},
             "gpu_launches": launches,
             "roofline": roof,
             "predictive": pred or None,
