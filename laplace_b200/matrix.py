@@ -791,7 +791,7 @@ class B200KronDecomposed(KronDecomposed):
         blocks = []
         for Qs, ls, delta in zip(self.eigenvectors, self.eigenvalues, self._delta_list()):
             spec = torch.pow(self._spectrum(ls, delta), exponent).reshape(-1)
-            Q = Qs[0] if len(ls) == 1 else torch.kron(Qs[0], Qs[1])
+            Q = Qs[0] if len(ls) == 1 else torch.kron(Qs[0].contiguous(), Qs[1].contiguous())   # kron() views its inputs
             blocks.append((Q * spec) @ Q.T)
         return torch.block_diag(*blocks)
 
