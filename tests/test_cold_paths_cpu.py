@@ -132,3 +132,106 @@ def test_prefetch_loader_host_path_and_structure():
 
     enc = Encoding(input_ids=X[:2])
     assert PrefetchLoader(Batches([enc]), "cpu")._move(enc) is enc and Encoding.moved == torch.device("cpu")
+
+
+@pytest.mark.parametrize("kind", ["mlp", "conv"])
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_subnetwork_indices_select_columns_everywhere(golden, cpu_kernels, kind, lik):
+    """``subnetwork_indices`` (curvature/curvature.py:76-86, 125-127): Jacobians, gradients, full and diagonal GGN / EF are
+    those of the selected parameter columns -- against the fp64 oracle's dense quantities restricted to the same columns."""
+    from laplace_b200 import B200EF, B200GGN
+    from oracle import curvature_oracle as co
+
+    model, X, y, rec = load(golden, kind, lik, dtype=torch.float32)
+    P = sum(p.numel() for p in model.parameters())
+    idx = torch.randperm(P, generator=torch.Generator().manual_seed(1))[: P // 3].sort().values
+    md = load(golden, kind, lik)[0]
+    Jo, fo = co.jacobians(md, X.double())
+    yd = y if lik == "classification" else y.double()
+    Js_sub = Jo[:, :, idx]
+    ggn = B200GGN(model, lik, subnetwork_indices=idx)
+    Js, f = ggn.jacobians(X)
+    assert Js.shape == (len(X), fo.shape[1], len(idx)) and rel_fro(Js, Js_sub) < 1e-5
+    Gs, loss = ggn.gradients(X, y)
+    Go, lo = co.gradients(Jo, fo, yd, lik)
+    assert rel_fro(Gs, Go[:, idx]) < 1e-5 and torch.allclose(loss.double(), lo, rtol=1e-5)
+    _, H = ggn.full(X, y)
+    _, Ho = co.ggn_full(Js_sub, fo, yd, lik)
+    assert rel_fro(H, Ho) < 1e-5
+    _, d = ggn.diag(X, y)
+    _, do = co.ggn_diag(Js_sub, fo, yd, lik)
+    assert rel_fro(d, do) < 1e-5
+    ef = B200EF(model, lik, subnetwork_indices=idx)
+    _, He = ef.full(X, y)
+    _, Heo = co.ef_full(Js_sub, fo, yd, lik)
+    assert rel_fro(He, Heo) < 1e-5
+    _, de = ef.diag(X, y)
+    _, deo = co.ef_diag(Js_sub, fo, yd, lik)
+    assert rel_fro(de, deo) < 1e-5
+
+
+@needs_reference
+def test_enable_backprop_delegates_to_the_reference_path(golden, cpu_kernels):
+    """``enable_backprop=True`` (curvature/curvature.py:88-129): the Jacobians must stay attached to the autograd graph of the
+    input; the kernels are not differentiable, so both Jacobian entry points hand over to the reference's torch.func code."""
+    from laplace_b200 import B200GGN
+
+    model, X, y, rec = load(golden, "mlp", "classification", dtype=torch.float32)
+    be = B200GGN(model, "classification")
+    Xg = X.clone().requires_grad_(True)
+    Js, f = be.jacobians(Xg, enable_backprop=True)
+    assert Js.requires_grad and rel_fro(Js.detach(), rec["Js"]) < 1e-5
+    (g,) = torch.autograd.grad(Js.square().sum(), Xg)
+    assert g.shape == X.shape and torch.isfinite(g).all() and float(g.abs().max()) > 0
+    Js_plain, _ = be.jacobians(X)
+    assert not Js_plain.requires_grad and torch.allclose(Js_plain, Js.detach(), atol=1e-6)
+
+
+def test_unsupported_layer_configurations_raise(cpu_kernels):
+    from laplace_b200 import B200GGN
+
+    X, y = torch.randn(2, 4, 6, 6), torch.randint(3, (2,))
+    for conv in (torch.nn.Conv2d(4, 4, 3, groups=2), torch.nn.Conv2d(4, 4, 3, padding="same"),
+                 torch.nn.Conv2d(4, 4, 3, padding=1, padding_mode="reflect")):
+        net = torch.nn.Sequential(conv, torch.nn.Flatten(), torch.nn.LazyLinear(3))
+        net(X)
+        with pytest.raises(ValueError, match="not supported|only zero padding"):
+            B200GGN(net, "classification").kron(X, y, N=2)
+
+
+def test_ops_without_a_batching_rule_fall_back_to_one_pass_per_column(golden, cpu_kernels):
+    """A custom ``autograd.Function`` whose reverse pass cannot be vmapped (it reads a value on the host) between the layers: the column-batched reverse pass is not
+    available, ``last_backward_mode`` says so, and the per-column passes give the same factors / Jacobians as the oracle."""
+    from laplace_b200 import B200GGN
+    from oracle import curvature_oracle as co
+
+    class Cube(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            ctx.save_for_backward(x)
+            return x ** 3
+
+        @staticmethod
+        def backward(ctx, g):
+            (x,) = ctx.saved_tensors
+            keep = 1.0 if float(g.abs().sum()) >= 0 else 0.0        # a host read: legal in eager mode, impossible under vmap
+            return 3 * x ** 2 * g * keep
+
+    class Act(torch.nn.Module):
+        def forward(self, x):
+            return Cube.apply(x)
+
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), Act(), torch.nn.Linear(6, 3))
+    X, y = torch.randn(7, 4), torch.randint(3, (7,))
+    be = B200GGN(net, "classification")
+    _, kron = be.kron(X, y, N=7)
+    assert be.last_backward_mode.startswith("loop"), be.last_backward_mode
+    _, kf = co.kfac_factors(net.double(), "classification", X.double(), y, N=7)
+    Jo, _ = co.jacobians(net, X.double())
+    net.float()
+    assert max(rel_fro(H, Ho) for F, Fo in zip(kron.kfacs, kf) for H, Ho in zip(F, Fo)) < 1e-5
+    assert rel_fro(be.jacobians(X)[0], Jo) < 1e-5
+    # and the explicit switch gives the same
+    _, kron2 = B200GGN(net, "classification", batched_backward=False).kron(X, y, N=7)
+    assert max(rel_fro(H, Ho) for F, Fo in zip(kron2.kfacs, kf) for H, Ho in zip(F, Fo)) < 1e-5
