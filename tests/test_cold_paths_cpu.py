@@ -235,3 +235,52 @@ def test_ops_without_a_batching_rule_fall_back_to_one_pass_per_column(golden, cp
     # and the explicit switch gives the same
     _, kron2 = B200GGN(net, "classification", batched_backward=False).kron(X, y, N=7)
     assert max(rel_fro(H, Ho) for F, Fo in zip(kron2.kfacs, kf) for H, Ho in zip(F, Fo)) < 1e-5
+
+
+@pytest.mark.parametrize("lik", ["classification", "regression"])
+def test_standalone_driver_validation_logdets_and_empty_shard_layout(golden, cpu_kernels, lik):
+    """``B200Laplace`` (what runs when the reference package is not importable): argument validation like
+    ``BaseLaplace.__init__`` (baselaplace.py:100-140), ``log_det_posterior_precision`` of the three structures against the
+    dense matrix, the zero curvature of an empty shard laid out like a fitted one, ``__call__`` contract."""
+    from laplace_b200.posterior import B200Laplace
+
+    model, X, y, _ = load(golden, "conv", lik, dtype=torch.float32)
+    with pytest.raises(ValueError, match="likelihood"):
+        B200Laplace(model, "poisson")
+    with pytest.raises(ValueError, match="unsupported"):
+        B200Laplace(model, lik, "subnetwork", "full")
+    with pytest.raises(ValueError, match="unsupported"):
+        B200Laplace(model, lik, "all", "lowrank")
+    if lik == "classification":
+        with pytest.raises(ValueError, match="Sigma noise"):
+            B200Laplace(model, lik, sigma_noise=0.5)
+    loader = DataLoader(TensorDataset(X, y), batch_size=5)
+    las = {s: B200Laplace(model, lik, "all", s, prior_precision=0.6).fit(loader) for s in ("kron", "full", "diag")}
+    dense = {"kron": las["kron"].posterior_precision.to_matrix(), "full": las["full"].posterior_precision,
+             "diag": torch.diag(las["diag"].posterior_precision)}
+    for s, la in las.items():
+        assert torch.allclose(la.log_det_posterior_precision.double(), torch.logdet(dense[s].double()), rtol=1e-4), s
+        Z = la.zero_curvature()
+        H = la.H_facs if s == "kron" else la.H
+        if s == "kron":
+            assert Z.dims() == H.dims() and float(Z._flat.abs().sum()) == 0
+        else:
+            assert Z.shape == H.shape and float(Z.abs().sum()) == 0
+        out = la(X)
+        if lik == "classification":
+            assert out.shape == (len(X), 2) and torch.allclose(out.sum(-1), torch.ones(len(X)), atol=1e-5)
+            with pytest.raises(ValueError, match="probit"):
+                la(X, link_approx="mc")
+        else:
+            assert out[0].shape == (len(X), 2) and out[1].shape == (len(X), 2, 2)
+        with pytest.raises(ValueError, match="GLM"):
+            la(X, pred_type="nn")
+    # the bias blocks of fully connected layers are exact in KFAC (no weight sharing): equal to the full GGN's diagonal block
+    full, kron = las["full"].H, las["kron"].H_facs.to_matrix()
+    linear_biases = {id(m.bias) for m in model.modules() if isinstance(m, torch.nn.Linear)}
+    off = 0
+    for p in model.parameters():
+        n = p.numel()
+        if id(p) in linear_biases:
+            assert rel_fro(kron[off:off + n, off:off + n], full[off:off + n, off:off + n]) < 1e-4
+        off += n
