@@ -284,3 +284,70 @@ def test_standalone_driver_validation_logdets_and_empty_shard_layout(golden, cpu
         if id(p) in linear_biases:
             assert rel_fro(kron[off:off + n, off:off + n], full[off:off + n, off:off + n]) < 1e-4
         off += n
+
+
+def test_batched_mid_size_route_host_logic(monkeypatch):
+    """``_symeig_mid_batched`` (one ``cusolverDnXsyevBatched`` call per size class for live blocks <= 513 rows): grouping,
+    dead-coordinate compaction, the negative border that pads a block to its class, scatter of the results -- with the
+    library call replaced by ``torch.linalg.eigh`` -- and its three ways out (single-member class, per-matrix ``info != 0``,
+    library error), which must hand the factors back for the one-by-one route."""
+    from laplace_b200 import _cusolver
+    from laplace_b200 import matrix as mx
+
+    def fake_solver(batch):
+        W, Q = torch.linalg.eigh(batch.double())
+        return W.float(), Q.float(), torch.zeros(len(batch), dtype=torch.int32)
+
+    monkeypatch.setattr(_cusolver, "available", lambda: True)
+    monkeypatch.setattr(_cusolver, "syev_batched", fake_solver)
+    monkeypatch.setattr(mx, "BATCHED_MID_CLASSES", (16, 40))
+
+    def factor(n, live, seed):
+        g = torch.Generator().manual_seed(seed)
+        idx = torch.randperm(n, generator=g)[:live].sort().values
+        X = torch.randn(3 * live, live, generator=g)
+        H = torch.zeros(n, n)
+        H[idx.unsqueeze(1), idx.unsqueeze(0)] = X.t() @ X
+        return H
+
+    # (n, live): two in class 16 (one full, one compacted from 60 rows), three in class 40, one beyond every class, one
+    # alone in ... no class of its own (it joins class 40), one all-dead
+    specs = [(12, 12), (60, 9), (40, 40), (33, 33), (90, 20), (70, 70), (25, 0)]
+    Hs = [factor(n, lv, s) for s, (n, lv) in enumerate(specs)]
+    items = sorted([(i, 0, H) for i, H in enumerate(Hs)], key=lambda t: -t[2].shape[0])
+    live = [int((H.diagonal() != 0).sum()) for _, _, H in items]
+    eigvals = [[None] for _ in Hs]
+    eigvecs = [[None] for _ in Hs]
+    rest, rest_live = mx._symeig_mid_batched(items, live, eigvals, eigvecs)
+    assert sorted(it[0] for it in rest) == [5, 6] and len(rest_live) == 2          # 70 live rows: too large; 0 live rows: nothing to solve
+    for i, (n, lv) in enumerate(specs):
+        if i in (5, 6):
+            assert eigvals[i][0] is None
+            continue
+        L, W = eigvals[i][0], eigvecs[i][0]
+        assert L.shape == (n,) and W.shape == (n, n) and torch.all(L[1:] >= L[:-1]) and torch.all(L >= 0)
+        assert int((L == 0).sum()) >= n - lv
+        assert torch.allclose(W.t() @ W, torch.eye(n), atol=1e-4)
+        assert rel_fro(W @ torch.diag(L) @ W.t(), Hs[i]) < 1e-5
+    # a class with a single member is left to the one-by-one route
+    eigvals2, eigvecs2 = [[None]], [[None]]
+    rest, _ = mx._symeig_mid_batched([(0, 0, Hs[0])], [12], eigvals2, eigvecs2)
+    assert len(rest) == 1 and eigvals2[0][0] is None
+    # info != 0 for one matrix of a batch: that one is handed back, the other solved
+    monkeypatch.setattr(_cusolver, "syev_batched", lambda b: fake_solver(b)[:2] + (torch.tensor([0, 3], dtype=torch.int32),))
+    ev, evec = [[None], [None]], [[None], [None]]
+    rest, _ = mx._symeig_mid_batched([(0, 0, Hs[2]), (1, 0, Hs[3])], None, ev, evec)
+    assert [it[0] for it in rest] == [1] and ev[0][0] is not None and ev[1][0] is None
+    # the library raising: a warning, everything handed back
+    def broken(batch):
+        raise RuntimeError("no such entry point")
+
+    monkeypatch.setattr(_cusolver, "syev_batched", broken)
+    ev, evec = [[None], [None]], [[None], [None]]
+    with pytest.warns(UserWarning, match="batched eigensolver unavailable"):
+        rest, _ = mx._symeig_mid_batched([(0, 0, Hs[2]), (1, 0, Hs[3])], None, ev, evec)
+    assert len(rest) == 2 and ev[0][0] is None
+    # solver absent altogether: untouched
+    monkeypatch.setattr(_cusolver, "available", lambda: False)
+    same, same_live = mx._symeig_mid_batched(items, live, eigvals, eigvecs)
+    assert same is items and same_live is live
