@@ -8,7 +8,21 @@ from torch.utils.data import DataLoader, TensorDataset
 from oracle import ref_shim
 from tests.fixtures import load, rel_fro
 
-needs_reference = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not mounted")
+
+
+def _reference_usable():
+    if not ref_shim.reference_available():
+        return False
+    try:
+        import laplace  # noqa: F401
+    except ImportError:
+        return False
+    from laplace_b200.interface import HAVE_REFERENCE
+
+    return HAVE_REFERENCE
+
+
+needs_reference = pytest.mark.skipif(not _reference_usable(), reason="reference package not importable (not mounted, or LPB_NO_REFERENCE=1)")
 
 
 def _spd(n, seed):
@@ -185,6 +199,17 @@ def test_enable_backprop_delegates_to_the_reference_path(golden, cpu_kernels):
     assert g.shape == X.shape and torch.isfinite(g).all() and float(g.abs().max()) > 0
     Js_plain, _ = be.jacobians(X)
     assert not Js_plain.requires_grad and torch.allclose(Js_plain, Js.detach(), atol=1e-6)
+
+
+@pytest.mark.skipif(_reference_usable(), reason="mirror mode only (LPB_NO_REFERENCE=1 / GPU box without baseline/_ref)")
+def test_enable_backprop_without_the_reference_says_why(golden, cpu_kernels):
+    from laplace_b200 import B200GGN
+
+    model, X, _, _ = load(golden, "mlp", "classification", dtype=torch.float32)
+    be = B200GGN(model, "classification")
+    for fn in (be.jacobians, be.last_layer_jacobians):
+        with pytest.raises(NotImplementedError, match="not differentiable"):
+            fn(X, enable_backprop=True)
 
 
 def test_unsupported_layer_configurations_raise(cpu_kernels):
