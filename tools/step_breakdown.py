@@ -27,7 +27,7 @@ def wrap(obj, name, label=None):
         rec[label or name].append((s, e)); return r
     setattr(obj, name, g)
 
-for n in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd", "syrk_conv_patches", "col2im_nhwc", "pack_cast_fused", "conv_bwd_strided", "diag_conv_sq"):
+for n in ("pack_rows", "pack_conv", "pack_nchw", "gemm_nt", "pack_conv_rows", "pack_nchw_rows", "pack_cast", "col2im", "conv_nhwc", "gemm_tn", "scale_channels", "relu_bwd", "maxpool2d_bwd", "syrk_conv_patches", "col2im_nhwc", "pack_cast_fused", "conv_bwd_strided", "diag_conv_sq", "maxpool2d_bwd_pack"):
     wrap(K, n)
 wrap(be, "_forward"); wrap(be, "_backward")
 for i in range(3):
