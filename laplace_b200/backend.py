@@ -971,12 +971,20 @@ class B200GGN(_B200Mixin, GGNInterface):
                               stochastic, num_samples)
         self._b200_init(precision, batched_backward, model_tf32, conv_engine, fuse_elementwise, cuda_graph)
 
-    def _ggn_cols(self, f, y=None):
-        return self._mc_cols(f, self.num_samples) if self.stochastic else self._hessian_sqrt_cols(f)
+    def _ggn_cols(self, f, y=None, mc_samples=None):
+        return self._mc_cols(f, mc_samples or self.num_samples) if self.stochastic else self._hessian_sqrt_cols(f)
 
-    def _functional_hessian(self, f):
+    def _cols_fn(self, kwargs):
+        """``mc_samples=S`` passed per call (as to ``CurvlinopsGGN.full`` / ``.kron``, curvlinops.py:92-98, 121) overrides the
+        constructor's ``num_samples`` for a stochastic backend."""
+        S = kwargs.get("mc_samples")
+        if not self.stochastic or S is None:
+            return self._ggn_cols
+        return lambda f, y=None: self._ggn_cols(f, y, int(S))
+
+    def _functional_hessian(self, f, mc_samples=None):
         if self.stochastic:
-            cols = self._mc_cols(f, self.num_samples)               # [S, M, C]
+            cols = self._mc_cols(f, mc_samples or self.num_samples)               # [S, M, C]
             return torch.einsum("smc,smk->mck", cols, cols)
         if self.likelihood == "regression":
             return torch.eye(f.shape[1], device=f.device, dtype=f.dtype).expand(f.shape[0], -1, -1)
@@ -1000,10 +1008,10 @@ class B200GGN(_B200Mixin, GGNInterface):
         if self.last_layer:
             f, phi = self._ll_forward(x)
             y = y.to(f.device)
-            H = self._ll_full(phi, self._functional_hessian(f), 1.0)
+            H = self._ll_full(phi, self._functional_hessian(f, kwargs.get("mc_samples")), 1.0)
             return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(H)
         y = y.to(next(self.model.parameters()).device)
-        Z, f, _ = self._rows(x, self._ggn_cols)
+        Z, f, _ = self._rows(x, self._cols_fn(kwargs))
         P = Z.shape[-1]
         Z2 = Z.reshape(-1, P)
         if self.subnetwork_indices is not None:
@@ -1016,10 +1024,10 @@ class B200GGN(_B200Mixin, GGNInterface):
         if self.last_layer:
             f, phi = self._ll_forward(x)
             y = y.to(f.device)
-            lam = torch.diagonal(self._functional_hessian(f), dim1=1, dim2=2).t()   # [C, M]
+            lam = torch.diagonal(self._functional_hessian(f, kwargs.get("mc_samples")), dim1=1, dim2=2).t()   # [C, M]
             return (self.factor * self.lossfunc(f, y)).detach(), self._out_dtype(self._ll_diag(phi, lam, 1.0))
         y = y.to(next(self.model.parameters()).device)
-        loss_f, d = self._diag_impl(x, self._ggn_cols, None, 1.0)
+        loss_f, d = self._diag_impl(x, self._cols_fn(kwargs), None, 1.0)
         if self.subnetwork_indices is not None:
             d = d[self.subnetwork_indices]
         return (self.factor * self.lossfunc(loss_f, y)).detach(), self._out_dtype(d)
