@@ -187,12 +187,15 @@ class B200Kron(Kron):
         return torch.block_diag(*blocks)
 
     def logdet(self) -> torch.Tensor:
+        def ld(H):   # diagonal factors are stored as vectors (utils/matrix.py:230-238)
+            return torch.logdet(H) if H.ndim > 1 else H.log().sum()
+
         total = 0
         for F in self.kfacs:
             if len(F) == 1:
-                total = total + torch.logdet(F[0])
+                total = total + ld(F[0])
             else:
-                total = total + F[1].shape[0] * torch.logdet(F[0]) + F[0].shape[0] * torch.logdet(F[1])
+                total = total + F[1].shape[0] * ld(F[0]) + F[0].shape[0] * ld(F[1])
         return total
 
 
