@@ -78,6 +78,42 @@ class _Fp32Model:
         return False
 
 
+def _inert_hook(mod, inp, out):
+    """What a pickled ``_CaptureHook`` comes back as: its backend did not travel with it (the unpickled backend registers its
+    own hooks)."""
+    return None
+
+
+class _CaptureHook:
+    """Forward hook of one Linear / Conv2d layer: records ``(input, output)`` while its backend runs a captured forward pass.
+    An object rather than a closure so that a model carrying it can be pickled (see ``_B200Mixin.__getstate__``)."""
+
+    def __init__(self, backend, name):
+        import weakref
+
+        self.ref = weakref.ref(backend)     # the module must not keep the backend (and its captured graphs / buffers) alive
+        self.name = name
+
+    def __call__(self, mod, inp, out):
+        be, name = self.ref(), self.name
+        if be is not None and be._capturing:
+            if name in be._outs:
+                # the reference's hook-based KFAC sums the contributions of every call; this backend captures one
+                # (input, output) pair per module, so say so instead of silently keeping the last call only
+                raise ValueError(f"B200 backend: module {name!r} is called more than once per forward pass (weight "
+                                 "sharing across calls); give every call its own module")
+            be._acts[name] = inp[0].detach()
+            be._outs[name] = out
+            be._out_state[name] = (out._version, out.grad_fn)
+
+    def __reduce__(self):
+        return (_inert_hook_factory, ())
+
+
+def _inert_hook_factory():
+    return _inert_hook
+
+
 class _B200Mixin:
     """Shared machinery of the GGN and EF flavours."""
 
@@ -151,22 +187,24 @@ class _B200Mixin:
             )
 
     def _make_hook(self, name):
-        import weakref
+        return _CaptureHook(self, name)
 
-        ref = weakref.ref(self)     # the module must not keep the backend (and its captured graphs / buffers) alive
+    # ``torch.save(la, path)`` (reference tests/test_serialization.py:295-336) pickles the posterior together with its backend
+    # and the model -- forward hooks included.  Streams, captured graphs, hook handles and captured tensors are per-process
+    # state: they are dropped here and rebuilt lazily (``_plan`` registers fresh hooks on the unpickled model).
+    _TRANSIENT = {"_graphs": dict, "_side": lambda: None, "_layers": lambda: None, "_hooks": list, "_acts": dict,
+                  "_outs": dict, "_out_state": dict, "_unsupported": list, "_jac_cache": lambda: None}
 
-        def hook(mod, inp, out):
-            self = ref()
-            if self is not None and self._capturing:
-                if name in self._outs:
-                    # the reference's hook-based KFAC sums the contributions of every call; this backend captures one
-                    # (input, output) pair per module, so say so instead of silently keeping the last call only
-                    raise ValueError(f"B200 backend: module {name!r} is called more than once per forward pass (weight "
-                                     "sharing across calls); give every call its own module")
-                self._acts[name] = inp[0].detach()
-                self._outs[name] = out
-                self._out_state[name] = (out._version, out.grad_fn)
-        return hook
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k, fresh in self._TRANSIENT.items():
+            if k in state:
+                state[k] = fresh()
+        state["_capturing"] = False
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
 
     def __del__(self):
         for h in getattr(self, "_hooks", ()):
