@@ -958,7 +958,7 @@ class _B200Mixin:
         M, D = phi.shape
         C = Lam.shape[1]
         has_bias = self.model.last_layer.bias is not None
-        phit = torch.cat([phi, torch.ones(M, 1, device=phi.device)], 1).contiguous() if has_bias else phi
+        phit = torch.cat([phi, torch.ones(M, 1, device=phi.device, dtype=phi.dtype)], 1).contiguous() if has_bias else phi
         Dt = phit.shape[1]
         iu = torch.triu_indices(C, C, device=phi.device)
         w = Lam[:, iu[0], iu[1]].t().contiguous().float()            # [npairs, M]
@@ -977,7 +977,7 @@ class _B200Mixin:
         """diag of the above: ``sum_n Lam_n[c,c] * [phi;1]^2`` -> ``[C*D (+C)]``."""
         has_bias = self.model.last_layer.bias is not None
         M = phi.shape[0]
-        phit = torch.cat([phi, torch.ones(M, 1, device=phi.device)], 1).contiguous() if has_bias else phi
+        phit = torch.cat([phi, torch.ones(M, 1, device=phi.device, dtype=phi.dtype)], 1).contiguous() if has_bias else phi
         lam_diag = lam_diag.float().contiguous()                       # [C, M] is already K-major
         A = K.Packed(lam_diag, None, K.F32, lam_diag.shape[0], lam_diag.shape[1])
         Bq = K.pack_rows(phit, K.F32, square=True)                     # [Dt, M]

@@ -423,13 +423,13 @@ def prewarm_eigensolver(device) -> None:
             torch.cuda.set_device(dev)
             with torch.cuda.stream(torch.cuda.Stream(dev)):
                 for n in (8, 300, 600):
-                    A = torch.eye(n, device=dev) + 0.01
+                    A = torch.eye(n, device=dev, dtype=torch.float32) + 0.01
                     torch.linalg.eigh(A, UPLO="U")
                 if BATCHED_MID_SIZES:
                     from . import _cusolver
 
                     if _cusolver.available():
-                        _cusolver.syev_batched((torch.eye(256, device=dev) + 0.01).expand(2, 256, 256).contiguous())
+                        _cusolver.syev_batched((torch.eye(256, device=dev, dtype=torch.float32) + 0.01).expand(2, 256, 256).contiguous())
                 torch.cuda.current_stream(dev).synchronize()
         except Exception:  # noqa: BLE001 -- a warm-up must never fail a fit
             pass

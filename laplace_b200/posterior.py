@@ -182,8 +182,8 @@ class B200Laplace:
                 dims.append([p.shape[0]] if p.ndim == 1 else [p.shape[0], int(p.numel() // p.shape[0])])
             return B200Kron.zeros(dims, dev, torch.float32)
         if self.structure == "full":
-            return torch.zeros(self.n_params, self.n_params, device=dev)
-        return torch.zeros(self.n_params, device=dev)
+            return torch.zeros(self.n_params, self.n_params, device=dev, dtype=self.params[0].dtype)
+        return torch.zeros(self.n_params, device=dev, dtype=self.params[0].dtype)
 
     # ------------------------------------------------------------------ posterior
     @property

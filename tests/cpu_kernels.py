@@ -97,7 +97,7 @@ def jac_linear_write(g, a, Js_view, stride_n, stride_c, off_w, off_b):
 def ll_jacobian_write(phi, C_out, has_bias):
     Nn, D = phi.shape
     P = C_out * D + (C_out if has_bias else 0)
-    Js = torch.zeros(Nn, C_out, P)
+    Js = torch.zeros(Nn, C_out, P, dtype=phi.dtype)
     for c in range(C_out):
         Js[:, c, c * D:(c + 1) * D] = phi
         if has_bias:
@@ -124,7 +124,7 @@ def ll_ggn_expand(G, C_out, D, has_bias, H, accumulate):
         return c * D + d if d < D else C_out * D + c
 
     P = C_out * D + (C_out if has_bias else 0)
-    out = torch.zeros(P, P)
+    out = torch.zeros(P, P, dtype=G.dtype)
     pair = 0
     for c in range(C_out):
         for k in range(c, C_out):
@@ -147,7 +147,7 @@ def ll_sigma_gather(Sigma, C_out, D, has_bias):
     def idx(c, d):
         return c * D + d if d < D else C_out * D + c
 
-    Sg = torch.zeros(C_out * C_out, Dt, Dt)
+    Sg = torch.zeros(C_out * C_out, Dt, Dt, dtype=Sigma.dtype)
     for c in range(C_out):
         for k in range(C_out):
             rows = torch.tensor([idx(c, d) for d in range(Dt)])
@@ -283,7 +283,7 @@ def conv_nhwc(X, Q, H, W, Wt, N, KH, KW, base_h, base_w, sgn, out, alpha=1.0):
     Kc = X.K
     x = X.hi[:, :Kc].reshape(Q, H, W, Kc)
     w = Wt.hi[:, :Kc].reshape(KH * KW, N, Kc)
-    res = torch.zeros(Q, H, W, N)
+    res = torch.zeros(Q, H, W, N, dtype=x.dtype)
     for kh in range(KH):
         for kw in range(KW):
             dh, dw = base_h + sgn * kh, base_w + sgn * kw
@@ -319,7 +319,7 @@ def maxpool2d_bwd(g, idx, in_shape, k, s, p):
     Q, C, OH, OW = g.shape
     H, W = in_shape[-2:]
     Nb = idx.shape[0]
-    out = torch.zeros(Q, C, H * W)
+    out = torch.zeros(Q, C, H * W, dtype=torch.float32)
     ii = idx.reshape(Nb, C, OH * OW).repeat(Q // Nb, 1, 1)
     out.scatter_add_(2, ii, g.reshape(Q, C, OH * OW).float())
     out = out.reshape(Q, C, H, W)
