@@ -376,3 +376,29 @@ def test_batched_mid_size_route_host_logic(monkeypatch):
     monkeypatch.setattr(_cusolver, "available", lambda: False)
     same, same_live = mx._symeig_mid_batched(items, live, eigvals, eigvecs)
     assert same is items and same_live is live
+
+
+def test_results_do_not_depend_on_the_process_default_dtype(golden, cpu_kernels):
+    """``torch.set_default_dtype(torch.float64)`` (what the reference's own test modules do at import time) must not change
+    what a float32 model gets back: last-layer full / diagonal curvature (the ones column of ``[phi; 1]``), the empty-shard
+    curvature of the stand-alone driver."""
+    from laplace_b200 import B200GGN
+    from laplace_b200.posterior import B200Laplace, LastLayerModel
+
+    model, X, y, _ = load(golden, "mlp", "classification", dtype=torch.float32)
+
+    def run():
+        be = B200GGN(LastLayerModel(model), "classification", last_layer=True)
+        return be.full(X, y)[1], be.diag(X, y)[1]
+
+    H32, d32 = run()
+    keep = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        H64, d64 = run()
+        la = B200Laplace(model, "classification", "all", "full")
+        Z = la.zero_curvature()
+    finally:
+        torch.set_default_dtype(keep)
+    assert H64.dtype == H32.dtype == torch.float32 and torch.equal(H64, H32) and torch.equal(d64, d32)
+    assert Z.dtype == torch.float32
